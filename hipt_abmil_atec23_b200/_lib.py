@@ -1,0 +1,154 @@
+"""ctypes binding of libhipt_b200.so (the C ABI declared in include/hipt_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.  Tensors cross the boundary as raw
+device pointers (`tensor.data_ptr()`) plus sizes; the CUDA stream is torch's current stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libhipt_b200.so")
+
+HB_EPI_BIAS_BF16 = 0
+HB_EPI_BIAS_GELU_BF16 = 1
+HB_EPI_BIAS_RESADD_F32 = 2
+HB_EPI_TOKENS_F32 = 3
+HB_EPI_TOKENS_GELU_F32 = 4
+
+
+class HbVitConfig(C.Structure):
+    _fields_ = [("dim", C.c_int), ("heads", C.c_int), ("depth", C.c_int), ("mlp_dim", C.c_int),
+                ("max_rows", C.c_int), ("ln_eps", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol of include/hipt_b200.h
+SIGNATURES = {
+    "hb_abi_version": (C.c_int, []),
+    "hb_last_error": (C.c_char_p, []),
+    "hb_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "hb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_int, C.c_void_p]),
+    "hb_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_int, C.c_void_p]),
+    "hb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "hb_im2col_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p]),
+    "hb_vit_workspace_bytes": (C.c_size_t, [C.POINTER(HbVitConfig)]),
+    "hb_vit_plan_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_void_p)]),
+    "hb_vit_plan_destroy": (None, [C.c_void_p]),
+    "hb_vit_plan_set_depth_limit": (C.c_int, [C.c_void_p, C.c_int]),
+    "hb_vit_plan_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "hb_vit256_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_vit4k_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_clam_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hb_clam_sb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m hipt_abmil_atec23_b200.build` "
+                "(there is no CPU or PyTorch fallback for this path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libhipt_b200: " + load().hb_last_error().decode("utf-8", "replace"))
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: this path has no CPU implementation")
+
+
+_device_checked = set()
+
+
+def device_check():
+    dev = torch.cuda.current_device()
+    if dev not in _device_checked:
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        check(load().hb_device_check(C.byref(sm), C.byref(ma), C.byref(mi)))
+        _device_checked.add(dev)
+
+
+# ------------------------------------------------------------------------------------------------ thin op wrappers
+def gemm_bf16(a, w, bias, epilogue, out=None, tok_table=None, tokens_per_seq=0):
+    """out = epilogue(a @ w.T + bias); a [M,K] bf16, w [N,K] bf16, bias [N] fp32."""
+    require_cuda(a, "a")
+    device_check()
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert a.is_contiguous() and w.is_contiguous() and w.shape[1] == K
+    if out is None:
+        if epilogue in (HB_EPI_BIAS_BF16, HB_EPI_BIAS_GELU_BF16):
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        else:
+            raise ValueError("an output tensor is required for this epilogue")
+    check(load().hb_gemm_bf16(ptr(a), ptr(w), ptr(bias), epilogue, ptr(out), M, N, K, ptr(tok_table), tokens_per_seq,
+                              stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma, beta, eps, rows, dim, row_stride=None, want_bf16=True, want_f32=False):
+    require_cuda(x, "x")
+    device_check()
+    assert x.dtype == torch.float32
+    ob = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    of = torch.empty((rows, dim), dtype=torch.float32, device=x.device) if want_f32 else None
+    check(load().hb_layernorm(ptr(x), row_stride if row_stride is not None else dim, ptr(gamma), ptr(beta), eps,
+                              ptr(ob), ptr(of), rows, dim, stream_ptr()))
+    return ob, of
+
+
+def attention(qkv, n_seq, seq_len, heads, head_dim, scale):
+    require_cuda(qkv, "qkv")
+    device_check()
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    out = torch.empty((n_seq * seq_len, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    check(load().hb_attention(ptr(qkv), ptr(out), n_seq, seq_len, heads, head_dim, scale, stream_ptr()))
+    return out
+
+
+def im2col_patches(image, grid_cols, patch_begin, n_patches):
+    """image: [3, H, W] uint8 or fp32 view with unit stride along W."""
+    require_cuda(image, "image")
+    device_check()
+    assert image.dim() == 3 and image.shape[0] == 3 and image.stride(2) == 1
+    assert image.dtype in (torch.uint8, torch.float32)
+    a = torch.empty((n_patches * 256, 768), dtype=torch.bfloat16, device=image.device)
+    check(load().hb_im2col_patches(ptr(image), int(image.dtype == torch.float32), image.stride(0), image.stride(1),
+                                   grid_cols, patch_begin, n_patches, ptr(a), stream_ptr()))
+    return a

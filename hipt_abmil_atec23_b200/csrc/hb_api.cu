@@ -1,0 +1,286 @@
+// hb_api.cu — the extern "C" surface declared in include/hipt_b200.h plus the host-side drivers that sequence the
+// kernels of a ViT forward (HIPT_4K/vision_transformer.py:248-253, vision_transformer4k.py:241-246).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/hipt_b200.h"
+#include "hb_internal.h"
+
+namespace hb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                   uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMapDataType cdt = dt == TMAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                              : dt == TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                               : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    const uint32_t esz = dt == TMAP_BF16 ? 2 : dt == TMAP_F32 ? 4 : 1;
+    if (box_cols * esz != 128) return set_error("encode_tmap_2d: box inner extent must be 128 B");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0)
+        return set_error("encode_tmap_2d: base/pitch must be 16 B aligned");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, cdt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return 0;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+// ---------------------------------------------------------------------------------------------------- plan object
+struct hb_vit_plan {
+    hb_vit_config cfg;
+    int depth_limit;
+    // workspace carve-up
+    float* x;          // [max_rows, dim] fp32 residual stream
+    void* xn;          // [max_rows, dim] bf16 LayerNorm output
+    void* qkv;         // [max_rows, 3 dim] bf16
+    void* att;         // [max_rows, dim] bf16 attention output
+    void* hid;         // [max_rows, mlp] bf16 MLP hidden (also the im2col operand of the patch embed)
+    size_t hid_bytes;
+    std::vector<const void*> w;
+    std::vector<GemmArgs> g_qkv, g_proj, g_fc1, g_fc2;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t ws_layout(const hb_vit_config* c, size_t* off_x, size_t* off_xn, size_t* off_qkv, size_t* off_att,
+                        size_t* off_hid, size_t* hid_bytes) {
+    const size_t rows = align_up(static_cast<size_t>(c->max_rows), 128);
+    size_t o = 0;
+    *off_x = o;   o += align_up(rows * c->dim * 4, 1024);
+    *off_xn = o;  o += align_up(rows * c->dim * 2, 1024);
+    *off_qkv = o; o += align_up(rows * c->dim * 3 * 2, 1024);
+    *off_att = o; o += align_up(rows * c->dim * 2, 1024);
+    *off_hid = o;
+    *hid_bytes = align_up(rows * c->mlp_dim * 2, 1024);
+    o += *hid_bytes;
+    return o;
+}
+
+extern "C" {
+
+int hb_abi_version(void) { return HB_ABI_VERSION; }
+const char* hb_last_error(void) { return g_err; }
+
+int hb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0, major = 0, minor = 0, sms = 0;
+    HB_CUDA_OK(cudaGetDevice(&dev));
+    HB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    HB_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    HB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sm_count) *sm_count = sms;
+    if (cc_major) *cc_major = major;
+    if (cc_minor) *cc_minor = minor;
+    if (major != 10) return set_error("libhipt_b200 needs an sm_100 (B200) device, found sm_%d%d", major, minor);
+    return 0;
+}
+
+int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int epilogue, void* out, int M, int N,
+                 int K, const float* tok_table, int tokens_per_seq, void* stream) {
+    GemmArgs g;
+    if (gemm_prepare(g, a_bf16, w_bf16, bias, epilogue, out, M, N, K, tok_table, tokens_per_seq)) return -1;
+    return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+int hb_layernorm(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps, void* out_bf16,
+                 float* out_f32, int rows, int dim, void* stream) {
+    return layernorm_launch(x, x_row_stride, gamma, beta, eps, out_bf16, out_f32, rows, dim,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int hb_attention(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
+                 void* stream) {
+    return attention_launch(qkv_bf16, out_bf16, n_seq, seq_len, heads, head_dim, scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int hb_im2col_patches(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
+                      int patch_begin, int n_patches, void* a_bf16, void* stream) {
+    return im2col_launch(image, image_is_f32, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, a_bf16,
+                         static_cast<cudaStream_t>(stream));
+}
+
+size_t hb_vit_workspace_bytes(const hb_vit_config* cfg) {
+    size_t a, b, c, d, e, f;
+    return ws_layout(cfg, &a, &b, &c, &d, &e, &f);
+}
+
+int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host, int n_weights, void* workspace,
+                       size_t workspace_bytes, hb_vit_plan** plan_out) {
+    if (!cfg || !weights_host || !workspace || !plan_out) return set_error("hb_vit_plan_create: null argument");
+    if (cfg->dim != 384 && cfg->dim != 192) return set_error("hb_vit_plan_create: dim %d not supported", cfg->dim);
+    if (cfg->dim % cfg->heads != 0 || (cfg->dim / cfg->heads != 64 && cfg->dim / cfg->heads != 32))
+        return set_error("hb_vit_plan_create: head_dim must be 64 or 32");
+    if (n_weights != 3 + 12 * cfg->depth)
+        return set_error("hb_vit_plan_create: expected %d weight pointers, got %d", 3 + 12 * cfg->depth, n_weights);
+    for (int i = 0; i < n_weights; ++i)
+        if (!weights_host[i]) return set_error("hb_vit_plan_create: weight pointer %d is null", i);
+    size_t ox, oxn, oqkv, oatt, ohid, hid_bytes;
+    const size_t need = ws_layout(cfg, &ox, &oxn, &oqkv, &oatt, &ohid, &hid_bytes);
+    if (workspace_bytes < need) return set_error("hb_vit_plan_create: workspace %zu < %zu bytes", workspace_bytes, need);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error("hb_vit_plan_create: workspace must be 1 KiB aligned");
+
+    hb_vit_plan* p = new (std::nothrow) hb_vit_plan();
+    if (!p) return set_error("hb_vit_plan_create: out of host memory");
+    p->cfg = *cfg;
+    p->depth_limit = cfg->depth;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    p->x = reinterpret_cast<float*>(ws + ox);
+    p->xn = ws + oxn;
+    p->qkv = ws + oqkv;
+    p->att = ws + oatt;
+    p->hid = ws + ohid;
+    p->hid_bytes = hid_bytes;
+    p->w.assign(weights_host, weights_host + n_weights);
+    const int D = cfg->dim, H = cfg->mlp_dim, R = cfg->max_rows;
+    p->g_qkv.resize(cfg->depth); p->g_proj.resize(cfg->depth); p->g_fc1.resize(cfg->depth); p->g_fc2.resize(cfg->depth);
+    for (int i = 0; i < cfg->depth; ++i) {
+        const void* const* w = &p->w[3 + 12 * i];
+        int rc = 0;
+        rc |= gemm_prepare(p->g_qkv[i], p->xn, w[2], static_cast<const float*>(w[3]), HB_EPI_BIAS_BF16, p->qkv, R, 3 * D, D, nullptr, 0);
+        rc |= gemm_prepare(p->g_proj[i], p->att, w[4], static_cast<const float*>(w[5]), HB_EPI_BIAS_RESADD_F32, p->x, R, D, D, nullptr, 0);
+        rc |= gemm_prepare(p->g_fc1[i], p->xn, w[8], static_cast<const float*>(w[9]), HB_EPI_BIAS_GELU_BF16, p->hid, R, H, D, nullptr, 0);
+        rc |= gemm_prepare(p->g_fc2[i], p->hid, w[10], static_cast<const float*>(w[11]), HB_EPI_BIAS_RESADD_F32, p->x, R, D, H, nullptr, 0);
+        if (rc) { delete p; return -1; }
+    }
+    *plan_out = p;
+    return 0;
+}
+
+void hb_vit_plan_destroy(hb_vit_plan* plan) { delete plan; }
+
+int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit) {
+    if (!plan) return set_error("null plan");
+    plan->depth_limit = (depth_limit <= 0 || depth_limit > plan->cfg.depth) ? plan->cfg.depth : depth_limit;
+    return 0;
+}
+
+int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes) {
+    if (!plan || !ptr || !bytes) return set_error("null argument");
+    const size_t rows = align_up(static_cast<size_t>(plan->cfg.max_rows), 128);
+    switch (which) {
+        case 0: *ptr = plan->x; *bytes = rows * plan->cfg.dim * 4; return 0;
+        case 1: *ptr = plan->xn; *bytes = rows * plan->cfg.dim * 2; return 0;
+        case 2: *ptr = plan->qkv; *bytes = rows * plan->cfg.dim * 6; return 0;
+        case 3: *ptr = plan->att; *bytes = rows * plan->cfg.dim * 2; return 0;
+        case 4: *ptr = plan->hid; *bytes = plan->hid_bytes; return 0;
+    }
+    return set_error("hb_vit_plan_buffer: unknown buffer %d", which);
+}
+
+}  // extern "C"
+
+// x already holds the token rows; runs the transformer blocks and the final LayerNorm on the CLS rows.
+static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, void* cls_bf16, cudaStream_t st) {
+    const hb_vit_config& c = p->cfg;
+    const int M = n_seq * seq_len;
+    const int D = c.dim, hd = D / c.heads;
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    for (int i = 0; i < p->depth_limit; ++i) {
+        const void* const* w = &p->w[3 + 12 * i];
+        if (layernorm_launch(p->x, D, static_cast<const float*>(w[0]), static_cast<const float*>(w[1]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1;
+        GemmArgs g = p->g_qkv[i]; g.M = M;
+        if (gemm_launch(g, st)) return -1;
+        if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st)) return -1;
+        g = p->g_proj[i]; g.M = M;
+        if (gemm_launch(g, st)) return -1;
+        if (layernorm_launch(p->x, D, static_cast<const float*>(w[6]), static_cast<const float*>(w[7]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1;
+        g = p->g_fc1[i]; g.M = M;
+        if (gemm_launch(g, st)) return -1;
+        g = p->g_fc2[i]; g.M = M;
+        if (gemm_launch(g, st)) return -1;
+    }
+    // final LayerNorm only where it is consumed: x[:, 0] (vision_transformer.py:252-253)
+    return layernorm_launch(p->x, static_cast<size_t>(seq_len) * D, static_cast<const float*>(p->w[1]),
+                            static_cast<const float*>(p->w[2]), c.ln_eps, cls_bf16, cls_f32, n_seq, D, st);
+}
+
+extern "C" {
+
+int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch,
+                      int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
+                      const float* pos_table, float* cls_f32, void* cls_bf16, void* stream) {
+    if (!plan || !image || !embed_w_bf16 || !embed_b || !pos_table) return set_error("hb_vit256_forward: null argument");
+    const int seq_len = 257, T = 256;
+    if (n_patches <= 0) return 0;
+    if (static_cast<long long>(n_patches) * seq_len > plan->cfg.max_rows)
+        return set_error("hb_vit256_forward: %d patches exceed the plan capacity of %d rows", n_patches, plan->cfg.max_rows);
+    if (static_cast<size_t>(n_patches) * T * 768 * 2 > plan->hid_bytes)
+        return set_error("hb_vit256_forward: im2col operand does not fit the workspace");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = plan->cfg.dim;
+    if (im2col_launch(image, image_is_f32, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, plan->hid, st)) return -1;
+    GemmArgs g;
+    if (gemm_prepare(g, plan->hid, embed_w_bf16, embed_b, HB_EPI_TOKENS_F32, plan->x, n_patches * T, D, 768, pos_table, T)) return -1;
+    if (gemm_launch(g, st)) return -1;
+    if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_patches, seq_len, D, st)) return -1;
+    return run_blocks(plan, n_patches, seq_len, cls_f32, cls_bf16, st);
+}
+
+int hb_vit4k_forward(hb_vit_plan* plan, const void* cls256_bf16, int n_regions, int tokens_per_region, int in_dim,
+                     const void* phi_w_bf16, const float* phi_b, const float* pos_table, float* out_f32, void* stream) {
+    if (!plan || !cls256_bf16 || !phi_w_bf16 || !phi_b || !pos_table || !out_f32) return set_error("hb_vit4k_forward: null argument");
+    if (n_regions <= 0) return 0;
+    const int seq_len = tokens_per_region + 1;
+    if (static_cast<long long>(n_regions) * seq_len > plan->cfg.max_rows)
+        return set_error("hb_vit4k_forward: %d regions exceed the plan capacity of %d rows", n_regions, plan->cfg.max_rows);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = plan->cfg.dim;
+    GemmArgs g;
+    if (gemm_prepare(g, cls256_bf16, phi_w_bf16, phi_b, HB_EPI_TOKENS_GELU_F32, plan->x, n_regions * tokens_per_region, D, in_dim, pos_table, tokens_per_region)) return -1;
+    if (gemm_launch(g, st)) return -1;
+    if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_regions, seq_len, D, st)) return -1;
+    return run_blocks(plan, n_regions, seq_len, out_f32, nullptr, st);
+}
+
+}  // extern "C"

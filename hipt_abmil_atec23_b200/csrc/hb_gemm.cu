@@ -1,0 +1,328 @@
+// hb_gemm.cu — persistent, warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] * W[N,K]^T + bias)
+//
+//   warp 0 : TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1 : MMA issuer    (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 per instr)
+//   warp 2 : TMEM allocator (2 x BN fp32 accumulator columns, double buffered against the epilogue)
+//   warps 4-7 : epilogue   (tcgen05.ld -> bias / exact-erf GELU -> swizzled smem -> TMA store or TMA reduce-add)
+//
+// This replaces the nn.Linear call sites of the reference's ViT blocks (HIPT_4K/vision_transformer.py:93-95 fc1/fc2,
+// :114-116 qkv/proj; HIPT_4K/vision_transformer4k.py:169 phi) and, fed with an im2col'd region, the patch-embed
+// convolution (vision_transformer.py:165-169).  nn.Linear.weight is [out,in] = [N,K] K-major, which is exactly the
+// UMMA "B K-major" operand, so weights are used as stored (cast to bf16 once at load).
+#include "hb_ptx.cuh"
+#include "hb_internal.h"
+
+namespace hb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle span
+constexpr int GEMM_THREADS = 256;    // 8 warps: producer, mma, tmem-alloc, spare, 4x epilogue
+constexpr int GEMM_EPI_THREADS = 128;
+constexpr int STAGE_BYTES_OUT = 128 * 128;   // 128 rows x 128 B staging chunk for the TMA store
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 2 * STAGE_BYTES_OUT + 256 + 1024;
+};
+
+// Epilogue kinds (mirrored in include/hipt_b200.h as HB_EPI_*)
+enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2, EPI_TOKENS_F32 = 3, EPI_TOKENS_GELU_F32 = 4 };
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_out, const float* __restrict__ bias,
+                 const float* __restrict__ tok_table, float* __restrict__ tok_out, int M, int N, int K,
+                 int tokens_per_seq) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+    constexpr bool OUT_TOKENS = (EPI == EPI_TOKENS_F32 || EPI == EPI_TOKENS_GELU_F32);
+    constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;      // 128 B of output per row per chunk
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint8_t* smem_o = smem_b + STAGES * Cfg::B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 2 * STAGE_BYTES_OUT);
+    uint64_t* full_bar = bars;                  // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]  MMA -> TMA
+    uint64_t* acc_full = bars + 2 * STAGES;     // [2]       MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * STAGES + 2;// [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_w);
+        if (!OUT_TOKENS) tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], GEMM_EPI_THREADS); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_tiles = N / BN;
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    const int total_tiles = m_tiles * n_tiles;
+    const int k_blocks = K / GEMM_BK;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint64_t pol_w = policy_evict_last();
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * GEMM_BM;
+                const int n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * GEMM_BK, m0);
+                    tma_load_2d_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+            uint32_t stage = 0, phase = 0;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+                    const uint64_t db = umma_desc_k128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // advance 16 bf16 = 32 B inside the swizzle span: +2 in the (addr >> 4) field
+                        umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(&acc_full[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int ew = warp & 3;                       // TMEM lane quadrant of this warp
+        const int row_in_tile = ew * 32 + lane;
+        const bool store_leader = (warp == 4 && lane == 0);
+        uint32_t it = 0;
+        uint32_t chunk_ctr = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / n_tiles) * GEMM_BM;
+            const int n0 = (tile % n_tiles) * BN;
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+
+            if constexpr (OUT_TOKENS) {
+                // fp32 token rows written straight to global with a per-sequence row remap (+1 for the CLS slot)
+                // and a per-(token,col) additive table (positional embedding).
+                const int row = m0 + row_in_tile;
+                const int seq = row / tokens_per_seq;
+                const int tok = row - seq * tokens_per_seq;
+                const size_t out_row = static_cast<size_t>(seq) * (tokens_per_seq + 1) + 1 + tok;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr_row + c * 32, v);
+                    tmem_ld_wait();
+                    if (row < M) {
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+                        const float4* t4 = reinterpret_cast<const float4*>(tok_table + static_cast<size_t>(1 + tok) * N + n0 + c * 32);
+                        float4* o4 = reinterpret_cast<float4*>(tok_out + out_row * N + n0 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            const float4 t = __ldg(t4 + j);
+                            float4 r;
+                            r.x = __uint_as_float(v[4 * j + 0]) + b.x;
+                            r.y = __uint_as_float(v[4 * j + 1]) + b.y;
+                            r.z = __uint_as_float(v[4 * j + 2]) + b.z;
+                            r.w = __uint_as_float(v[4 * j + 3]) + b.w;
+                            if constexpr (EPI == EPI_TOKENS_GELU_F32) {
+                                r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
+                            }
+                            r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+                            o4[j] = r;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[as]);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / CHUNK_COLS; ++c, ++chunk_ctr) {
+                    uint8_t* stage_buf = smem_o + (chunk_ctr & 1) * STAGE_BYTES_OUT;
+                    // the TMA store that last read this staging buffer (2 chunks ago) must have drained it
+                    if (store_leader) tma_store_wait_read<1>();
+                    named_bar_sync(1, GEMM_EPI_THREADS);
+
+                    uint8_t* row_ptr = stage_buf + row_in_tile * 128;
+                    const int sw = row_in_tile & 7;
+                    if constexpr (OUT_BF16) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(taddr_row + c * 64 + h * 32, v);
+                            tmem_ld_wait();
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 64 + h * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {       // 4 x (8 values -> one 16 B chunk)
+                                const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
+                                float f[8];
+                                f[0] = __uint_as_float(v[8 * j + 0]) + b0.x; f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+                                f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+                                f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+                                f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+                                if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                                }
+                                uint4 pk;
+                                pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
+                                pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
+                                const int chunk16 = h * 4 + j;
+                                *reinterpret_cast<uint4*>(row_ptr + ((chunk16 ^ sw) << 4)) = pk;
+                            }
+                        }
+                    } else {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr_row + c * 32, v);
+                        tmem_ld_wait();
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            float4 r;
+                            r.x = __uint_as_float(v[4 * j + 0]) + b.x; r.y = __uint_as_float(v[4 * j + 1]) + b.y;
+                            r.z = __uint_as_float(v[4 * j + 2]) + b.z; r.w = __uint_as_float(v[4 * j + 3]) + b.w;
+                            *reinterpret_cast<float4*>(row_ptr + ((j ^ sw) << 4)) = r;
+                        }
+                    }
+                    if (c == BN / CHUNK_COLS - 1) {     // accumulator fully drained: hand TMEM back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[as]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, GEMM_EPI_THREADS);
+                    if (store_leader) {
+                        if constexpr (EPI == EPI_BIAS_RESADD_F32)
+                            tma_reduce_add_2d(&map_out, stage_buf, n0 + c * CHUNK_COLS, m0);
+                        else
+                            tma_store_2d(&map_out, stage_buf, n0 + c * CHUNK_COLS, m0);
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (store_leader) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_bf16_kernel<BN, EPI>;
+    static bool attr_done = false;     // per instantiation
+    if (!attr_done) {
+        HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
+    const int total = m_tiles * (g.N / BN);
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.map_a, g.map_w, g.map_out, g.bias, g.tok_table, g.tok_out,
+                                                           g.M, g.N, g.K, g.tokens_per_seq);
+    HB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int BN>
+static int launch_gemm_bn(const GemmArgs& g, cudaStream_t stream) {
+    switch (g.epi) {
+        case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(g, stream);
+        case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(g, stream);
+        case EPI_BIAS_RESADD_F32: return launch_gemm_t<BN, EPI_BIAS_RESADD_F32>(g, stream);
+        case EPI_TOKENS_F32: return launch_gemm_t<BN, EPI_TOKENS_F32>(g, stream);
+        case EPI_TOKENS_GELU_F32: return launch_gemm_t<BN, EPI_TOKENS_GELU_F32>(g, stream);
+    }
+    return set_error("hb_gemm: unknown epilogue %d", g.epi);
+}
+
+int gemm_pick_bn(int N) {
+    if (N % 256 == 0 && N >= 1024) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    return 0;
+}
+
+int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, int epi, void* out, int M, int N, int K,
+                 const float* tok_table, int tokens_per_seq) {
+    if (M <= 0 || N <= 0 || K <= 0) return set_error("hb_gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    if (K % GEMM_BK != 0) return set_error("hb_gemm: K=%d must be a multiple of %d", K, GEMM_BK);
+    const int bn = gemm_pick_bn(N);
+    if (bn == 0) return set_error("hb_gemm: N=%d must be a multiple of 128 or 192", N);
+    if (bias == nullptr) return set_error("hb_gemm: bias is required");
+    g.bn = bn; g.epi = epi; g.M = M; g.N = N; g.K = K; g.bias = bias;
+    g.tok_table = tok_table; g.tok_out = nullptr; g.tokens_per_seq = tokens_per_seq;
+    if (encode_tmap_2d(&g.map_a, TMAP_BF16, A, M, K, static_cast<uint64_t>(K) * 2, GEMM_BM, GEMM_BK)) return -1;
+    if (encode_tmap_2d(&g.map_w, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn, GEMM_BK)) return -1;
+    if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) {
+        if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, GEMM_BM, 64)) return -1;
+    } else if (epi == EPI_BIAS_RESADD_F32) {
+        if (encode_tmap_2d(&g.map_out, TMAP_F32, out, M, N, static_cast<uint64_t>(N) * 4, GEMM_BM, 32)) return -1;
+    } else if (epi == EPI_TOKENS_F32 || epi == EPI_TOKENS_GELU_F32) {
+        if (tok_table == nullptr || tokens_per_seq <= 0) return set_error("hb_gemm: token epilogue needs a table");
+        g.map_out = g.map_a;   // unused by the kernel; keep the parameter well-formed
+        g.tok_out = static_cast<float*>(out);
+    } else {
+        return set_error("hb_gemm: unknown epilogue %d", epi);
+    }
+    return 0;
+}
+
+int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
+    switch (g.bn) {
+        case 128: return launch_gemm_bn<128>(g, stream);
+        case 192: return launch_gemm_bn<192>(g, stream);
+        case 256: return launch_gemm_bn<256>(g, stream);
+    }
+    return set_error("hb_gemm: bad BN %d", g.bn);
+}
+
+}  // namespace hb

@@ -1,0 +1,53 @@
+// hb_internal.h — host-side plumbing shared by the translation units of libhipt_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace hb {
+
+int set_error(const char* fmt, ...);          // records the message for hb_last_error(), returns -1
+int num_sms();
+
+#define HB_CUDA_OK(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) return ::hb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+enum TmapDtype { TMAP_BF16 = 0, TMAP_F32 = 1, TMAP_U8 = 2 };
+// 2-D row-major tensor [rows, cols] with a row pitch in bytes; box [box_rows, box_cols]; SWIZZLE_128B
+// (box_cols * elem_size must be 128 B).  Out-of-bounds elements read as zero and are not written.
+int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                   uint32_t box_rows, uint32_t box_cols);
+
+struct GemmArgs {
+    CUtensorMap map_a, map_w, map_out;
+    const float* bias;
+    const float* tok_table;
+    float* tok_out;
+    int M, N, K, bn, epi, tokens_per_seq;
+};
+int gemm_pick_bn(int N);
+int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, int epi, void* out, int M, int N, int K,
+                 const float* tok_table, int tokens_per_seq);
+int gemm_launch(const GemmArgs& g, cudaStream_t stream);
+
+// elementwise / row kernels
+int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps,
+                     void* out_bf16, float* out_f32, int rows, int dim, cudaStream_t stream);
+int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
+                     cudaStream_t stream);
+int im2col_launch(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
+                  int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream);
+int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, int n_seq, int seq_len, int dim,
+                    cudaStream_t stream);
+
+int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
+                        int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
+                        float* a_raw, float* m_out, float* logits, float* y_prob, long long* y_hat, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1);
+
+}  // namespace hb

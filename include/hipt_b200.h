@@ -1,0 +1,125 @@
+/* hipt_b200.h — C ABI of libhipt_b200.so: the B200 (sm_100a) implementation of the HIPT_4K + CLAM_SB hot path.
+ *
+ * The reference (scjjb/HIPT_ABMIL_ATEC23) has no FFI: its hot path is reached through Python nn.Module.forward calls
+ * that bottom out in ATen/cuBLAS/cuDNN.  Each entry point below therefore cites the reference Python call site it
+ * replaces; the Python modules in hipt_abmil_atec23_b200/ (same class names, constructor arguments and state_dict
+ * keys as the reference) bind these symbols with ctypes — see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host;
+ * `stream` is a cudaStream_t passed as void*; every function returns 0 on success and -1 on failure, after which
+ * hb_last_error() describes the failure (thread-local).  Nothing here allocates device memory: callers pass
+ * workspaces sized by the *_workspace_bytes() queries.  bf16 buffers are passed as void*.
+ */
+#ifndef HIPT_B200_H
+#define HIPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+/* GEMM epilogues */
+#define HB_EPI_BIAS_BF16 0        /* out_bf16[M,N]  = A W^T + bias                                  */
+#define HB_EPI_BIAS_GELU_BF16 1   /* out_bf16[M,N]  = gelu_erf(A W^T + bias)                        */
+#define HB_EPI_BIAS_RESADD_F32 2  /* out_f32[M,N]  += A W^T + bias     (residual stream, in place)  */
+#define HB_EPI_TOKENS_F32 3       /* token rows: out_f32[(r/T)*(T+1)+1+r%T, :] = A W^T + bias + table[1+r%T, :] */
+#define HB_EPI_TOKENS_GELU_F32 4  /* same with gelu_erf applied before the table add               */
+
+int hb_abi_version(void);
+const char* hb_last_error(void);
+/* sm_count / compute capability of the current device; fails unless it is sm_100 */
+int hb_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Single kernels (also the units the parity tests exercise).
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* nn.Linear (+GELU / +residual): HIPT_4K/vision_transformer.py:93-95,114-116 ; vision_transformer4k.py:169.
+ * a_bf16 [M,K] row-major, w_bf16 [N,K] row-major (nn.Linear.weight layout), bias fp32 [N].
+ * K % 64 == 0; N % 128 == 0 or N % 192 == 0.  tok_table / tokens_per_seq only for the TOKENS epilogues. */
+int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int epilogue, void* out, int M, int N,
+                 int K, const float* tok_table, int tokens_per_seq, void* stream);
+
+/* nn.LayerNorm(dim, eps): vision_transformer.py:138,142,195.  x fp32 rows at x_row_stride (elements);
+ * writes out_bf16 and/or out_f32 (either may be NULL), densely packed [rows, dim].  dim in {384, 192}. */
+int hb_layernorm(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps, void* out_bf16,
+                 float* out_f32, int rows, int dim, void* stream);
+
+/* softmax(q k^T * scale) v per (sequence, head): vision_transformer.py:119-128.
+ * qkv_bf16 [n_seq*seq_len, 3*heads*head_dim] (q|k|v, head-major); out_bf16 [n_seq*seq_len, heads*head_dim]. */
+int hb_attention(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
+                 void* stream);
+
+/* unfold(2,256,256).unfold(3,256,256) + rearrange (HIPT_4K/hipt_4k.py:64-65) composed with the receptive fields of the
+ * 16x16/16 patch-embed conv (vision_transformer.py:165-169): image [3, H, W] (uint8 or fp32; element strides given)
+ * -> a_bf16 [n_patches*256, 768], row = patch*256 + ty*16 + tx, col = c*256 + i*16 + j.
+ * Patch p of the region grid is at (p / grid_cols, p % grid_cols). */
+int hb_im2col_patches(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
+                      int patch_begin, int n_patches, void* a_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ViT encoder plans: VisionTransformer.forward (vision_transformer.py:248-253) and VisionTransformer4K.forward
+ * (vision_transformer4k.py:241-246).  A plan binds the block weights and a caller-owned workspace and pre-encodes
+ * the TMA descriptors of the 4*depth block GEMMs.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct hb_vit_plan hb_vit_plan;
+
+typedef struct hb_vit_config {
+    int dim;       /* 384 (ViT-256) / 192 (ViT-4K) */
+    int heads;     /* 6 */
+    int depth;     /* 12 / 6 */
+    int mlp_dim;   /* 1536 / 768 */
+    int max_rows;  /* capacity in token rows (n_seq * seq_len) */
+    float ln_eps;  /* 1e-6 */
+} hb_vit_config;
+
+/* weights[]: [0] cls_token f32[dim], [1] norm.weight, [2] norm.bias, then for block i at 3+12*i:
+ * norm1.weight, norm1.bias, attn.qkv.weight (bf16 [3dim,dim]), attn.qkv.bias, attn.proj.weight (bf16), attn.proj.bias,
+ * norm2.weight, norm2.bias, mlp.fc1.weight (bf16 [mlp,dim]), mlp.fc1.bias, mlp.fc2.weight (bf16 [dim,mlp]), mlp.fc2.bias.
+ * All other entries fp32. */
+size_t hb_vit_workspace_bytes(const hb_vit_config* cfg);
+int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host, int n_weights, void* workspace,
+                       size_t workspace_bytes, hb_vit_plan** plan_out);
+void hb_vit_plan_destroy(hb_vit_plan* plan);
+/* debug / test hooks: run only the first `depth_limit` blocks (<=0: all); fetch a workspace buffer
+ * (0 = x fp32 residual stream, 1 = LN out bf16, 2 = qkv bf16, 3 = attention out bf16, 4 = MLP hidden bf16) */
+int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit);
+int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes);
+
+/* ViT-256 over n_patches 256x256 patches of one region image (HIPT_4K.forward steps 2-3, hipt_4k.py:64-70).
+ * embed_w_bf16 [dim, 768] / embed_b f32 [dim]: patch_embed.proj with any input normalisation folded in by the caller;
+ * pos_table f32 [257, dim]: cls+pos rows after interpolate_pos_encoding (vision_transformer.py:213-233).
+ * Outputs the final-LayerNorm CLS rows: cls_f32 [n_patches, dim] and/or cls_bf16 (either may be NULL). */
+int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch,
+                      int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
+                      const float* pos_table, float* cls_f32, void* cls_bf16, void* stream);
+
+/* ViT-4K over n_regions grids of tokens_per_region ViT-256 CLS tokens (hipt_4k.py:72-75; the reshape/transpose at :73
+ * is the identity on token order).  cls256_bf16 [n_regions*tokens_per_region, in_dim]; phi_w_bf16 [dim, in_dim];
+ * pos_table f32 [tokens_per_region+1, dim]; out_f32 [n_regions, dim]. */
+int hb_vit4k_forward(hb_vit_plan* plan, const void* cls256_bf16, int n_regions, int tokens_per_region, int in_dim,
+                     const void* phi_w_bf16, const float* phi_b, const float* pos_table, float* out_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * CLAM_SB gated-attention MIL pooling over ragged bags (models/model_clam.py:59-64 Attn_Net_Gated.forward,
+ * :147-191 CLAM_SB.forward), n_models weight sets ("folds") evaluated over the same bags in one pass.
+ * feats f32 [total_instances, L0]; bag_offsets int32 [n_bags+1] (device); weights_host[m*10 + k], k =
+ * fc.weight[L1,L0], fc.bias, attention_a.weight[D,L1], attention_a.bias, attention_b.weight, attention_b.bias,
+ * attention_c.weight[1,D], attention_c.bias[1], classifiers.weight[C,L1], classifiers.bias[C].
+ * Outputs (any may be NULL except a_raw): a_raw [n_models, total_instances] (pre-softmax scores), m_out
+ * [n_models, n_bags, L1], logits [n_models, n_bags, C], y_prob [n_models, n_bags, C], y_hat int64 [n_models, n_bags].
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t hb_clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1);
+int hb_clam_sb_forward(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
+                       int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
+                       float* a_raw, float* m_out, float* logits, float* y_prob, int64_t* y_hat, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPT_B200_H */

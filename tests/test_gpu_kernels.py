@@ -1,0 +1,143 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against plain PyTorch fp32 on the same bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from hipt_abmil_atec23_b200 import _lib as L
+    return L
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 384, 384), (257, 1152, 384), (1000, 1536, 384), (514, 384, 1536),
+                                   (65792, 1152, 384), (257, 576, 192), (257, 192, 768), (300, 768, 192)])
+def test_gemm_bias_bf16(M, N, K):
+    L = _lib()
+    a = _rand((M, K), 1).cuda().bfloat16()
+    w = _rand((N, K), 2, 0.05).cuda().bfloat16()
+    b = _rand((N,), 3, 0.1).cuda()
+    out = L.gemm_bf16(a, w, b, L.HB_EPI_BIAS_BF16)
+    ref = a.float() @ w.float().t() + b
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("M,N,K", [(257, 1536, 384), (4112, 768, 192)])
+def test_gemm_gelu_bf16(M, N, K):
+    L = _lib()
+    a = _rand((M, K), 4).cuda().bfloat16()
+    w = _rand((N, K), 5, 0.05).cuda().bfloat16()
+    b = _rand((N,), 6, 0.1).cuda()
+    out = L.gemm_bf16(a, w, b, L.HB_EPI_BIAS_GELU_BF16)
+    ref = F.gelu(a.float() @ w.float().t() + b)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("M,N,K", [(257, 384, 384), (1000, 384, 1536), (65792, 384, 1536), (257, 192, 768)])
+def test_gemm_resadd_f32(M, N, K):
+    L = _lib()
+    a = _rand((M, K), 7).cuda().bfloat16()
+    w = _rand((N, K), 8, 0.05).cuda().bfloat16()
+    b = _rand((N,), 9, 0.1).cuda()
+    x0 = _rand((M, N), 10).cuda()
+    x = x0.clone()
+    L.gemm_bf16(a, w, b, L.HB_EPI_BIAS_RESADD_F32, out=x)
+    ref = x0 + a.float() @ w.float().t() + b
+    err = (x - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("n_seq,T,N,K,gelu", [(3, 256, 384, 768, False), (2, 256, 192, 384, True), (3, 35, 192, 384, True)])
+def test_gemm_tokens(n_seq, T, N, K, gelu):
+    L = _lib()
+    M = n_seq * T
+    a = _rand((M, K), 11).cuda().bfloat16()
+    w = _rand((N, K), 12, 0.05).cuda().bfloat16()
+    b = _rand((N,), 13, 0.1).cuda()
+    tab = _rand((T + 1, N), 14, 0.02).cuda()
+    out = torch.full((n_seq * (T + 1), N), 7.0, device="cuda")
+    L.gemm_bf16(a, w, b, L.HB_EPI_TOKENS_GELU_F32 if gelu else L.HB_EPI_TOKENS_F32, out=out, tok_table=tab,
+                tokens_per_seq=T)
+    y = a.float() @ w.float().t() + b
+    if gelu:
+        y = F.gelu(y)
+    y = y.view(n_seq, T, N) + tab[1:]
+    o = out.view(n_seq, T + 1, N)
+    assert torch.all(o[:, 0] == 7.0)          # CLS slots untouched
+    err = (o[:, 1:] - y).abs().max().item()
+    assert err <= 1e-3 * max(1.0, y.abs().max().item()), err
+
+
+@pytest.mark.parametrize("rows,dim", [(1, 384), (257, 384), (65792, 384), (257, 192), (5, 192)])
+def test_layernorm(rows, dim):
+    L = _lib()
+    x = _rand((rows, dim), 20, 3.0).cuda() + 0.5
+    g = _rand((dim,), 21).cuda()
+    b = _rand((dim,), 22).cuda()
+    ob, of = L.layernorm(x, g, b, 1e-6, rows, dim, want_bf16=True, want_f32=True)
+    ref = F.layer_norm(x, (dim,), g, b, 1e-6)
+    assert (of - ref).abs().max().item() < 2e-5
+    assert (ob.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_layernorm_strided_cls_rows():
+    L = _lib()
+    n, S, dim = 7, 257, 384
+    x = _rand((n * S, dim), 23).cuda()
+    g = _rand((dim,), 24).cuda()
+    b = _rand((dim,), 25).cuda()
+    _, of = L.layernorm(x, g, b, 1e-6, n, dim, row_stride=S * dim, want_bf16=False, want_f32=True)
+    ref = F.layer_norm(x.view(n, S, dim)[:, 0], (dim,), g, b, 1e-6)
+    assert (of - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("n_seq,S,heads,hd", [(4, 257, 6, 64), (2, 257, 6, 32), (3, 64, 6, 64), (2, 100, 6, 32),
+                                              (1, 17, 6, 64), (2, 128, 6, 64)])
+def test_attention(n_seq, S, heads, hd):
+    L = _lib()
+    D = heads * hd
+    qkv = _rand((n_seq * S, 3 * D), 30).cuda().bfloat16()
+    scale = hd ** -0.5
+    out = L.attention(qkv, n_seq, S, heads, hd, scale)
+    q, k, v = qkv.float().view(n_seq, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(n_seq * S, D)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_im2col(dtype):
+    L = _lib()
+    g = torch.Generator().manual_seed(40)
+    H, W = 512, 768
+    if dtype == torch.uint8:
+        img = torch.randint(0, 256, (3, H, W), dtype=torch.uint8, generator=g).cuda()
+    else:
+        img = torch.randn((3, H, W), generator=g).cuda()
+    grid_cols = W // 256
+    n = (H // 256) * grid_cols
+    a = L.im2col_patches(img, grid_cols, 0, n)
+    x = img.float().unsqueeze(0)
+    patches = x.unfold(2, 256, 256).unfold(3, 256, 256)            # [1,3,p1,p2,256,256]
+    patches = patches.permute(0, 2, 3, 1, 4, 5).reshape(n, 3, 256, 256)
+    cols = F.unfold(patches, kernel_size=16, stride=16)            # [n, 768, 256], K order (c,i,j)
+    ref = cols.transpose(1, 2).reshape(n * 256, 768)
+    if dtype == torch.uint8:
+        assert torch.equal(a.float(), ref)
+    else:
+        assert torch.equal(a, ref.bfloat16())
+    # a sub-range of patches
+    a2 = L.im2col_patches(img, grid_cols, 2, 3)
+    assert torch.equal(a2, a[2 * 256:5 * 256])
