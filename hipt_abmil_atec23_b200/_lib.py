@@ -28,12 +28,15 @@ SIGNATURES = {
     "hb_abi_version": (C.c_int, []),
     "hb_last_error": (C.c_char_p, []),
     "hb_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "hb_launch_count": (C.c_longlong, []),
+    "hb_prof_enable": (C.c_int, [C.c_int]),
+    "hb_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "hb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p]),
     "hb_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p]),
     "hb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
-    "hb_im2col_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+    "hb_im2col_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p]),
     "hb_vit_workspace_bytes": (C.c_size_t, [C.POINTER(HbVitConfig)]),
     "hb_vit_plan_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t,
@@ -41,7 +44,7 @@ SIGNATURES = {
     "hb_vit_plan_destroy": (None, [C.c_void_p]),
     "hb_vit_plan_set_depth_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_vit_plan_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
-    "hb_vit256_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+    "hb_vit256_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_vit4k_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -103,6 +106,32 @@ def device_check():
         _device_checked.add(dev)
 
 
+PROF_KINDS = 32
+PROF_NAMES = {0: "im2col", 1: "embed_gemm", 2: "cls_rows", 3: "layernorm", 4: "qkv_gemm", 5: "attention",
+              6: "proj_gemm", 7: "fc1_gemm", 8: "fc2_gemm", 9: "final_ln", 10: "clam_scores", 11: "clam_combine"}
+
+
+def prof_enable(on=True):
+    check(load().hb_prof_enable(int(on)))
+
+
+def prof_read():
+    """{kernel name: (total ms, launches)} since the last read; ViT-4K kinds are prefixed 'vit4k_'."""
+    ms = (C.c_double * PROF_KINDS)()
+    cnt = (C.c_longlong * PROF_KINDS)()
+    check(load().hb_prof_read(ms, cnt, PROF_KINDS))
+    out = {}
+    for k in range(PROF_KINDS):
+        if cnt[k]:
+            base = PROF_NAMES.get(k % 16, f"kind{k % 16}")
+            out[("vit4k_" if k >= 16 else "") + base] = (ms[k], cnt[k])
+    return out
+
+
+def launch_count():
+    return int(load().hb_launch_count())
+
+
 # ------------------------------------------------------------------------------------------------ thin op wrappers
 def gemm_bf16(a, w, bias, epilogue, out=None, tok_table=None, tokens_per_seq=0):
     """out = epilogue(a @ w.T + bias); a [M,K] bf16, w [N,K] bf16, bias [N] fp32."""
@@ -142,13 +171,23 @@ def attention(qkv, n_seq, seq_len, heads, head_dim, scale):
     return out
 
 
-def im2col_patches(image, grid_cols, patch_begin, n_patches):
-    """image: [3, H, W] uint8 or fp32 view with unit stride along W."""
+def image_layout(image):
+    """(patch_stride, chan_stride, row_pitch, grid_cols, n_patches) of a region [3,H,W] or a patch batch [B,3,256,256]."""
+    assert image.dtype in (torch.uint8, torch.float32) and image.stride(-1) == 1
+    if image.dim() == 3:
+        assert image.shape[0] == 3 and image.shape[1] % 256 == 0 and image.shape[2] % 256 == 0
+        gc = image.shape[2] // 256
+        return 0, image.stride(0), image.stride(1), gc, (image.shape[1] // 256) * gc
+    assert image.dim() == 4 and tuple(image.shape[1:]) == (3, 256, 256)
+    return image.stride(0), image.stride(1), image.stride(2), 0, image.shape[0]
+
+
+def im2col_patches(image, patch_begin, n_patches):
+    """image: region [3, H, W] or patch batch [B, 3, 256, 256]; uint8 or fp32; unit stride along the last dim."""
     require_cuda(image, "image")
     device_check()
-    assert image.dim() == 3 and image.shape[0] == 3 and image.stride(2) == 1
-    assert image.dtype in (torch.uint8, torch.float32)
+    ps, cs, rp, gc, _ = image_layout(image)
     a = torch.empty((n_patches * 256, 768), dtype=torch.bfloat16, device=image.device)
-    check(load().hb_im2col_patches(ptr(image), int(image.dtype == torch.float32), image.stride(0), image.stride(1),
-                                   grid_cols, patch_begin, n_patches, ptr(a), stream_ptr()))
+    check(load().hb_im2col_patches(ptr(image), int(image.dtype == torch.float32), ps, cs, rp, gc, patch_begin,
+                                   n_patches, ptr(a), stream_ptr()))
     return a

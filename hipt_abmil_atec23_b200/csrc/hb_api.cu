@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -70,6 +71,32 @@ int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t ro
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- launch profiler
+// Optional CUDA-event bracket around every kernel launch of the drivers below, on the launching stream, so bench.py
+// can report each kernel's measured share of a step (and the dominant kernel's roofline) from the timed region itself.
+std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int kind; };
+static std::vector<ProfRec> g_prof_recs;
+static size_t g_prof_used = 0;
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+ProfScope::ProfScope(int kind, cudaStream_t st) : st_(st), idx_(-1) {
+    if (!g_prof_on) return;
+    if (g_prof_used == g_prof_recs.size()) {
+        ProfRec r;
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        g_prof_recs.push_back(r);
+    }
+    idx_ = static_cast<long long>(g_prof_used++);
+    g_prof_recs[idx_].kind = kind;
+    cudaEventRecord(g_prof_recs[idx_].a, st_);
+}
+ProfScope::~ProfScope() {
+    if (idx_ >= 0) cudaEventRecord(g_prof_recs[idx_].b, st_);
 }
 
 }  // namespace hb
@@ -144,10 +171,32 @@ int hb_attention(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, i
                             static_cast<cudaStream_t>(stream));
 }
 
-int hb_im2col_patches(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
-                      int patch_begin, int n_patches, void* a_bf16, void* stream) {
-    return im2col_launch(image, image_is_f32, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, a_bf16,
+int hb_im2col_patches(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
+                      int grid_cols, int patch_begin, int n_patches, void* a_bf16, void* stream) {
+    return im2col_launch(image, image_is_f32, patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, a_bf16,
                          static_cast<cudaStream_t>(stream));
+}
+
+long long hb_launch_count(void) { return g_launches.load(); }
+
+int hb_prof_enable(int on) {
+    g_prof_on = on != 0;
+    g_prof_used = 0;
+    return 0;
+}
+
+int hb_prof_read(double* ms_by_kind, long long* count_by_kind, int n_kinds) {
+    if (!ms_by_kind || !count_by_kind) return set_error("hb_prof_read: null argument");
+    for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.0; count_by_kind[i] = 0; }
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        HB_CUDA_OK(cudaEventSynchronize(g_prof_recs[i].b));
+        float ms = 0.f;
+        HB_CUDA_OK(cudaEventElapsedTime(&ms, g_prof_recs[i].a, g_prof_recs[i].b));
+        const int k = g_prof_recs[i].kind;
+        if (k >= 0 && k < n_kinds) { ms_by_kind[k] += ms; count_by_kind[k] += 1; }
+    }
+    g_prof_used = 0;
+    return 0;
 }
 
 size_t hb_vit_workspace_bytes(const hb_vit_config* cfg) {
@@ -226,29 +275,34 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
     const int M = n_seq * seq_len;
     const int D = c.dim, hd = D / c.heads;
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    const int kb = (D == 192) ? HB_PROF_4K_OFFSET : 0;     // profiler kind base: ViT-256 vs ViT-4K
     for (int i = 0; i < p->depth_limit; ++i) {
         const void* const* w = &p->w[3 + 12 * i];
-        if (layernorm_launch(p->x, D, static_cast<const float*>(w[0]), static_cast<const float*>(w[1]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1;
+        { ProfScope ps(kb + HB_PROF_LAYERNORM, st);
+          if (layernorm_launch(p->x, D, static_cast<const float*>(w[0]), static_cast<const float*>(w[1]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1; }
         GemmArgs g = p->g_qkv[i]; g.M = M;
-        if (gemm_launch(g, st)) return -1;
-        if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st)) return -1;
+        { ProfScope ps(kb + HB_PROF_QKV_GEMM, st); if (gemm_launch(g, st)) return -1; }
+        { ProfScope ps(kb + HB_PROF_ATTENTION, st);
+          if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st)) return -1; }
         g = p->g_proj[i]; g.M = M;
-        if (gemm_launch(g, st)) return -1;
-        if (layernorm_launch(p->x, D, static_cast<const float*>(w[6]), static_cast<const float*>(w[7]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1;
+        { ProfScope ps(kb + HB_PROF_PROJ_GEMM, st); if (gemm_launch(g, st)) return -1; }
+        { ProfScope ps(kb + HB_PROF_LAYERNORM, st);
+          if (layernorm_launch(p->x, D, static_cast<const float*>(w[6]), static_cast<const float*>(w[7]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1; }
         g = p->g_fc1[i]; g.M = M;
-        if (gemm_launch(g, st)) return -1;
+        { ProfScope ps(kb + HB_PROF_FC1_GEMM, st); if (gemm_launch(g, st)) return -1; }
         g = p->g_fc2[i]; g.M = M;
-        if (gemm_launch(g, st)) return -1;
+        { ProfScope ps(kb + HB_PROF_FC2_GEMM, st); if (gemm_launch(g, st)) return -1; }
     }
     // final LayerNorm only where it is consumed: x[:, 0] (vision_transformer.py:252-253)
+    ProfScope ps(kb + HB_PROF_FINAL_LN, st);
     return layernorm_launch(p->x, static_cast<size_t>(seq_len) * D, static_cast<const float*>(p->w[1]),
                             static_cast<const float*>(p->w[2]), c.ln_eps, cls_bf16, cls_f32, n_seq, D, st);
 }
 
 extern "C" {
 
-int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch,
-                      int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
+int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t patch_stride,
+                      size_t chan_stride, size_t row_pitch, int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
                       const float* pos_table, float* cls_f32, void* cls_bf16, void* stream) {
     if (!plan || !image || !embed_w_bf16 || !embed_b || !pos_table) return set_error("hb_vit256_forward: null argument");
     const int seq_len = 257, T = 256;
@@ -259,11 +313,13 @@ int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, si
         return set_error("hb_vit256_forward: im2col operand does not fit the workspace");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = plan->cfg.dim;
-    if (im2col_launch(image, image_is_f32, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, plan->hid, st)) return -1;
+    { ProfScope ps(HB_PROF_IM2COL, st);
+      if (im2col_launch(image, image_is_f32, patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, plan->hid, st)) return -1; }
     GemmArgs g;
     if (gemm_prepare(g, plan->hid, embed_w_bf16, embed_b, HB_EPI_TOKENS_F32, plan->x, n_patches * T, D, 768, pos_table, T)) return -1;
-    if (gemm_launch(g, st)) return -1;
-    if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_patches, seq_len, D, st)) return -1;
+    { ProfScope ps(HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
+    { ProfScope ps(HB_PROF_CLS_ROWS, st);
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_patches, seq_len, D, st)) return -1; }
     return run_blocks(plan, n_patches, seq_len, cls_f32, cls_bf16, st);
 }
 
@@ -278,8 +334,9 @@ int hb_vit4k_forward(hb_vit_plan* plan, const void* cls256_bf16, int n_regions, 
     const int D = plan->cfg.dim;
     GemmArgs g;
     if (gemm_prepare(g, cls256_bf16, phi_w_bf16, phi_b, HB_EPI_TOKENS_GELU_F32, plan->x, n_regions * tokens_per_region, D, in_dim, pos_table, tokens_per_region)) return -1;
-    if (gemm_launch(g, st)) return -1;
-    if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_regions, seq_len, D, st)) return -1;
+    { ProfScope ps(HB_PROF_4K_OFFSET + HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
+    { ProfScope ps(HB_PROF_4K_OFFSET + HB_PROF_CLS_ROWS, st);
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_regions, seq_len, D, st)) return -1; }
     return run_blocks(plan, n_regions, seq_len, out_f32, nullptr, st);
 }
 

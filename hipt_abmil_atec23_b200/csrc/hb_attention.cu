@@ -217,6 +217,7 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
     } else {
         return set_error("hb_attention: head_dim %d not supported (64 or 32)", head_dim);
     }
+    count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }

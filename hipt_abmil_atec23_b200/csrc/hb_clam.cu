@@ -23,7 +23,8 @@
 
 namespace hb {
 
-constexpr int CLAM_CHUNK = 128;     // instances per CTA
+constexpr int CLAM_CHUNK = 128;     // instances per CTA (32 when L1 > 256 so that h1 still fits in shared memory)
+__host__ __device__ inline int clam_chunk_for(int L1) { return L1 <= 256 ? CLAM_CHUNK : 32; }
 constexpr int CLAM_KC = 64;         // feature columns staged per step
 constexpr int CLAM_OB = 16;         // first-layer output columns per pass
 constexpr int CLAM_MAX_MODELS = 8;
@@ -36,7 +37,9 @@ __device__ __forceinline__ float block_reduce_max_128(float v, float* red) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    v = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    const int nw = blockDim.x >> 5;
+    v = red[0];
+    for (int i = 1; i < nw; ++i) v = fmaxf(v, red[i]);
     __syncthreads();
     return v;
 }
@@ -45,7 +48,9 @@ __device__ __forceinline__ float block_reduce_sum_128(float v, float* red) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    v = (red[0] + red[1]) + (red[2] + red[3]);
+    const int nw = blockDim.x >> 5;
+    v = red[0];
+    for (int i = 1; i < nw; ++i) v += red[i];
     __syncthreads();
     return v;
 }
@@ -57,19 +62,20 @@ __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __
                                                                   int L1, int D, int max_chunks,
                                                                   float* __restrict__ a_raw, float* __restrict__ partials) {
     extern __shared__ __align__(16) float smem_clam[];
-    float* sX = smem_clam;                                   // [128][65]
-    float* sW = sX + CLAM_CHUNK * (CLAM_KC + 1);             // [64][16]
-    float* sE = sW + CLAM_KC * CLAM_OB;                      // [128]
-    float* red = sE + CLAM_CHUNK;                            // [4]
-    float* sH = red + 4;                                     // [128][L1+1]
+    const int CH = blockDim.x;                               // instances per CTA (128 or 32)
+    float* sX = smem_clam;                                   // [CH][65]
+    float* sW = sX + CH * (CLAM_KC + 1);                     // [64][16]
+    float* sE = sW + CLAM_KC * CLAM_OB;                      // [CH]
+    float* red = sE + CH;                                    // [4]
+    float* sH = red + 4;                                     // [CH][L1+1]
     const int ldh = L1 + 1;
 
     const int bag = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int start = bag_offsets[bag];
     const int len = bag_offsets[bag + 1] - start;
-    const int i0 = chunk * CLAM_CHUNK;
+    const int i0 = chunk * CH;
     if (i0 >= len) return;
-    const int n_valid = min(CLAM_CHUNK, len - i0);
+    const int n_valid = min(CH, len - i0);
     const bool valid = tid < n_valid;
     const float* xbase = feats + static_cast<size_t>(start + i0) * L0;
 
@@ -88,15 +94,15 @@ __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __
             for (int kc = 0; kc < L0; kc += CLAM_KC) {
                 // stage X[:, kc:kc+64] (coalesced float4) and W1[ob:ob+16, kc:kc+64]^T
 #pragma unroll 4
-                for (int it = 0; it < (CLAM_CHUNK * CLAM_KC / 4) / CLAM_CHUNK; ++it) {
-                    const int idx = tid + it * CLAM_CHUNK;
+                for (int it = 0; it < CLAM_KC / 4; ++it) {
+                    const int idx = tid + it * CH;
                     const int r = idx >> 4, c4 = idx & 15;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < n_valid) v = __ldg(reinterpret_cast<const float4*>(xbase + static_cast<size_t>(r) * L0 + kc) + c4);
                     float* d = sX + r * (CLAM_KC + 1) + c4 * 4;
                     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
                 }
-                for (int idx = tid; idx < CLAM_KC * CLAM_OB; idx += CLAM_CHUNK) {
+                for (int idx = tid; idx < CLAM_KC * CLAM_OB; idx += CH) {
                     const int j = idx / CLAM_KC, k = idx - j * CLAM_KC;      // consecutive threads walk k: coalesced
                     const int col = ob + j;
                     sW[k * CLAM_OB + j] = (col < L1) ? __ldg(W1 + static_cast<size_t>(col) * L0 + kc + k) : 0.f;
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __
         const float sum = block_reduce_sum_128(e, red);     // contains the __syncthreads that publishes sE
         float* out = partials + (static_cast<size_t>(mi * n_bags + bag) * max_chunks + chunk) * (L1 + 2);
         if (tid == 0) { out[0] = mx; out[1] = sum; }
-        for (int j = tid; j < L1; j += CLAM_CHUNK) {
+        for (int j = tid; j < L1; j += CH) {
             float acc = 0.f;
             for (int i = 0; i < n_valid; ++i) acc = fmaf(sE[i], sH[i * ldh + j], acc);
             out[2 + j] = acc;
@@ -167,7 +173,8 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
     float* sL = sM + L1;
     const int bag = blockIdx.x, mi = blockIdx.y, tid = threadIdx.x;
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
-    const int n_chunks = (len + CLAM_CHUNK - 1) / CLAM_CHUNK;
+    const int CH = clam_chunk_for(L1);
+    const int n_chunks = (len + CH - 1) / CH;
     const float* base = partials + static_cast<size_t>(mi * n_bags + bag) * max_chunks * (L1 + 2);
     float gmax = -INFINITY;
     for (int c = 0; c < n_chunks; ++c) gmax = fmaxf(gmax, base[static_cast<size_t>(c) * (L1 + 2)]);
@@ -209,7 +216,8 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
 }
 
 size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1) {
-    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + CLAM_CHUNK - 1) / CLAM_CHUNK;
+    const size_t ch = clam_chunk_for(L1);
+    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + ch - 1) / ch;
     return static_cast<size_t>(n_models) * n_bags * (max_chunks ? max_chunks : 1) * (L1 + 2) * sizeof(float);
 }
 
@@ -233,22 +241,27 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
             models.m[m].p[k] = static_cast<const float*>(weights_host[m * 10 + k]);
             if (!models.m[m].p[k]) return set_error("hb_clam: weight pointer %d of model %d is null", k, m);
         }
-    const int max_chunks = (max_bag_len + CLAM_CHUNK - 1) / CLAM_CHUNK;
+    const int CH = clam_chunk_for(L1);
+    const int max_chunks = (max_bag_len + CH - 1) / CH;
     float* partials = static_cast<float*>(workspace);
     if (max_chunks > 0) {
-        const size_t smem = (static_cast<size_t>(CLAM_CHUNK) * (CLAM_KC + 1) + CLAM_KC * CLAM_OB + CLAM_CHUNK + 4 +
-                             static_cast<size_t>(CLAM_CHUNK) * (L1 + 1)) * sizeof(float);
+        const size_t smem = (static_cast<size_t>(CH) * (CLAM_KC + 1) + CLAM_KC * CLAM_OB + CH + 4 +
+                             static_cast<size_t>(CH) * (L1 + 1)) * sizeof(float);
         if (smem > 220 * 1024) return set_error("hb_clam: L1=%d too large for the fused kernel", L1);
         HB_CUDA_OK(cudaFuncSetAttribute(clam_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         dim3 grid(max_chunks, n_bags);
-        clam_scores_kernel<<<grid, CLAM_CHUNK, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags,
+        ProfScope ps(10, stream);
+        clam_scores_kernel<<<grid, CH, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags,
                                                                 total_instances, L0, L1, D, max_chunks, a_raw, partials);
-        HB_CUDA_OK(cudaGetLastError());
+        count_launch();
+    HB_CUDA_OK(cudaGetLastError());
     }
     dim3 grid2(n_bags, n_models);
+    ProfScope ps2(11, stream);
     clam_combine_kernel<<<grid2, 128, (L1 + C) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                            max_chunks > 0 ? max_chunks : 1, partials,
                                                                            m_out, logits, y_prob, y_hat);
+    count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -268,6 +268,7 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
     const int grid = total < num_sms() ? total : num_sms();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.map_a, g.map_w, g.map_out, g.bias, g.tok_table, g.tok_out,
                                                            g.M, g.N, g.K, g.tokens_per_seq);
+    count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -16,6 +16,14 @@ int num_sms();
         if (_e != cudaSuccess) return ::hb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+void count_launch();                           // every kernel launch of the library bumps hb_launch_count()
+struct ProfScope {                             // CUDA-event bracket on the launching stream when profiling is on
+    ProfScope(int kind, cudaStream_t st);
+    ~ProfScope();
+    cudaStream_t st_;
+    long long idx_;
+};
+
 enum TmapDtype { TMAP_BF16 = 0, TMAP_F32 = 1, TMAP_U8 = 2 };
 // 2-D row-major tensor [rows, cols] with a row pitch in bytes; box [box_rows, box_cols]; SWIZZLE_128B
 // (box_cols * elem_size must be 128 B).  Out-of-bounds elements read as zero and are not written.
@@ -39,8 +47,8 @@ int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, co
                      void* out_bf16, float* out_f32, int rows, int dim, cudaStream_t stream);
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
                      cudaStream_t stream);
-int im2col_launch(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
-                  int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream);
+int im2col_launch(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
+                  int grid_cols, int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream);
 int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, int n_seq, int seq_len, int dim,
                     cudaStream_t stream);
 

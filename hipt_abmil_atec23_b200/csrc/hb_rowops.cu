@@ -91,6 +91,7 @@ int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, co
                                                           static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows);
     else
         return set_error("hb_layernorm: dim %d not supported (384 or 192)", dim);
+    count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -98,9 +99,10 @@ int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, co
 // ------------------------------------------------------------------------------------------------ im2col
 // One thread moves one 16-pixel run (fixed c, image row, token column) = 32 B of bf16 output.
 template <bool F32>
-__global__ void __launch_bounds__(256) im2col_kernel(const uint8_t* __restrict__ img, size_t chan_stride,
-                                                     size_t row_pitch, int grid_cols, int patch_begin, int n_patches,
-                                                     __nv_bfloat16* __restrict__ a, int vec_ok) {
+__global__ void __launch_bounds__(256) im2col_kernel(const uint8_t* __restrict__ img, size_t patch_stride,
+                                                     size_t chan_stride, size_t row_pitch, int grid_cols,
+                                                     int patch_begin, int n_patches, __nv_bfloat16* __restrict__ a,
+                                                     int vec_ok) {
     const size_t total = static_cast<size_t>(n_patches) * 3 * 256 * 16;
     for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -109,9 +111,13 @@ __global__ void __launch_bounds__(256) im2col_kernel(const uint8_t* __restrict__
         const int c = (idx >> 12) % 3;
         const int pl = static_cast<int>(idx / (12288));
         const int p = patch_begin + pl;
-        const int p1 = p / grid_cols, p2 = p - p1 * grid_cols;
+        // grid mode (grid_cols > 0): patch p is tile (p / grid_cols, p % grid_cols) of one region image;
+        // batch mode (grid_cols == 0): patch p is a separate 256x256 image at p * patch_stride.
+        const int p1 = grid_cols > 0 ? p / grid_cols : 0;
+        const int p2 = grid_cols > 0 ? p - p1 * grid_cols : 0;
         const int ty = yrow >> 4, i = yrow & 15;
-        const size_t src = static_cast<size_t>(c) * chan_stride + static_cast<size_t>(p1 * 256 + yrow) * row_pitch +
+        const size_t src = (grid_cols > 0 ? 0 : static_cast<size_t>(p) * patch_stride) +
+                           static_cast<size_t>(c) * chan_stride + static_cast<size_t>(p1 * 256 + yrow) * row_pitch +
                            static_cast<size_t>(p2 * 256 + tx * 16);
         uint32_t pk[8];
         if constexpr (F32) {
@@ -151,8 +157,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const uint8_t* __restrict__
     }
 }
 
-int im2col_launch(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
-                  int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream) {
+int im2col_launch(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
+                  int grid_cols, int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream) {
     if (n_patches <= 0) return 0;
     const size_t total = static_cast<size_t>(n_patches) * 12288;
     size_t blocks = (total + 255) / 256;
@@ -160,15 +166,16 @@ int im2col_launch(const void* image, int image_is_f32, size_t chan_stride, size_
     if (blocks > cap) blocks = cap;
     const size_t esz = image_is_f32 ? 4 : 1;
     const int vec_ok = (reinterpret_cast<uintptr_t>(image) % 16 == 0) && ((chan_stride * esz) % 16 == 0) &&
-                       ((row_pitch * esz) % 16 == 0);
+                       ((row_pitch * esz) % 16 == 0) && ((patch_stride * esz) % 16 == 0);
     if (image_is_f32)
         im2col_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-            static_cast<const uint8_t*>(image), chan_stride, row_pitch, grid_cols, patch_begin, n_patches,
+            static_cast<const uint8_t*>(image), patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches,
             static_cast<__nv_bfloat16*>(a_bf16), vec_ok);
     else
         im2col_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-            static_cast<const uint8_t*>(image), chan_stride, row_pitch, grid_cols, patch_begin, n_patches,
+            static_cast<const uint8_t*>(image), patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches,
             static_cast<__nv_bfloat16*>(a_bf16), vec_ok);
+    count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -187,6 +194,7 @@ int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, in
     if (n_seq <= 0) return 0;
     const int total = n_seq * dim;
     cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cls_token, pos_table, x, n_seq, seq_len, dim);
+    count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }

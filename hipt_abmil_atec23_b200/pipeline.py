@@ -1,0 +1,72 @@
+"""Slide-level inference pipeline: uint8 regions -> HIPT_4K region embeddings -> CLAM_SB fold ensemble.
+
+This is the call a user of the accelerated path makes for one slide (the reference spreads it over three scripts and
+the file system: extract_features_fp.py:159-171 -> .h5/.pt -> eval.py / create_heatmaps.py:34-57).  `run_device` takes
+regions already resident in HBM; `run_host` takes pinned host memory and overlaps the host->device copy of region r+1
+with the ViT-256 pass of region r on a second stream (two staging buffers).
+"""
+import torch
+
+from . import clam_engine
+from .hipt_model_utils import HIPT_MEAN, HIPT_STD
+
+
+class SlidePipeline:
+    def __init__(self, hipt, clam_models, mean=HIPT_MEAN, std=HIPT_STD):
+        self.hipt = hipt
+        self.clam_models = list(clam_models)
+        self.mean, self.std = mean, std
+        self.device = torch.device(hipt.device256)
+        self._stage = None
+        self._copy_stream = None
+
+    # ------------------------------------------------------------------------------------------------ device input
+    @torch.no_grad()
+    def run_device(self, regions_u8):
+        """regions_u8 [R,3,4096,4096] uint8 on the GPU -> dict(features [R,192], logits [F,1,C], y_prob, y_hat, a_raw [F,R])."""
+        feats = self.hipt.forward_regions_u8(regions_u8, self.mean, self.std)
+        return self._pool(feats)
+
+    def _pool(self, feats):
+        R = feats.shape[0]
+        offs = torch.tensor([0, R], dtype=torch.int32)
+        r = clam_engine.forward_bags(self.clam_models, feats, offs, max_bag_len=R, want=("logits", "y_prob", "y_hat"))
+        r["features"] = feats
+        return r
+
+    # -------------------------------------------------------------------------------------------------- host input
+    @torch.no_grad()
+    def run_host(self, regions_u8_pinned):
+        """Same as run_device for a pinned HOST tensor; returns host copies of features / logits / y_prob / y_hat / a_raw.
+        Bytes moved per call: R * 3 * H * W in, R * 192 * 4 + small out."""
+        assert not regions_u8_pinned.is_cuda and regions_u8_pinned.dtype == torch.uint8
+        R, _, W, H = regions_u8_pinned.shape
+        dev = self.device
+        T = (W // 256) * (H // 256)
+        with torch.cuda.device(dev):
+            if self._stage is None or self._stage.shape[1:] != regions_u8_pinned.shape[1:]:
+                self._stage = torch.empty((2,) + tuple(regions_u8_pinned.shape[1:]), dtype=torch.uint8, device=dev)
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            eng = self.hipt.model256._engine(dev)
+            cls_bf16 = torch.empty((R * T, eng.dim), dtype=torch.bfloat16, device=dev)
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            for r in range(R):
+                b = r & 1
+                with torch.cuda.stream(self._copy_stream):
+                    if r >= 2:
+                        self._copy_stream.wait_event(consumed[b])
+                    else:
+                        self._copy_stream.wait_stream(main)
+                    self._stage[b].copy_(regions_u8_pinned[r], non_blocking=True)
+                    copied[b].record(self._copy_stream)
+                main.wait_event(copied[b])
+                eng.forward_patches(self._stage[b], mean=self.mean, std=self.std, want_f32=False,
+                                    out_bf16=cls_bf16[r * T:(r + 1) * T])
+                consumed[b].record(main)
+            feats = self.hipt.model4k._engine(dev).forward_grid(cls_bf16, R, W // 256, H // 256)
+            out = self._pool(feats)
+            host = {k: v.to("cpu", non_blocking=True) for k, v in out.items() if v is not None}
+            main.synchronize()
+        return host

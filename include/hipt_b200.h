@@ -34,6 +34,27 @@ const char* hb_last_error(void);
 /* sm_count / compute capability of the current device; fails unless it is sm_100 */
 int hb_device_check(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Measurement hooks.  hb_launch_count: kernels launched by this library since load.  hb_prof_enable(1) brackets every
+ * kernel launch of the drivers below with CUDA events on the launching stream; hb_prof_read synchronises, sums the
+ * elapsed milliseconds and launch counts per kind (HB_PROF_*, + HB_PROF_4K_OFFSET for the ViT-4K plan) and clears. */
+#define HB_PROF_IM2COL 0
+#define HB_PROF_EMBED_GEMM 1
+#define HB_PROF_CLS_ROWS 2
+#define HB_PROF_LAYERNORM 3
+#define HB_PROF_QKV_GEMM 4
+#define HB_PROF_ATTENTION 5
+#define HB_PROF_PROJ_GEMM 6
+#define HB_PROF_FC1_GEMM 7
+#define HB_PROF_FC2_GEMM 8
+#define HB_PROF_FINAL_LN 9
+#define HB_PROF_CLAM_SCORES 10
+#define HB_PROF_CLAM_COMBINE 11
+#define HB_PROF_4K_OFFSET 16
+#define HB_PROF_KINDS 32
+long long hb_launch_count(void);
+int hb_prof_enable(int on);
+int hb_prof_read(double* ms_by_kind, long long* count_by_kind, int n_kinds);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Single kernels (also the units the parity tests exercise).
  * ---------------------------------------------------------------------------------------------------------------- */
@@ -57,9 +78,10 @@ int hb_attention(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, i
 /* unfold(2,256,256).unfold(3,256,256) + rearrange (HIPT_4K/hipt_4k.py:64-65) composed with the receptive fields of the
  * 16x16/16 patch-embed conv (vision_transformer.py:165-169): image [3, H, W] (uint8 or fp32; element strides given)
  * -> a_bf16 [n_patches*256, 768], row = patch*256 + ty*16 + tx, col = c*256 + i*16 + j.
- * Patch p of the region grid is at (p / grid_cols, p % grid_cols). */
-int hb_im2col_patches(const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch, int grid_cols,
-                      int patch_begin, int n_patches, void* a_bf16, void* stream);
+ * grid_cols > 0: patch p is tile (p / grid_cols, p % grid_cols) of one region image (patch_stride ignored);
+ * grid_cols == 0: patch p is a separate 256x256 image at image + p * patch_stride (a [B,3,256,256] batch). */
+int hb_im2col_patches(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
+                      int grid_cols, int patch_begin, int n_patches, void* a_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * ViT encoder plans: VisionTransformer.forward (vision_transformer.py:248-253) and VisionTransformer4K.forward
@@ -94,8 +116,8 @@ int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes);
  * embed_w_bf16 [dim, 768] / embed_b f32 [dim]: patch_embed.proj with any input normalisation folded in by the caller;
  * pos_table f32 [257, dim]: cls+pos rows after interpolate_pos_encoding (vision_transformer.py:213-233).
  * Outputs the final-LayerNorm CLS rows: cls_f32 [n_patches, dim] and/or cls_bf16 (either may be NULL). */
-int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t chan_stride, size_t row_pitch,
-                      int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
+int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t patch_stride,
+                      size_t chan_stride, size_t row_pitch, int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
                       const float* pos_table, float* cls_f32, void* cls_bf16, void* stream);
 
 /* ViT-4K over n_regions grids of tokens_per_region ViT-256 CLS tokens (hipt_4k.py:72-75; the reshape/transpose at :73

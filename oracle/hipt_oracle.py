@@ -16,6 +16,7 @@ cross-checked in make_golden.py against the reference's second statement of the 
 
 All state dicts use the reference's key names.
 """
+import hashlib
 import math
 
 import torch
@@ -194,3 +195,15 @@ def mil_fc_forward(sd, h, top_k=1):
 def synthetic_region_u8(seed=1, size=4096):
     g = torch.Generator().manual_seed(seed)
     return torch.randint(0, 256, (1, 3, size, size), dtype=torch.uint8, generator=g)
+
+
+def sd_digest(sd):
+    """Order-independent fingerprint of a state dict (float64 sums + a sha1 of a few raw tensors)."""
+    h = hashlib.sha1()
+    tot = 0.0
+    for k in sorted(sd):
+        v = sd[k].detach().double()
+        tot += float(v.sum()) + 0.5 * float((v * v).sum())
+        if v.numel() <= 4096:
+            h.update(sd[k].detach().contiguous().numpy().tobytes())
+    return {"sum": tot, "sha1_small": h.hexdigest(), "n": len(sd)}

@@ -128,7 +128,7 @@ def test_im2col(dtype):
         img = torch.randn((3, H, W), generator=g).cuda()
     grid_cols = W // 256
     n = (H // 256) * grid_cols
-    a = L.im2col_patches(img, grid_cols, 0, n)
+    a = L.im2col_patches(img, 0, n)
     x = img.float().unsqueeze(0)
     patches = x.unfold(2, 256, 256).unfold(3, 256, 256)            # [1,3,p1,p2,256,256]
     patches = patches.permute(0, 2, 3, 1, 4, 5).reshape(n, 3, 256, 256)
@@ -139,5 +139,8 @@ def test_im2col(dtype):
     else:
         assert torch.equal(a, ref.bfloat16())
     # a sub-range of patches
-    a2 = L.im2col_patches(img, grid_cols, 2, 3)
+    a2 = L.im2col_patches(img, 2, 3)
     assert torch.equal(a2, a[2 * 256:5 * 256])
+    # batch mode: separate [B,3,256,256] patches
+    a3 = L.im2col_patches(patches.to(dtype).contiguous(), 1, 4)
+    assert torch.equal(a3, a[256:5 * 256])

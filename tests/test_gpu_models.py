@@ -1,0 +1,219 @@
+"""End-to-end parity of the CUDA path (through the reference-shaped Python API and the C ABI) against the golden
+outputs of the reference (tests/golden/) and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): region / patch features cosine >= 0.999 vs the reference fp32 path with max-abs
+error reported; CLAM attention scores and slide logits within 1e-3 on identical input features; identical labels.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hipt_oracle as O
+from tests.common import seeded_clam, seeded_modules
+
+pytestmark = pytest.mark.gpu
+GOLD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(GOLD_DIR, "hipt_reference_outputs.pt"), map_location="cpu")
+
+
+@pytest.fixture(scope="module")
+def hipt():
+    from hipt_abmil_atec23_b200.hipt_4k import HIPT_4K
+    m256, m4k = seeded_modules(0)
+    return HIPT_4K.from_modules(m256, m4k, DEV, DEV)
+
+
+def _cos(a, b):
+    return F.cosine_similarity(a.double().flatten(), b.double().flatten(), dim=0).item()
+
+
+def _min_row_cos(a, b):
+    return F.cosine_similarity(a.double(), b.double(), dim=1).min().item()
+
+
+def test_vit256_per_block_against_reference(gold, hipt):
+    g = gold["vit256_small"]
+    px = torch.randint(0, 256, (2, 3, 256, 256), dtype=torch.uint8,
+                       generator=torch.Generator().manual_seed(g["pixels_seed"]))
+    x = O.eval_transforms_u8(px).to(DEV)
+    eng = hipt.model256._engine(DEV)
+    try:
+        for depth in (1, 2, 6, 12):
+            eng.set_depth_limit(depth)
+            eng.forward_patches(x)
+            torch.cuda.synchronize()
+            tok = eng.buffer(0, 2 * 257, 384, torch.float32).view(2, 257, 384)[:, :3].cpu()
+            ref = g["tokens_first3_per_block"][depth]
+            err = (tok - ref).abs().max().item()
+            print(f"depth {depth}: max abs {err:.4e}, cos {_cos(tok, ref):.6f}")
+            assert _cos(tok, ref) > 0.9995, depth
+    finally:
+        eng.set_depth_limit(0)
+    cls = hipt.model256(x).cpu()
+    assert cls.shape == (2, 384) and cls.dtype == torch.float32
+    assert _min_row_cos(cls, g["cls"]) >= 0.999
+    print("vit256 cls max abs", (cls - g["cls"]).abs().max().item())
+
+
+def test_tokens_before_blocks_match_oracle(hipt):
+    """Patch embed (im2col + GEMM + bias + pos) and CLS rows against the oracle's prepare_tokens."""
+    px = torch.randint(0, 256, (3, 3, 256, 256), dtype=torch.uint8, generator=torch.Generator().manual_seed(77))
+    x = O.eval_transforms_u8(px)
+    sd = {k: v.detach().cpu() for k, v in hipt.model256.state_dict().items()}
+    ref = O.vit256_tokens(sd, x)
+    eng = hipt.model256._engine(DEV)
+    # depth limit cannot be 0 through the ABI (0 = all), so compare after zero blocks via the u8 path's token buffer:
+    # run one block and check the token rows written by the embed kernels are consistent with block 1 of the oracle.
+    eng.set_depth_limit(1)
+    try:
+        eng.forward_patches(x.to(DEV))
+        torch.cuda.synchronize()
+        tok = eng.buffer(0, 3 * 257, 384, torch.float32).view(3, 257, 384).cpu()
+    finally:
+        eng.set_depth_limit(0)
+    ref1 = O.block(sd, "blocks.0.", ref, 6)
+    assert _cos(tok, ref1) > 0.9999
+    assert (tok - ref1).abs().max().item() < 0.05
+
+
+def test_mini_region_forward_fp32_with_crop(gold, hipt):
+    g = gold["mini_region"]
+    reg = torch.randint(0, 256, g["shape"], dtype=torch.uint8, generator=torch.Generator().manual_seed(g["pixels_seed"]))
+    x = O.eval_transforms_u8(reg).to(DEV)
+    out = hipt(x)
+    assert out.shape == (1, 192) and out.dtype == torch.float32 and out.device == DEV
+    c = _cos(out.cpu(), g["out"])
+    print("mini region cos", c, "max abs", (out.cpu() - g["out"]).abs().max().item())
+    assert c >= 0.999
+    # asset dict variant (hipt_4k.py:79-118)
+    d = hipt.forward_asset_dict(x)
+    assert d["features_cls256"].shape == (6, 384) and d["features_mean256_cls4k"].shape == (1, 576)
+    assert _min_row_cos(torch.from_numpy(d["features_cls256"]), g["cls256"]) >= 0.999
+
+
+def test_u8_path_equals_fp32_path(hipt):
+    reg = torch.randint(0, 256, (2, 3, 512, 768), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).to(DEV)
+    out_u8 = hipt.forward_regions_u8(reg)
+    outs = [hipt(O.eval_transforms_u8(reg[i:i + 1].cpu()).to(DEV)) for i in range(2)]
+    out_f = torch.cat(outs)
+    assert out_u8.shape == (2, 192)
+    assert _min_row_cos(out_u8, out_f) > 0.9995
+
+
+def test_config1_full_region(gold, hipt):
+    g = gold["config1_region"]
+    reg = O.synthetic_region_u8(seed=g["pixels_seed"]).to(DEV)
+    out, cls_bf16 = hipt.forward_regions_u8(reg, return_cls256=True)
+    torch.cuda.synchronize()
+    rc = _min_row_cos(cls_bf16.float().cpu(), g["cls256"])
+    c = _cos(out.cpu(), g["out"])
+    print(f"config1: min patch-CLS cosine {rc:.6f}, region cosine {c:.6f}, region max abs "
+          f"{(out.cpu() - g['out']).abs().max().item():.4e}")
+    assert rc >= 0.999 and c >= 0.999
+    # the reference-API call on the normalised fp32 tensor gives the same region embedding
+    out2 = hipt(O.eval_transforms_u8(reg.cpu()).to(DEV))
+    assert _cos(out2, out) > 0.9995
+
+
+def test_batch_gt_1_rejected_like_reference(hipt):
+    with pytest.raises(RuntimeError):
+        hipt(torch.zeros(2, 3, 256, 256, device=DEV))
+
+
+def test_cpu_input_fails_loudly():
+    m256, _ = seeded_modules(0)
+    with pytest.raises(RuntimeError):
+        m256(torch.zeros(1, 3, 256, 256))
+    with pytest.raises(RuntimeError):
+        seeded_clam()(torch.zeros(4, 192))
+
+
+def test_loader_roundtrip(tmp_path, hipt):
+    """get_vit256 / get_vit4k through a DINO-style checkpoint ('teacher' dict, module./backbone. prefixes, head.* extras)."""
+    from hipt_abmil_atec23_b200.hipt_4k import HIPT_4K
+    sd256 = {"module.backbone." + k: v.cpu() for k, v in hipt.model256.state_dict().items()}
+    sd256["module.head.mlp.0.weight"] = torch.zeros(4, 4)
+    sd4k = {"backbone." + k: v.cpu() for k, v in hipt.model4k.state_dict().items()}
+    p256, p4k = str(tmp_path / "vit256.pth"), str(tmp_path / "vit4k.pth")
+    torch.save({"teacher": sd256, "student": {}}, p256)
+    torch.save({"teacher": sd4k}, p4k)
+    model = HIPT_4K(p256, p4k, DEV, DEV).to(DEV).eval()
+    assert not any(p.requires_grad for p in model.parameters())
+    x = O.eval_transforms_u8(torch.randint(0, 256, (1, 3, 256, 512), dtype=torch.uint8,
+                                           generator=torch.Generator().manual_seed(9))).to(DEV)
+    assert torch.equal(model(x), hipt(x))
+    with pytest.raises(AssertionError):
+        HIPT_4K(str(tmp_path / "missing.pth"), p4k, DEV, DEV)
+
+
+# ------------------------------------------------------------------------------------------------------- CLAM
+def test_clam_cases_against_reference(gold):
+    for name, g in gold["clam"].items():
+        model = seeded_clam(g["size_arg"], g["model_seed"], g["dropout"], g["n_classes"]).to(DEV)
+        bag = torch.randn(g["n"], 192, generator=torch.Generator().manual_seed(g["bag_seed"])).to(DEV)
+        with torch.no_grad():
+            logits, y_prob, y_hat, a_raw, res = model(bag, return_features=True)
+            a_only = model(bag, attention_only=True)
+        assert logits.shape == (1, g["n_classes"]) and a_raw.shape == (1, g["n"]) and y_hat.shape == (1, 1)
+        assert y_hat.dtype == torch.int64
+        for got, ref, what in ((logits, g["logits"], "logits"), (a_raw, g["a_raw"], "a_raw"), (a_only, g["a_raw"], "a_only"),
+                               (y_prob, g["y_prob"], "y_prob"), (res["features"], g["features"], "M")):
+            err = (got.cpu() - ref).abs().max().item()
+            assert err < 1e-3, (name, what, err)
+        assert torch.equal(y_hat.cpu(), g["y_hat"]), name
+
+
+def test_clam_autograd_path_matches_fused(gold):
+    g = gold["clam"]["hipt_smaller_64"]
+    model = seeded_clam(g["size_arg"], g["model_seed"], 0.0, 2).to(DEV)
+    bag = torch.randn(64, 192, generator=torch.Generator().manual_seed(3)).to(DEV)
+    logits, _, _, a_raw, _ = model(bag)                    # grad enabled + trainable params -> torch composition
+    assert logits.requires_grad
+    F.cross_entropy(logits, torch.tensor([1], device=DEV)).backward()
+    with torch.no_grad():
+        l2, _, _, a2, _ = model(bag)
+    assert (logits - l2).abs().max().item() < 1e-4 and (a_raw - a2).abs().max().item() < 1e-4
+
+
+def test_clam_ragged_bags_and_fold_ensemble():
+    from hipt_abmil_atec23_b200 import clam_engine
+    gen = torch.Generator().manual_seed(4)
+    lens = [50, 75, 200, 1000, 5000, 20000, 1, 129, 128, 0, 333]
+    offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    feats = torch.randn(sum(lens), 192, generator=gen)
+    models = [seeded_clam("hipt_smaller", 10 + i) for i in range(5)]
+    r = clam_engine.forward_bags([m.to(DEV) for m in models], feats.to(DEV), offs)
+    torch.cuda.synchronize()
+    for mi, m in enumerate(models):
+        sd = {k: v.cpu() for k, v in m.state_dict().items()}
+        for b, n in enumerate(lens):
+            if n == 0:
+                assert torch.allclose(r["logits"][mi, b].cpu(), sd["classifiers.bias"], atol=1e-6)
+                continue
+            bag = feats[offs[b]:offs[b + 1]]
+            logits, y_prob, y_hat, a_raw, _ = O.clam_sb_forward(sd, bag)
+            assert (r["a_raw"][mi, offs[b]:offs[b + 1]].cpu() - a_raw[0]).abs().max().item() < 1e-3
+            assert (r["logits"][mi, b].cpu() - logits[0]).abs().max().item() < 1e-3
+            assert (r["y_prob"][mi, b].cpu() - y_prob[0]).abs().max().item() < 1e-3
+            assert int(r["y_hat"][mi, b]) == int(y_hat)
+
+
+def test_clam_demo_checkpoint_trained_weights():
+    from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+    g = torch.load(os.path.join(GOLD_DIR, "clam_demo_ckpt.pt"), map_location="cpu")
+    model = CLAM_SB(size_arg="small", dropout=True, n_classes=2)
+    model.load_state_dict(g["state_dict"], strict=True)          # gate at attention_net.3 with dropout=True
+    model = model.to(DEV).eval()
+    bag = torch.randn(300, 1024, generator=torch.Generator().manual_seed(g["bag_seed"])).to(DEV)
+    with torch.no_grad():
+        logits, y_prob, y_hat, a_raw, _ = model(bag)
+    assert (a_raw.cpu() - g["a_raw"]).abs().max().item() < 1e-3 * max(1.0, g["a_raw"].abs().max().item())
+    assert (logits.cpu() - g["logits"]).abs().max().item() < 1e-3 * max(1.0, g["logits"].abs().max().item())
+    assert torch.equal(y_hat.cpu(), g["y_hat"])
