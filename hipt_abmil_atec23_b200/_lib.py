@@ -16,6 +16,7 @@ HB_EPI_BIAS_GELU_BF16 = 1
 HB_EPI_BIAS_RESADD_F32 = 2
 HB_EPI_TOKENS_F32 = 3
 HB_EPI_TOKENS_GELU_F32 = 4
+HB_EPI_BIAS_GELU_FAST_BF16 = 5
 
 
 class HbVitConfig(C.Structure):
@@ -142,7 +143,7 @@ def gemm_bf16(a, w, bias, epilogue, out=None, tok_table=None, tokens_per_seq=0):
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and bias.dtype == torch.float32
     assert a.is_contiguous() and w.is_contiguous() and w.shape[1] == K
     if out is None:
-        if epilogue in (HB_EPI_BIAS_BF16, HB_EPI_BIAS_GELU_BF16):
+        if epilogue in (HB_EPI_BIAS_BF16, HB_EPI_BIAS_GELU_BF16, HB_EPI_BIAS_GELU_FAST_BF16):
             out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
         else:
             raise ValueError("an output tensor is required for this epilogue")

@@ -238,7 +238,7 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
         int rc = 0;
         rc |= gemm_prepare(p->g_qkv[i], p->xn, w[2], static_cast<const float*>(w[3]), HB_EPI_BIAS_BF16, p->qkv, R, 3 * D, D, nullptr, 0);
         rc |= gemm_prepare(p->g_proj[i], p->att, w[4], static_cast<const float*>(w[5]), HB_EPI_BIAS_RESADD_F32, p->x, R, D, D, nullptr, 0);
-        rc |= gemm_prepare(p->g_fc1[i], p->xn, w[8], static_cast<const float*>(w[9]), HB_EPI_BIAS_GELU_BF16, p->hid, R, H, D, nullptr, 0);
+        rc |= gemm_prepare(p->g_fc1[i], p->xn, w[8], static_cast<const float*>(w[9]), HB_EPI_BIAS_GELU_FAST_BF16, p->hid, R, H, D, nullptr, 0);
         rc |= gemm_prepare(p->g_fc2[i], p->hid, w[10], static_cast<const float*>(w[11]), HB_EPI_BIAS_RESADD_F32, p->x, R, D, H, nullptr, 0);
         if (rc) { delete p; return -1; }
     }

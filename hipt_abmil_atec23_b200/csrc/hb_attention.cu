@@ -117,7 +117,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[HD / 16][4], uin
 }
 
 template <int HD>
-__global__ void __launch_bounds__(512) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         __nv_bfloat16* __restrict__ out, int seq_len, int heads,
                                                         float scale_log2) {
     extern __shared__ __align__(128) uint8_t smem_attn[];
@@ -200,7 +200,7 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
     if (smem > 200 * 1024) return set_error("hb_attention: seq_len %d too long for the single-pass kernel", seq_len);
     const int q_tiles = s_pad / 16;
     int warps = (q_tiles + 1) / 2;
-    if (warps > 16) warps = 16;
+    if (warps > 9) warps = 9;
     if (warps < 1) warps = 1;
     const float scale_log2 = scale * 1.4426950408889634f;
     const unsigned grid = static_cast<unsigned>(n_seq) * heads;

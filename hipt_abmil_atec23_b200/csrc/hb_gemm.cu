@@ -3,7 +3,7 @@
 //   warp 0 : TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B, mbarrier complete_tx)
 //   warp 1 : MMA issuer    (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 per instr)
 //   warp 2 : TMEM allocator (2 x BN fp32 accumulator columns, double buffered against the epilogue)
-//   warps 4-7 : epilogue   (tcgen05.ld -> bias / exact-erf GELU -> swizzled smem -> TMA store or TMA reduce-add)
+//   warps 4-11 : epilogue  (two warpgroups; tcgen05.ld -> bias / GELU -> swizzled smem -> TMA store or TMA reduce-add)
 //
 // This replaces the nn.Linear call sites of the reference's ViT blocks (HIPT_4K/vision_transformer.py:93-95 fc1/fc2,
 // :114-116 qkv/proj; HIPT_4K/vision_transformer4k.py:169 phi) and, fed with an im2col'd region, the patch-embed
@@ -16,8 +16,8 @@ namespace hb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle span
-constexpr int GEMM_THREADS = 256;    // 8 warps: producer, mma, tmem-alloc, spare, 4x epilogue
-constexpr int GEMM_EPI_THREADS = 128;
+constexpr int GEMM_THREADS = 384;    // 12 warps: producer, mma, tmem-alloc, spare, 2 x 4 epilogue
+constexpr int GEMM_EPI_THREADS = 128; // per epilogue warpgroup
 constexpr int STAGE_BYTES_OUT = 128 * 128;   // 128 rows x 128 B staging chunk for the TMA store
 
 template <int BN>
@@ -30,7 +30,8 @@ struct GemmCfg {
 };
 
 // Epilogue kinds (mirrored in include/hipt_b200.h as HB_EPI_*)
-enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2, EPI_TOKENS_F32 = 3, EPI_TOKENS_GELU_F32 = 4 };
+enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2, EPI_TOKENS_F32 = 3, EPI_TOKENS_GELU_F32 = 4,
+              EPI_BIAS_GELU_FAST_BF16 = 5 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -40,7 +41,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  int tokens_per_seq) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+    constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_FAST_BF16);
     constexpr bool OUT_TOKENS = (EPI == EPI_TOKENS_F32 || EPI == EPI_TOKENS_GELU_F32);
     constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;      // 128 B of output per row per chunk
 
@@ -66,7 +67,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], GEMM_EPI_THREADS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * GEMM_EPI_THREADS); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -128,12 +129,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue
-        const int ew = warp & 3;                       // TMEM lane quadrant of this warp
+        // ------------------------------------------------------------------ epilogue (2 warpgroups)
+        // Each warpgroup covers all 128 accumulator rows (warp & 3 = TMEM lane quadrant) and takes every other
+        // 128-byte-wide column chunk of the tile, with its own staging buffer, named barrier and TMA-store thread.
+        const int wg = (warp - 4) >> 2;
+        const int ew = warp & 3;
         const int row_in_tile = ew * 32 + lane;
-        const bool store_leader = (warp == 4 && lane == 0);
+        const bool store_leader = ((warp & 3) == 0 && lane == 0);
+        uint8_t* stage_buf = smem_o + wg * STAGE_BYTES_OUT;
+        uint8_t* row_ptr = stage_buf + row_in_tile * 128;
+        const int sw = row_in_tile & 7;
+        constexpr int NCHUNK = BN / CHUNK_COLS;
         uint32_t it = 0;
-        uint32_t chunk_ctr = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int m0 = (tile / n_tiles) * GEMM_BM;
             const int n0 = (tile % n_tiles) * BN;
@@ -141,6 +148,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+            const int c_first = (wg + it * NCHUNK) & 1;     // alternate so odd chunk counts balance across tiles
 
             if constexpr (OUT_TOKENS) {
                 // fp32 token rows written straight to global with a per-sequence row remap (+1 for the CLS slot)
@@ -150,7 +158,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int tok = row - seq * tokens_per_seq;
                 const size_t out_row = static_cast<size_t>(seq) * (tokens_per_seq + 1) + 1 + tok;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = c_first; c < NCHUNK; c += 2) {
                     uint32_t v[32];
                     tmem_ld_32x32(taddr_row + c * 32, v);
                     tmem_ld_wait();
@@ -175,19 +183,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&acc_empty[as]);
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN / CHUNK_COLS; ++c, ++chunk_ctr) {
-                    uint8_t* stage_buf = smem_o + (chunk_ctr & 1) * STAGE_BYTES_OUT;
-                    // the TMA store that last read this staging buffer (2 chunks ago) must have drained it
-                    if (store_leader) tma_store_wait_read<1>();
-                    named_bar_sync(1, GEMM_EPI_THREADS);
-
-                    uint8_t* row_ptr = stage_buf + row_in_tile * 128;
-                    const int sw = row_in_tile & 7;
+                for (int c = c_first; c < NCHUNK; c += 2) {
                     if constexpr (OUT_BF16) {
+                        uint32_t pk[32];                 // 64 bf16 of this row
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint32_t v[32];
@@ -195,44 +195,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             tmem_ld_wait();
                             const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 64 + h * 32);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {       // 4 x (8 values -> one 16 B chunk)
-                                const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
-                                float f[8];
-                                f[0] = __uint_as_float(v[8 * j + 0]) + b0.x; f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
-                                f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
-                                f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
-                                f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b = __ldg(b4 + j);
+                                float f0 = __uint_as_float(v[4 * j + 0]) + b.x, f1 = __uint_as_float(v[4 * j + 1]) + b.y;
+                                float f2 = __uint_as_float(v[4 * j + 2]) + b.z, f3 = __uint_as_float(v[4 * j + 3]) + b.w;
                                 if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                                    f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+                                } else if constexpr (EPI == EPI_BIAS_GELU_FAST_BF16) {
+                                    f0 = gelu_fast(f0); f1 = gelu_fast(f1); f2 = gelu_fast(f2); f3 = gelu_fast(f3);
                                 }
-                                uint4 pk;
-                                pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
-                                pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
-                                const int chunk16 = h * 4 + j;
-                                *reinterpret_cast<uint4*>(row_ptr + ((chunk16 ^ sw) << 4)) = pk;
+                                pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
+                                pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
                             }
                         }
+                        // the TMA store that last read this warpgroup's staging buffer must have drained it
+                        if (store_leader) tma_store_wait_read<0>();
+                        named_bar_sync(1 + wg, GEMM_EPI_THREADS);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<uint4*>(row_ptr + ((q ^ sw) << 4)) =
+                                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                     } else {
                         uint32_t v[32];
                         tmem_ld_32x32(taddr_row + c * 32, v);
                         tmem_ld_wait();
                         const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+                        float4 r[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b = __ldg(b4 + j);
-                            float4 r;
-                            r.x = __uint_as_float(v[4 * j + 0]) + b.x; r.y = __uint_as_float(v[4 * j + 1]) + b.y;
-                            r.z = __uint_as_float(v[4 * j + 2]) + b.z; r.w = __uint_as_float(v[4 * j + 3]) + b.w;
-                            *reinterpret_cast<float4*>(row_ptr + ((j ^ sw) << 4)) = r;
+                            r[j].x = __uint_as_float(v[4 * j + 0]) + b.x; r[j].y = __uint_as_float(v[4 * j + 1]) + b.y;
+                            r[j].z = __uint_as_float(v[4 * j + 2]) + b.z; r[j].w = __uint_as_float(v[4 * j + 3]) + b.w;
                         }
-                    }
-                    if (c == BN / CHUNK_COLS - 1) {     // accumulator fully drained: hand TMEM back to the MMA warp
-                        tc_fence_before();
-                        mbar_arrive(&acc_empty[as]);
+                        if (store_leader) tma_store_wait_read<0>();
+                        named_bar_sync(1 + wg, GEMM_EPI_THREADS);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(row_ptr + ((j ^ sw) << 4)) = r[j];
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, GEMM_EPI_THREADS);
+                    named_bar_sync(1 + wg, GEMM_EPI_THREADS);
                     if (store_leader) {
                         if constexpr (EPI == EPI_BIAS_RESADD_F32)
                             tma_reduce_add_2d(&map_out, stage_buf, n0 + c * CHUNK_COLS, m0);
@@ -242,6 +243,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }
+            // this thread has issued (and waited for) its last TMEM load of the tile: hand the buffer back
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
         }
         if (store_leader) tma_store_wait_all<0>();
     }
@@ -281,6 +285,7 @@ static int launch_gemm_bn(const GemmArgs& g, cudaStream_t stream) {
         case EPI_BIAS_RESADD_F32: return launch_gemm_t<BN, EPI_BIAS_RESADD_F32>(g, stream);
         case EPI_TOKENS_F32: return launch_gemm_t<BN, EPI_TOKENS_F32>(g, stream);
         case EPI_TOKENS_GELU_F32: return launch_gemm_t<BN, EPI_TOKENS_GELU_F32>(g, stream);
+        case EPI_BIAS_GELU_FAST_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_FAST_BF16>(g, stream);
     }
     return set_error("hb_gemm: unknown epilogue %d", g.epi);
 }
@@ -303,7 +308,7 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     g.tok_table = tok_table; g.tok_out = nullptr; g.tokens_per_seq = tokens_per_seq;
     if (encode_tmap_2d(&g.map_a, TMAP_BF16, A, M, K, static_cast<uint64_t>(K) * 2, GEMM_BM, GEMM_BK)) return -1;
     if (encode_tmap_2d(&g.map_w, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn, GEMM_BK)) return -1;
-    if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) {
+    if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16) {
         if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, GEMM_BM, 64)) return -1;
     } else if (epi == EPI_BIAS_RESADD_F32) {
         if (encode_tmap_2d(&g.map_out, TMAP_F32, out, M, N, static_cast<uint64_t>(N) * 4, GEMM_BM, 32)) return -1;

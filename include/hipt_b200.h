@@ -28,6 +28,7 @@ extern "C" {
 #define HB_EPI_BIAS_RESADD_F32 2  /* out_f32[M,N]  += A W^T + bias     (residual stream, in place)  */
 #define HB_EPI_TOKENS_F32 3       /* token rows: out_f32[(r/T)*(T+1)+1+r%T, :] = A W^T + bias + table[1+r%T, :] */
 #define HB_EPI_TOKENS_GELU_F32 4  /* same with gelu_erf applied before the table add               */
+#define HB_EPI_BIAS_GELU_FAST_BF16 5 /* as 1 with the tanh-form GELU fitted to erf (|err| <= 3e-4 |x|), MLP hot path */
 
 int hb_abi_version(void);
 const char* hb_last_error(void);
