@@ -9,10 +9,18 @@
 // One CTA per (sequence, head): Q, K, V are staged once in shared memory (cp.async, XOR-swizzled 16 B chunks), each
 // warp owns 16-query tiles and runs a flash-style online softmax over 64-key chunks with bf16 tensor-core MMAs
 // (fp32 accumulate, fp32 softmax statistics, exp2 with log2(e) folded into the scale).
+#include <stdlib.h>
+
 #include "hb_ptx.cuh"
 #include "hb_internal.h"
 
 namespace hb {
+
+static bool attention_force_legacy() {      // test hook: HB_ATTENTION_LEGACY=1 routes every shape through mma.sync
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HB_ATTENTION_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 
 template <int HD>
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
@@ -191,10 +199,329 @@ __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* 
     }
 }
 
+// =====================================================================================================================
+// tcgen05 path for the ViT-256 shape (seq_len 257, head_dim 64).
+//
+// One persistent CTA per SM walks (sequence, head) items; each item is two 128-query tiles plus the single 257th query.
+//   warp 0      TMA producer: K [272 x 64] and V [272 x 64] (double buffered across items) and the two Q tiles, all
+//               SWIZZLE_128B boxes of the qkv matrix (rows past the end of the matrix read as zero)
+//   warp 1      MMA issuer: S = Q K^T as M128 x N256 + M128 x N16 (keys 256..271) into 272 TMEM columns, then
+//               O += P V over five key atoms (4 x 64 + 16) with P read K-major from shared memory and V read MN-major
+//               in place (no transpose); QK^T of the next tile is issued before P V of the current one
+//   warp 2      TMEM allocator
+//   warp 3      the 257th query row on the legacy mma.sync path against the same K / V tiles
+//   warps 4-11  two softmax warpgroups; thread = query row, warpgroup 0 owns keys 0..127, warpgroup 1 keys 128..256:
+//               S row slice -> registers (one TMEM read), row max exchanged through shared memory, exp2 with the scale
+//               folded in, P atoms written as bf16 into the swizzled layout the MMA consumes, row sums exchanged, then
+//               each warpgroup normalises and stores half of O's 64 columns.
+// Softmax statistics stay fp32; P is rounded to bf16 exactly like the legacy kernel.
+// =====================================================================================================================
+constexpr int ATC_THREADS = 384;
+constexpr int ATC_S = 257;
+constexpr int ATC_SPAD = 272;
+constexpr int ATC_KV_BYTES = ATC_SPAD * 128;            // 34816: [272 keys][64 bf16]
+constexpr int ATC_TILE_BYTES = 128 * 128;               // 16384: one 128-row x 128-byte swizzled tile
+constexpr int ATC_P_SLOTS = 3;
+constexpr int ATC_SMEM = 4 * ATC_KV_BYTES + 2 * ATC_TILE_BYTES + ATC_P_SLOTS * ATC_TILE_BYTES + 4096 + 256 + 1024;
+constexpr int ATC_TMEM_COLS = 512;
+constexpr int ATC_O_COL = 320;
+
+__device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map16,
+                    const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_items, int heads,
+                    float scale_log2) {
+    extern __shared__ uint8_t smem_raw_atc[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_atc) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;                                   // [2][34816]
+    uint8_t* sV = sK + 2 * ATC_KV_BYTES;                  // [2][34816]
+    uint8_t* sQ = sV + 2 * ATC_KV_BYTES;                  // [2 tiles][16384]
+    uint8_t* sP = sQ + 2 * ATC_TILE_BYTES;                // [3 slots][16384]
+    float* stat_max = reinterpret_cast<float*>(sP + ATC_P_SLOTS * ATC_TILE_BYTES);   // [2 parity][2 wg][128]
+    float* stat_sum = stat_max + 512;                                                 // [2 parity][2 wg][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_sum + 512);
+    uint64_t* kv_full = bars;            // [2]
+    uint64_t* kv_empty = bars + 2;       // [2]
+    uint64_t* q_full = bars + 4;
+    uint64_t* q_empty = bars + 5;
+    uint64_t* s_full = bars + 6;
+    uint64_t* s_free = bars + 7;
+    uint64_t* o_full = bars + 8;
+    uint64_t* o_free = bars + 9;
+    uint64_t* p_full = bars + 10;        // [3]
+    uint64_t* p_empty = bars + 13;       // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = heads * 64;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        mbar_init(s_full, 1); mbar_init(s_free, 256);
+        mbar_init(o_full, 1); mbar_init(o_free, 256);
+        for (int i = 0; i < ATC_P_SLOTS; ++i) { mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, ATC_TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    int my_items = 0;
+    if (static_cast<int>(blockIdx.x) < n_items) my_items = (n_items - 1 - blockIdx.x) / gridDim.x + 1;
+    const int n_tiles = my_items * 2;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int it = 0; it < my_items; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int seq = item / heads, h = item - seq * heads;
+                const int row0 = seq * ATC_S;
+                const int st = it & 1;
+                mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * ATC_KV_BYTES);
+                uint8_t* k = sK + st * ATC_KV_BYTES;
+                uint8_t* v = sV + st * ATC_KV_BYTES;
+                tma_load_2d(k, &map128, &kv_full[st], D + h * 64, row0);
+                tma_load_2d(k + ATC_TILE_BYTES, &map128, &kv_full[st], D + h * 64, row0 + 128);
+                tma_load_2d(k + 2 * ATC_TILE_BYTES, &map16, &kv_full[st], D + h * 64, row0 + 256);
+                tma_load_2d(v, &map128, &kv_full[st], 2 * D + h * 64, row0);
+                tma_load_2d(v + ATC_TILE_BYTES, &map128, &kv_full[st], 2 * D + h * 64, row0 + 128);
+                tma_load_2d(v + 2 * ATC_TILE_BYTES, &map16, &kv_full[st], 2 * D + h * 64, row0 + 256);
+                mbar_wait(q_empty, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(q_full, 2 * ATC_TILE_BYTES);
+                tma_load_2d(sQ, &map128, q_full, h * 64, row0);
+                tma_load_2d(sQ + ATC_TILE_BYTES, &map128, q_full, h * 64, row0 + 128);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        if (lane == 0 && n_tiles > 0) {
+            constexpr uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
+            constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);      // B (= V) is MN-major
+            auto issue_qk = [&](int tile) {
+                const int it = tile >> 1, t = tile & 1, st = it & 1;
+                if (t == 0) {
+                    mbar_wait(&kv_full[st], (it >> 1) & 1);
+                    mbar_wait(q_full, it & 1);
+                }
+                tc_fence_after();
+                const uint64_t dq = umma_desc_k128(smem_u32(sQ + t * ATC_TILE_BYTES));
+                const uint64_t dk = umma_desc_k128(smem_u32(sK + st * ATC_KV_BYTES));
+                const uint64_t dk_tail = umma_desc_k128(smem_u32(sK + st * ATC_KV_BYTES + 2 * ATC_TILE_BYTES));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    umma_bf16_ss(tmem_base, dq + 2 * kk, dk + 2 * kk, idesc_s256, kk != 0);
+                    umma_bf16_ss(tmem_base + 256, dq + 2 * kk, dk_tail + 2 * kk, idesc_s16, kk != 0);
+                }
+                umma_commit(s_full);
+                if (t == 1) umma_commit(q_empty);
+            };
+            issue_qk(0);
+            for (int tile = 0; tile < n_tiles; ++tile) {
+                const int it = tile >> 1, t = tile & 1, st = it & 1;
+                if (tile + 1 < n_tiles) {
+                    mbar_wait(s_free, tile & 1);               // S(tile) now lives in the softmax registers
+                    issue_qk(tile + 1);
+                }
+                if (tile > 0) mbar_wait(o_free, (tile - 1) & 1);
+                const uint32_t v_base = smem_u32(sV + st * ATC_KV_BYTES);
+                for (int a = 0; a < 5; ++a) {
+                    const int ga = tile * 5 + a, slot = ga % ATC_P_SLOTS;
+                    mbar_wait(&p_full[slot], (ga / ATC_P_SLOTS) & 1);
+                    tc_fence_after();
+                    const uint64_t dp = umma_desc_k128(smem_u32(sP + slot * ATC_TILE_BYTES));
+                    const int ksteps = (a < 4) ? 4 : 1;
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        const uint64_t dv = umma_desc_k128(v_base + (a * 64 + kk * 16) * 128);
+                        umma_bf16_ss(tmem_base + ATC_O_COL, dp + 2 * kk, dv, idesc_pv, (a | kk) != 0);
+                    }
+                    umma_commit(&p_empty[slot]);
+                }
+                umma_commit(o_full);
+                if (t == 1) umma_commit(&kv_empty[st]);
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------------------------------ query row 256
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int seq = item / heads, h = item - seq * heads;
+            const int st = it & 1;
+            const size_t row = static_cast<size_t>(seq) * ATC_S + 256;
+            uint32_t qf[4][4];
+            {
+                const uint32_t* qrow = reinterpret_cast<const uint32_t*>(qkv + row * 3 * D + h * 64);
+                const bool own = (lane >> 2) == 0;            // A-fragment rows 0 (valid) and 8 (padding)
+                const int t = lane & 3;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    qf[kk][0] = own ? __ldg(qrow + kk * 8 + t) : 0u;
+                    qf[kk][2] = own ? __ldg(qrow + kk * 8 + 4 + t) : 0u;
+                    qf[kk][1] = 0u; qf[kk][3] = 0u;
+                }
+            }
+            mbar_wait(&kv_full[st], (it >> 1) & 1);
+            const uint32_t k_addr = smem_u32(sK + st * ATC_KV_BYTES), v_addr = smem_u32(sV + st * ATC_KV_BYTES);
+            float o[8][4];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+            float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+            for (int c = 0; c < 4; ++c) attn_chunk<64, 4, false>(qf, k_addr, v_addr, c * 64, ATC_S, scale_log2, o, m, l, lane);
+            attn_chunk<64, 1, true>(qf, k_addr, v_addr, 256, ATC_S, scale_log2, o, m, l, lane);
+            float l0 = l[0];
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            if ((lane >> 2) == 0) {
+                const float inv = 1.0f / l0;
+                __nv_bfloat16* orow = out + row * D + h * 64 + (lane & 3) * 2;
+#pragma unroll
+                for (int d = 0; d < 8; ++d)
+                    *reinterpret_cast<uint32_t*>(orow + d * 8) = pack_bf16x2(o[d][0] * inv, o[d][1] * inv);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&kv_empty[st]);
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------------------------------ softmax warpgroups
+        const int wg = (warp - 4) >> 2;
+        const int r = (warp & 3) * 32 + lane;                 // query row inside the tile = TMEM lane
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const int sw = r & 7;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            const int it = tile >> 1, t = tile & 1;
+            const int item = blockIdx.x + it * gridDim.x;
+            const int seq = item / heads, h = item - seq * heads;
+            const int par = tile & 1;
+            mbar_wait(s_full, par);
+            tc_fence_after();
+            uint32_t sv[128];
+            uint32_t tail[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_x32_ptr(t_row + wg * 128 + c * 32, sv + c * 32);
+            if (wg == 1) tmem_ld_x32_ptr(t_row + 256, tail);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+
+            float mx = __uint_as_float(sv[0]);
+#pragma unroll
+            for (int j = 1; j < 128; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+            if (wg == 1) mx = fmaxf(mx, __uint_as_float(tail[0]));
+            stat_max[(par * 2 + wg) * 128 + r] = mx;
+            named_bar_sync(3, 256);
+            mx = fmaxf(mx, stat_max[(par * 2 + (wg ^ 1)) * 128 + r]);
+            const float neg_m = -mx * scale_log2;
+            float sum = 0.f;
+#pragma unroll
+            for (int a2 = 0; a2 < 2; ++a2) {                  // the two full 64-key atoms of this warpgroup
+                const int a = wg * 2 + a2;
+                const int ga = tile * 5 + a, slot = ga % ATC_P_SLOTS;
+                uint32_t pk[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[a2 * 64 + 2 * j]), scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[a2 * 64 + 2 * j + 1]), scale_log2, neg_m));
+                    sum += p0 + p1;
+                    pk[j] = pack_bf16x2(p0, p1);
+                }
+                mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
+                uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                fence_proxy_async_smem();
+                mbar_arrive(&p_full[slot]);
+            }
+            if (wg == 1) {                                    // tail atom: key 256 + 15 masked keys
+                const int ga = tile * 5 + 4, slot = ga % ATC_P_SLOTS;
+                const float p0 = ex2_approx(fmaf(__uint_as_float(tail[0]), scale_log2, neg_m));
+                sum += p0;
+                mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
+                uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
+                *reinterpret_cast<uint4*>(prow + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(prow + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                fence_proxy_async_smem();
+                mbar_arrive(&p_full[slot]);
+            }
+            stat_sum[(par * 2 + wg) * 128 + r] = sum;
+            mbar_wait(o_full, par);
+            tc_fence_after();
+            named_bar_sync(3, 256);
+            const float inv = 1.0f / (sum + stat_sum[(par * 2 + (wg ^ 1)) * 128 + r]);
+            uint32_t ov[32];
+            tmem_ld_x32_ptr(t_row + ATC_O_COL + wg * 32, ov);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_free);
+            uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seq) * ATC_S + t * 128 + r) * D + h * 64 + wg * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
+                w.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
+                w.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
+                w.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
+                dst[q] = w;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, ATC_TMEM_COLS);
+}
+
+static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int heads, float scale,
+                               cudaStream_t stream) {
+    const int D = heads * 64;
+    const uint64_t rows = static_cast<uint64_t>(n_seq) * ATC_S;
+    CUtensorMap map128, map16;
+    if (encode_tmap_2d(&map128, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 128, 64)) return -1;
+    if (encode_tmap_2d(&map16, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 16, 64)) return -1;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        attr_done = true;
+    }
+    const int n_items = n_seq * heads;
+    const int grid = n_items < num_sms() ? n_items : num_sms();
+    attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
+        map128, map16, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), n_items,
+        heads, scale * 1.4426950408889634f);
+    count_launch();
+    HB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
                      cudaStream_t stream) {
     if (n_seq <= 0) return 0;
     if (seq_len <= 0 || heads <= 0) return set_error("hb_attention: bad shape");
+    if (seq_len == ATC_S && head_dim == 64 && !attention_force_legacy())
+        return attention_tc_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream);
     const int s_pad = (seq_len + 15) & ~15;
     const size_t smem = static_cast<size_t>(3) * s_pad * head_dim * 2;
     if (smem > 200 * 1024) return set_error("hb_attention: seq_len %d too long for the single-pass kernel", seq_len);

@@ -109,7 +109,8 @@ def test_layernorm_strided_cls_rows():
 
 
 @pytest.mark.parametrize("n_seq,S,heads,hd", [(4, 257, 6, 64), (2, 257, 6, 32), (3, 64, 6, 64), (2, 100, 6, 32),
-                                              (1, 17, 6, 64), (2, 128, 6, 64)])
+                                              (1, 17, 6, 64), (2, 128, 6, 64), (1, 257, 6, 64), (256, 257, 6, 64),
+                                              (37, 257, 6, 64), (3, 257, 2, 64)])
 def test_attention(n_seq, S, heads, hd):
     L = _lib()
     D = heads * hd
