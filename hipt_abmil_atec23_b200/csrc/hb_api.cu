@@ -53,14 +53,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                   uint32_t box_rows, uint32_t box_cols) {
+                   uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMapDataType cdt = dt == TMAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                               : dt == TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                : CU_TENSOR_MAP_DATA_TYPE_UINT8;
     const uint32_t esz = dt == TMAP_BF16 ? 2 : dt == TMAP_F32 ? 4 : 1;
-    if (box_cols * esz != 128) return set_error("encode_tmap_2d: box inner extent must be 128 B");
+    if (box_cols * esz != static_cast<uint32_t>(swizzle_bytes) || (swizzle_bytes != 128 && swizzle_bytes != 64))
+        return set_error("encode_tmap_2d: box inner extent must equal the swizzle span (128 or 64 B)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0)
         return set_error("encode_tmap_2d: base/pitch must be 16 B aligned");
     cuuint64_t dims[2] = {cols, rows};
@@ -68,7 +69,8 @@ int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t ro
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, cdt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return 0;
 }

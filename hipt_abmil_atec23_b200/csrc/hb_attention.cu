@@ -221,8 +221,9 @@ constexpr int ATC_S = 257;
 constexpr int ATC_SPAD = 272;
 constexpr int ATC_KV_BYTES = ATC_SPAD * 128;            // 34816: [272 keys][64 bf16]
 constexpr int ATC_TILE_BYTES = 128 * 128;               // 16384: one 128-row x 128-byte swizzled tile
-constexpr int ATC_P_SLOTS = 3;
-constexpr int ATC_SMEM = 4 * ATC_KV_BYTES + 2 * ATC_TILE_BYTES + ATC_P_SLOTS * ATC_TILE_BYTES + 4096 + 256 + 1024;
+constexpr int ATC_P_SLOTS = 2;
+constexpr int ATC_O_STAGE_BYTES = 128 * 64;             // one warpgroup's half of an O tile: 128 rows x 32 bf16
+constexpr int ATC_SMEM = 4 * ATC_KV_BYTES + 2 * ATC_TILE_BYTES + ATC_P_SLOTS * ATC_TILE_BYTES + 2 * ATC_O_STAGE_BYTES + 4096 + 256 + 1024;
 constexpr int ATC_TMEM_COLS = 512;
 constexpr int ATC_O_COL = 320;
 
@@ -238,6 +239,18 @@ __device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x16_ptr(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -246,7 +259,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map16,
-                    const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_items, int heads,
+                    const __grid_constant__ CUtensorMap map_out, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_items, int heads,
                     float scale_log2) {
     extern __shared__ uint8_t smem_raw_atc[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_atc) + 1023) & ~uintptr_t(1023));
@@ -254,7 +267,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
     uint8_t* sV = sK + 2 * ATC_KV_BYTES;                  // [2][34816]
     uint8_t* sQ = sV + 2 * ATC_KV_BYTES;                  // [2 tiles][16384]
     uint8_t* sP = sQ + 2 * ATC_TILE_BYTES;                // [3 slots][16384]
-    float* stat_max = reinterpret_cast<float*>(sP + ATC_P_SLOTS * ATC_TILE_BYTES);   // [2 parity][2 wg][128]
+    uint8_t* sO = sP + ATC_P_SLOTS * ATC_TILE_BYTES;      // [2 wg][128 rows x 64 B], SWIZZLE_64B staging for the TMA store
+    float* stat_max = reinterpret_cast<float*>(sO + 2 * ATC_O_STAGE_BYTES);          // [2 parity][2 wg][128]
     float* stat_sum = stat_max + 512;                                                 // [2 parity][2 wg][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stat_sum + 512);
     uint64_t* kv_full = bars;            // [2]
@@ -265,14 +279,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
     uint64_t* s_free = bars + 7;
     uint64_t* o_full = bars + 8;
     uint64_t* o_free = bars + 9;
-    uint64_t* p_full = bars + 10;        // [3]
-    uint64_t* p_empty = bars + 13;       // [3]
+    uint64_t* p_full = bars + 10;        // [ATC_P_SLOTS]
+    uint64_t* p_empty = bars + 13;       // [ATC_P_SLOTS]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = heads * 64;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); tma_prefetch_desc(&map_out); }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
         mbar_init(q_full, 1); mbar_init(q_empty, 1);
@@ -406,87 +420,127 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------------------------------ softmax warpgroups
+        // Software-pipelined by one tile: S(tile) is pulled into registers and its row max computed BEFORE the
+        // epilogue of tile-1, so the wait for the last P V MMAs of tile-1 hides behind useful work, and one named
+        // barrier per tile publishes both max(tile) and sum(tile-1) between the two warpgroups.
         const int wg = (warp - 4) >> 2;
         const int r = (warp & 3) * 32 + lane;                 // query row inside the tile = TMEM lane
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const int sw = r & 7;
-        for (int tile = 0; tile < n_tiles; ++tile) {
-            const int it = tile >> 1, t = tile & 1;
-            const int item = blockIdx.x + it * gridDim.x;
-            const int seq = item / heads, h = item - seq * heads;
+        float prev_sum = 0.f;
+        int prev_row0 = 0, prev_col = 0;                      // TMA-store coordinates of tile-1's half tile
+        int seq = 0, h = 0;
+        const bool store_leader = ((warp & 3) == 0 && lane == 0);
+        uint8_t* o_stage = sO + wg * ATC_O_STAGE_BYTES;
+        uint8_t* o_row = o_stage + r * 64;
+        const int sw64 = (r >> 1) & 3;
+        for (int tile = 0; tile <= n_tiles; ++tile) {
             const int par = tile & 1;
-            mbar_wait(s_full, par);
-            tc_fence_after();
+            const bool cur = tile < n_tiles;
             uint32_t sv[128];
-            uint32_t tail[32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_x32_ptr(t_row + wg * 128 + c * 32, sv + c * 32);
-            if (wg == 1) tmem_ld_x32_ptr(t_row + 256, tail);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(s_free);
-
-            float mx = __uint_as_float(sv[0]);
-#pragma unroll
-            for (int j = 1; j < 128; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
-            if (wg == 1) mx = fmaxf(mx, __uint_as_float(tail[0]));
-            stat_max[(par * 2 + wg) * 128 + r] = mx;
-            named_bar_sync(3, 256);
-            mx = fmaxf(mx, stat_max[(par * 2 + (wg ^ 1)) * 128 + r]);
-            const float neg_m = -mx * scale_log2;
-            float sum = 0.f;
-#pragma unroll
-            for (int a2 = 0; a2 < 2; ++a2) {                  // the two full 64-key atoms of this warpgroup
-                const int a = wg * 2 + a2;
-                const int ga = tile * 5 + a, slot = ga % ATC_P_SLOTS;
-                uint32_t pk[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[a2 * 64 + 2 * j]), scale_log2, neg_m));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[a2 * 64 + 2 * j + 1]), scale_log2, neg_m));
-                    sum += p0 + p1;
-                    pk[j] = pack_bf16x2(p0, p1);
+            uint32_t tail0 = 0;
+            float mx = -INFINITY;
+            if (cur) {
+                if ((tile & 1) == 0) {
+                    const int item = blockIdx.x + (tile >> 1) * gridDim.x;
+                    seq = item / heads;
+                    h = item - seq * heads;
                 }
-                mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
-                uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
+                mbar_wait(s_full, par);
+                tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                fence_proxy_async_smem();
-                mbar_arrive(&p_full[slot]);
+                for (int c = 0; c < 4; ++c) tmem_ld_x32_ptr(t_row + wg * 128 + c * 32, sv + c * 32);
+                if (wg == 1) tmem_ld_x1(t_row + 256, tail0);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(s_free);
+                float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
+                float m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+#pragma unroll
+                for (int j = 4; j < 128; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(sv[j]));     m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(sv[j + 2])); m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+                }
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                if (wg == 1) mx = fmaxf(mx, __uint_as_float(tail0));
+                stat_max[(par * 2 + wg) * 128 + r] = mx;
             }
-            if (wg == 1) {                                    // tail atom: key 256 + 15 masked keys
-                const int ga = tile * 5 + 4, slot = ga % ATC_P_SLOTS;
-                const float p0 = ex2_approx(fmaf(__uint_as_float(tail[0]), scale_log2, neg_m));
-                sum += p0;
-                mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
-                uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
-                *reinterpret_cast<uint4*>(prow + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(prow + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-                fence_proxy_async_smem();
-                mbar_arrive(&p_full[slot]);
-            }
-            stat_sum[(par * 2 + wg) * 128 + r] = sum;
-            mbar_wait(o_full, par);
-            tc_fence_after();
+            if (tile > 0) stat_sum[((par ^ 1) * 2 + wg) * 128 + r] = prev_sum;
+            if (store_leader) tma_store_wait_read<0>();       // the previous TMA store has drained this staging buffer
             named_bar_sync(3, 256);
-            const float inv = 1.0f / (sum + stat_sum[(par * 2 + (wg ^ 1)) * 128 + r]);
-            uint32_t ov[32];
-            tmem_ld_x32_ptr(t_row + ATC_O_COL + wg * 32, ov);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(o_free);
-            uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seq) * ATC_S + t * 128 + r) * D + h * 64 + wg * 32);
+            if (tile > 0) {
+                // ---- epilogue of tile-1: normalise this warpgroup's 32 columns of O and store them
+                mbar_wait(o_full, par ^ 1);
+                tc_fence_after();
+                const float inv = 1.0f / (prev_sum + stat_sum[((par ^ 1) * 2 + (wg ^ 1)) * 128 + r]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 w;
-                w.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
-                w.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
-                w.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
-                w.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
-                dst[q] = w;
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t ov[16];
+                    tmem_ld_x16_ptr(t_row + ATC_O_COL + wg * 32 + hh * 16, ov);
+                    tmem_ld_wait();
+                    if (hh == 1) {
+                        tc_fence_before();
+                        mbar_arrive(o_free);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
+                        w.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
+                        w.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
+                        w.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
+                        *reinterpret_cast<uint4*>(o_row + (((hh * 2 + q) ^ sw64) << 4)) = w;
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(4 + wg, 128);
+                if (store_leader) {
+                    tma_store_2d(&map_out, o_stage, prev_col, prev_row0);
+                    tma_store_commit();
+                }
+            }
+            if (cur) {
+                mx = fmaxf(mx, stat_max[(par * 2 + (wg ^ 1)) * 128 + r]);
+                const float neg_m = -mx * scale_log2;
+                float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+                for (int a2 = 0; a2 < 2; ++a2) {              // the two full 64-key atoms of this warpgroup
+                    const int ga = tile * 5 + wg * 2 + a2, slot = ga % ATC_P_SLOTS;
+                    mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
+                    uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {             // one 16-byte chunk (8 keys) at a time
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = a2 * 64 + q * 8 + 2 * j;
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), scale_log2, neg_m));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), scale_log2, neg_m));
+                            sum0 += p0; sum1 += p1;
+                            pk[j] = pack_bf16x2(p0, p1);
+                        }
+                        *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&p_full[slot]);
+                }
+                if (wg == 1) {                                // tail atom: key 256 + 15 masked keys
+                    const int ga = tile * 5 + 4, slot = ga % ATC_P_SLOTS;
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(tail0), scale_log2, neg_m));
+                    sum0 += p0;
+                    mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
+                    uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
+                    *reinterpret_cast<uint4*>(prow + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(prow + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&p_full[slot]);
+                }
+                prev_sum = sum0 + sum1;
+                prev_row0 = seq * ATC_S + (tile & 1) * 128;
+                prev_col = h * 64 + wg * 32;
             }
         }
+        if (store_leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -501,6 +555,8 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
     CUtensorMap map128, map16;
     if (encode_tmap_2d(&map128, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 128, 64)) return -1;
     if (encode_tmap_2d(&map16, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 16, 64)) return -1;
+    CUtensorMap map_out;
+    if (encode_tmap_2d(&map_out, TMAP_BF16, out_bf16, rows, D, static_cast<uint64_t>(D) * 2, 128, 32, 64)) return -1;
     static bool attr_done = false;
     if (!attr_done) {
         HB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
@@ -509,7 +565,7 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
     const int n_items = n_seq * heads;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
-        map128, map16, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), n_items,
+        map128, map16, map_out, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), n_items,
         heads, scale * 1.4426950408889634f);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());

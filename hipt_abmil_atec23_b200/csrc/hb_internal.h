@@ -25,10 +25,10 @@ struct ProfScope {                             // CUDA-event bracket on the laun
 };
 
 enum TmapDtype { TMAP_BF16 = 0, TMAP_F32 = 1, TMAP_U8 = 2 };
-// 2-D row-major tensor [rows, cols] with a row pitch in bytes; box [box_rows, box_cols]; SWIZZLE_128B
-// (box_cols * elem_size must be 128 B).  Out-of-bounds elements read as zero and are not written.
+// 2-D row-major tensor [rows, cols] with a row pitch in bytes; box [box_rows, box_cols]; SWIZZLE_128B or _64B
+// (box_cols * elem_size must equal the swizzle span).  Out-of-bounds elements read as zero and are not written.
 int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                   uint32_t box_rows, uint32_t box_cols);
+                   uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 struct GemmArgs {
     CUtensorMap map_a, map_w, map_out;
