@@ -202,30 +202,29 @@ __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* 
 // =====================================================================================================================
 // tcgen05 path for the ViT-256 shape (seq_len 257, head_dim 64).
 //
-// One persistent CTA per SM walks (sequence, head) items; each item is two 128-query tiles plus the single 257th query.
-//   warp 0      TMA producer: K [272 x 64] and V [272 x 64] (double buffered across items) and the two Q tiles, all
-//               SWIZZLE_128B boxes of the qkv matrix (rows past the end of the matrix read as zero)
-//   warp 1      MMA issuer: S = Q K^T as M128 x N256 + M128 x N16 (keys 256..271) into 272 TMEM columns, then
-//               O += P V over five key atoms (4 x 64 + 16) with P read K-major from shared memory and V read MN-major
-//               in place (no transpose); QK^T of the next tile is issued before P V of the current one
-//   warp 2      TMEM allocator
-//   warp 3      the 257th query row on the legacy mma.sync path against the same K / V tiles
-//   warps 4-11  two softmax warpgroups; thread = query row, warpgroup 0 owns keys 0..127, warpgroup 1 keys 128..256:
-//               S row slice -> registers (one TMEM read), row max exchanged through shared memory, exp2 with the scale
-//               folded in, P atoms written as bf16 into the swizzled layout the MMA consumes, row sums exchanged, then
-//               each warpgroup normalises and stores half of O's 64 columns.
-// Softmax statistics stay fp32; P is rounded to bf16 exactly like the legacy kernel.
+// One persistent CTA per SM walks (sequence, head) items.  An item is two 128-query tiles plus the 257th query; the two
+// tiles run as two INDEPENDENT pipelines (A: queries 0..127, B: 128..255) so that one pipeline's exp2 phase overlaps the
+// other's TMEM loads / waits / epilogue.
+//   warp 0        TMA producer: K [272 x 64] and V [272 x 64] (double buffered across items) and one Q tile per pipeline,
+//                 SWIZZLE_128B boxes of the qkv matrix (rows past its end read as zero)
+//   warps 1, 2    MMA issuers of pipelines A and B: S = Q K^T (M128 x N256, keys 0..255) into the pipeline's 256 TMEM
+//                 columns, then O += P V over five key atoms (4 x 64 keys + key 256) with P read K-major from shared
+//                 memory and V read MN-major in place; O accumulates into S's first 64 columns, which the softmax has
+//                 already consumed when the first atom arrives
+//   warp 3        the 257th query row on the mma.sync path against the same K / V tiles
+//   warps 4-7     softmax warpgroup of pipeline A, warps 8-11 of pipeline B; thread = query row.  The score against key
+//                 256 is a 64-term dot product in the thread; pass 1 reads the row's 256 scores from TMEM (first 128 kept
+//                 in registers) for the max, pass 2 produces P = exp2((s - max) * scale * log2 e) atom by atom as bf16 in
+//                 the swizzled layout the MMA consumes; the epilogue scales O by 1/sum and stores the tile with TMA.
+// Softmax statistics stay fp32; P is rounded to bf16 exactly like the mma.sync kernel.
 // =====================================================================================================================
 constexpr int ATC_THREADS = 384;
 constexpr int ATC_S = 257;
 constexpr int ATC_SPAD = 272;
 constexpr int ATC_KV_BYTES = ATC_SPAD * 128;            // 34816: [272 keys][64 bf16]
 constexpr int ATC_TILE_BYTES = 128 * 128;               // 16384: one 128-row x 128-byte swizzled tile
-constexpr int ATC_P_SLOTS = 2;
-constexpr int ATC_O_STAGE_BYTES = 128 * 64;             // one warpgroup's half of an O tile: 128 rows x 32 bf16
-constexpr int ATC_SMEM = 4 * ATC_KV_BYTES + 2 * ATC_TILE_BYTES + ATC_P_SLOTS * ATC_TILE_BYTES + 2 * ATC_O_STAGE_BYTES + 4096 + 256 + 1024;
+constexpr int ATC_SMEM = 4 * ATC_KV_BYTES + 4 * ATC_TILE_BYTES + 512 + 1024;
 constexpr int ATC_TMEM_COLS = 512;
-constexpr int ATC_O_COL = 320;
 
 __device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -239,60 +238,48 @@ __device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_x16_ptr(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map16,
-                    const __grid_constant__ CUtensorMap map_out, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_items, int heads,
-                    float scale_log2) {
+                    const __grid_constant__ CUtensorMap map_out, const __nv_bfloat16* __restrict__ qkv,
+                    __nv_bfloat16* __restrict__ out, int n_items, int heads, float scale_log2) {
     extern __shared__ uint8_t smem_raw_atc[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_atc) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem;                                   // [2][34816]
-    uint8_t* sV = sK + 2 * ATC_KV_BYTES;                  // [2][34816]
-    uint8_t* sQ = sV + 2 * ATC_KV_BYTES;                  // [2 tiles][16384]
-    uint8_t* sP = sQ + 2 * ATC_TILE_BYTES;                // [3 slots][16384]
-    uint8_t* sO = sP + ATC_P_SLOTS * ATC_TILE_BYTES;      // [2 wg][128 rows x 64 B], SWIZZLE_64B staging for the TMA store
-    float* stat_max = reinterpret_cast<float*>(sO + 2 * ATC_O_STAGE_BYTES);          // [2 parity][2 wg][128]
-    float* stat_sum = stat_max + 512;                                                 // [2 parity][2 wg][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_sum + 512);
-    uint64_t* kv_full = bars;            // [2]
-    uint64_t* kv_empty = bars + 2;       // [2]
-    uint64_t* q_full = bars + 4;
-    uint64_t* q_empty = bars + 5;
-    uint64_t* s_full = bars + 6;
-    uint64_t* s_free = bars + 7;
-    uint64_t* o_full = bars + 8;
-    uint64_t* o_free = bars + 9;
-    uint64_t* p_full = bars + 10;        // [ATC_P_SLOTS]
-    uint64_t* p_empty = bars + 13;       // [ATC_P_SLOTS]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint8_t* sK = smem;                                   // [2 stages][34816]
+    uint8_t* sV = sK + 2 * ATC_KV_BYTES;                  // [2 stages][34816]
+    uint8_t* sQ = sV + 2 * ATC_KV_BYTES;                  // [2 pipelines][16384]
+    uint8_t* sP = sQ + 2 * ATC_TILE_BYTES;                // [2 pipelines][16384]  P atom slot, then O staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATC_TILE_BYTES);
+    uint64_t* kv_full = bars;            // [2 stages]
+    uint64_t* kv_empty = bars + 2;       // [2 stages]  2 MMA commits + tail warp
+    uint64_t* q_full = bars + 4;         // [2 pipelines]
+    uint64_t* q_empty = bars + 6;        // [2]  MMA commit + 128 softmax threads (they read their Q row for key 256)
+    uint64_t* s_full = bars + 8;         // [2]
+    uint64_t* o_full = bars + 10;        // [2]
+    uint64_t* o_free = bars + 12;        // [2]  128 softmax threads: O (= the S region) may be overwritten
+    uint64_t* p_full = bars + 14;        // [2]  128 softmax threads
+    uint64_t* p_empty = bars + 16;       // [2]  MMA commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = heads * 64;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); tma_prefetch_desc(&map_out); }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
-        mbar_init(q_full, 1); mbar_init(q_empty, 1);
-        mbar_init(s_full, 1); mbar_init(s_free, 256);
-        mbar_init(o_full, 1); mbar_init(o_free, 256);
-        for (int i = 0; i < ATC_P_SLOTS; ++i) { mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 3);
+            mbar_init(&q_full[i], 1);  mbar_init(&q_empty[i], 129);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&o_full[i], 1);  mbar_init(&o_free[i], 128);
+            mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, ATC_TMEM_COLS); tmem_relinquish(); }
@@ -303,7 +290,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
 
     int my_items = 0;
     if (static_cast<int>(blockIdx.x) < n_items) my_items = (n_items - 1 - blockIdx.x) / gridDim.x + 1;
-    const int n_tiles = my_items * 2;
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA producer
@@ -323,59 +309,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 tma_load_2d(v, &map128, &kv_full[st], 2 * D + h * 64, row0);
                 tma_load_2d(v + ATC_TILE_BYTES, &map128, &kv_full[st], 2 * D + h * 64, row0 + 128);
                 tma_load_2d(v + 2 * ATC_TILE_BYTES, &map16, &kv_full[st], 2 * D + h * 64, row0 + 256);
-                mbar_wait(q_empty, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, 2 * ATC_TILE_BYTES);
-                tma_load_2d(sQ, &map128, q_full, h * 64, row0);
-                tma_load_2d(sQ + ATC_TILE_BYTES, &map128, q_full, h * 64, row0 + 128);
+#pragma unroll
+                for (int x = 0; x < 2; ++x) {
+                    mbar_wait(&q_empty[x], (it & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[x], ATC_TILE_BYTES);
+                    tma_load_2d(sQ + x * ATC_TILE_BYTES, &map128, &q_full[x], h * 64, row0 + x * 128);
+                }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && n_tiles > 0) {
-            constexpr uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
-            constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
-            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);      // B (= V) is MN-major
-            auto issue_qk = [&](int tile) {
-                const int it = tile >> 1, t = tile & 1, st = it & 1;
-                if (t == 0) {
-                    mbar_wait(&kv_full[st], (it >> 1) & 1);
-                    mbar_wait(q_full, it & 1);
-                }
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------------------------------------ MMA issuers
+        if (lane == 0) {
+            const int x = warp - 1;                                                // pipeline
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
+            const uint32_t t_acc = tmem_base + x * 256;
+            const uint64_t dq = umma_desc_k128(smem_u32(sQ + x * ATC_TILE_BYTES));
+            const uint64_t dp = umma_desc_k128(smem_u32(sP + x * ATC_TILE_BYTES));
+            for (int it = 0; it < my_items; ++it) {
+                const int st = it & 1;
+                mbar_wait(&kv_full[st], (it >> 1) & 1);
+                mbar_wait(&q_full[x], it & 1);
+                if (it > 0) mbar_wait(&o_free[x], (it - 1) & 1);
                 tc_fence_after();
-                const uint64_t dq = umma_desc_k128(smem_u32(sQ + t * ATC_TILE_BYTES));
                 const uint64_t dk = umma_desc_k128(smem_u32(sK + st * ATC_KV_BYTES));
-                const uint64_t dk_tail = umma_desc_k128(smem_u32(sK + st * ATC_KV_BYTES + 2 * ATC_TILE_BYTES));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    umma_bf16_ss(tmem_base, dq + 2 * kk, dk + 2 * kk, idesc_s256, kk != 0);
-                    umma_bf16_ss(tmem_base + 256, dq + 2 * kk, dk_tail + 2 * kk, idesc_s16, kk != 0);
-                }
-                umma_commit(s_full);
-                if (t == 1) umma_commit(q_empty);
-            };
-            issue_qk(0);
-            for (int tile = 0; tile < n_tiles; ++tile) {
-                const int it = tile >> 1, t = tile & 1, st = it & 1;
-                if (tile + 1 < n_tiles) {
-                    mbar_wait(s_free, tile & 1);               // S(tile) now lives in the softmax registers
-                    issue_qk(tile + 1);
-                }
-                if (tile > 0) mbar_wait(o_free, (tile - 1) & 1);
+                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(t_acc, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+                umma_commit(&s_full[x]);
+                umma_commit(&q_empty[x]);
                 const uint32_t v_base = smem_u32(sV + st * ATC_KV_BYTES);
                 for (int a = 0; a < 5; ++a) {
-                    const int ga = tile * 5 + a, slot = ga % ATC_P_SLOTS;
-                    mbar_wait(&p_full[slot], (ga / ATC_P_SLOTS) & 1);
+                    mbar_wait(&p_full[x], (it * 5 + a) & 1);
                     tc_fence_after();
-                    const uint64_t dp = umma_desc_k128(smem_u32(sP + slot * ATC_TILE_BYTES));
                     const int ksteps = (a < 4) ? 4 : 1;
                     for (int kk = 0; kk < ksteps; ++kk) {
                         const uint64_t dv = umma_desc_k128(v_base + (a * 64 + kk * 16) * 128);
-                        umma_bf16_ss(tmem_base + ATC_O_COL, dp + 2 * kk, dv, idesc_pv, (a | kk) != 0);
+                        umma_bf16_ss(t_acc, dp + 2 * kk, dv, idesc_pv, (a | kk) != 0);
                     }
-                    umma_commit(&p_empty[slot]);
+                    umma_commit(&p_empty[x]);
                 }
-                umma_commit(o_full);
-                if (t == 1) umma_commit(&kv_empty[st]);
+                umma_commit(&o_full[x]);
+                umma_commit(&kv_empty[st]);
             }
         }
     } else if (warp == 3) {
@@ -398,6 +372,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 }
             }
             mbar_wait(&kv_full[st], (it >> 1) & 1);
+#ifdef ATC_SKIP_TAIL
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&kv_empty[st]);
+            continue;
+#endif
             const uint32_t k_addr = smem_u32(sK + st * ATC_KV_BYTES), v_addr = smem_u32(sV + st * ATC_KV_BYTES);
             float o[8][4];
 #pragma unroll
@@ -418,129 +397,133 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&kv_empty[st]);
         }
-    } else if (warp >= 4) {
+    } else {
         // ------------------------------------------------------------------------------------------ softmax warpgroups
-        // Software-pipelined by one tile: S(tile) is pulled into registers and its row max computed BEFORE the
-        // epilogue of tile-1, so the wait for the last P V MMAs of tile-1 hides behind useful work, and one named
-        // barrier per tile publishes both max(tile) and sum(tile-1) between the two warpgroups.
-        const int wg = (warp - 4) >> 2;
+        const int x = (warp - 4) >> 2;                        // pipeline = query tile of the item
         const int r = (warp & 3) * 32 + lane;                 // query row inside the tile = TMEM lane
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + x * 256;
         const int sw = r & 7;
-        float prev_sum = 0.f;
-        int prev_row0 = 0, prev_col = 0;                      // TMA-store coordinates of tile-1's half tile
-        int seq = 0, h = 0;
-        const bool store_leader = ((warp & 3) == 0 && lane == 0);
-        uint8_t* o_stage = sO + wg * ATC_O_STAGE_BYTES;
-        uint8_t* o_row = o_stage + r * 64;
-        const int sw64 = (r >> 1) & 3;
-        for (int tile = 0; tile <= n_tiles; ++tile) {
-            const int par = tile & 1;
-            const bool cur = tile < n_tiles;
+        const bool leader = ((warp & 3) == 0 && lane == 0);
+        uint8_t* q_row = sQ + x * ATC_TILE_BYTES + r * 128;
+        uint8_t* p_row = sP + x * ATC_TILE_BYTES + r * 128;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int seq = item / heads, h = item - seq * heads;
+            const int st = it & 1;
+            // ---- score against key 256: q_r . k_256 (row 256 of K is row 0 of its own swizzle atom: unswizzled)
+            mbar_wait(&kv_full[st], (it >> 1) & 1);
+            mbar_wait(&q_full[x], it & 1);
+            float s256 = 0.f;
+            {
+                const uint4* k256 = reinterpret_cast<const uint4*>(sK + st * ATC_KV_BYTES + 2 * ATC_TILE_BYTES);
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 qv = *reinterpret_cast<const uint4*>(q_row + ((c ^ sw) << 4));
+                    const uint4 kv = k256[c];
+                    acc0 = fmaf(bf16_lo(qv.x), bf16_lo(kv.x), acc0); acc1 = fmaf(bf16_hi(qv.x), bf16_hi(kv.x), acc1);
+                    acc0 = fmaf(bf16_lo(qv.y), bf16_lo(kv.y), acc0); acc1 = fmaf(bf16_hi(qv.y), bf16_hi(kv.y), acc1);
+                    acc0 = fmaf(bf16_lo(qv.z), bf16_lo(kv.z), acc0); acc1 = fmaf(bf16_hi(qv.z), bf16_hi(kv.z), acc1);
+                    acc0 = fmaf(bf16_lo(qv.w), bf16_lo(kv.w), acc0); acc1 = fmaf(bf16_hi(qv.w), bf16_hi(kv.w), acc1);
+                }
+                s256 = acc0 + acc1;
+            }
+            mbar_arrive(&q_empty[x]);
+
+            // ---- pass 1: row max over the 256 MMA scores (first 128 stay in registers) and key 256
+            mbar_wait(&s_full[x], it & 1);
+            tc_fence_after();
             uint32_t sv[128];
-            uint32_t tail0 = 0;
-            float mx = -INFINITY;
-            if (cur) {
-                if ((tile & 1) == 0) {
-                    const int item = blockIdx.x + (tile >> 1) * gridDim.x;
-                    seq = item / heads;
-                    h = item - seq * heads;
-                }
-                mbar_wait(s_full, par);
-                tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld_x32_ptr(t_row + wg * 128 + c * 32, sv + c * 32);
-                if (wg == 1) tmem_ld_x1(t_row + 256, tail0);
+            for (int c = 0; c < 4; ++c) tmem_ld_x32_ptr(t_row + c * 32, sv + c * 32);
+            tmem_ld_wait();
+            float m0 = s256, m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+            m0 = fmaxf(m0, __uint_as_float(sv[0]));
+#pragma unroll
+            for (int j = 4; j < 128; j += 4) {
+                m0 = fmaxf(m0, __uint_as_float(sv[j]));     m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+                m2 = fmaxf(m2, __uint_as_float(sv[j + 2])); m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+            }
+#pragma unroll
+            for (int c = 4; c < 8; ++c) {
+                uint32_t tmp[32];
+                tmem_ld_x32_ptr(t_row + c * 32, tmp);
                 tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(s_free);
-                float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
-                float m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
 #pragma unroll
-                for (int j = 4; j < 128; j += 4) {
-                    m0 = fmaxf(m0, __uint_as_float(sv[j]));     m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
-                    m2 = fmaxf(m2, __uint_as_float(sv[j + 2])); m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+                for (int j = 0; j < 32; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(tmp[j]));     m1 = fmaxf(m1, __uint_as_float(tmp[j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(tmp[j + 2])); m3 = fmaxf(m3, __uint_as_float(tmp[j + 3]));
                 }
-                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                if (wg == 1) mx = fmaxf(mx, __uint_as_float(tail0));
-                stat_max[(par * 2 + wg) * 128 + r] = mx;
             }
-            if (tile > 0) stat_sum[((par ^ 1) * 2 + wg) * 128 + r] = prev_sum;
-            if (store_leader) tma_store_wait_read<0>();       // the previous TMA store has drained this staging buffer
-            named_bar_sync(3, 256);
-            if (tile > 0) {
-                // ---- epilogue of tile-1: normalise this warpgroup's 32 columns of O and store them
-                mbar_wait(o_full, par ^ 1);
-                tc_fence_after();
-                const float inv = 1.0f / (prev_sum + stat_sum[((par ^ 1) * 2 + (wg ^ 1)) * 128 + r]);
+            const float neg_m = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2;
+
+            // the TMA store of the previous tile must have drained the P slot (it doubles as the O staging buffer)
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(4 + x, 128);
+
+            // ---- pass 2: P atoms.  exp2 into registers first, then wait for the slot, store, publish.
+            float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t ov[16];
-                    tmem_ld_x16_ptr(t_row + ATC_O_COL + wg * 32 + hh * 16, ov);
+            for (int a = 0; a < 4; ++a) {
+                if (a == 2) {                                 // keys 128..255 come back from TMEM
+                    tmem_ld_x32_ptr(t_row + 128, sv);
+                    tmem_ld_x32_ptr(t_row + 160, sv + 32);
+                    tmem_ld_x32_ptr(t_row + 192, sv + 64);
+                    tmem_ld_x32_ptr(t_row + 224, sv + 96);
                     tmem_ld_wait();
-                    if (hh == 1) {
-                        tc_fence_before();
-                        mbar_arrive(o_free);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        uint4 w;
-                        w.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
-                        w.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
-                        w.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
-                        w.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
-                        *reinterpret_cast<uint4*>(o_row + (((hh * 2 + q) ^ sw64) << 4)) = w;
-                    }
                 }
+                uint32_t pk[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int e = (a & 1) * 64 + 2 * j;
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), scale_log2, neg_m));
+                    sum0 += p0; sum1 += p1;
+                    pk[j] = pack_bf16x2(p0, p1);
+                }
+                mbar_wait(&p_empty[x], ((it * 5 + a) & 1) ^ 1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 fence_proxy_async_smem();
-                named_bar_sync(4 + wg, 128);
-                if (store_leader) {
-                    tma_store_2d(&map_out, o_stage, prev_col, prev_row0);
-                    tma_store_commit();
-                }
+                mbar_arrive(&p_full[x]);
             }
-            if (cur) {
-                mx = fmaxf(mx, stat_max[(par * 2 + (wg ^ 1)) * 128 + r]);
-                const float neg_m = -mx * scale_log2;
-                float sum0 = 0.f, sum1 = 0.f;
+            {                                                 // tail atom: key 256 (+ 15 zero columns)
+                const float p0 = ex2_approx(fmaf(s256, scale_log2, neg_m));
+                sum0 += p0;
+                mbar_wait(&p_empty[x], ((it * 5 + 4) & 1) ^ 1);
+                *reinterpret_cast<uint4*>(p_row + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p_row + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                fence_proxy_async_smem();
+                mbar_arrive(&p_full[x]);
+            }
+            const float inv = 1.0f / (sum0 + sum1);
+
+            // ---- epilogue: O (first 64 columns of the S region) -> bf16 -> swizzled staging (the P slot) -> TMA store
+            mbar_wait(&o_full[x], it & 1);
+            tc_fence_after();
+            tmem_ld_x32_ptr(t_row, sv);
+            tmem_ld_x32_ptr(t_row + 32, sv + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&o_free[x]);
 #pragma unroll
-                for (int a2 = 0; a2 < 2; ++a2) {              // the two full 64-key atoms of this warpgroup
-                    const int ga = tile * 5 + wg * 2 + a2, slot = ga % ATC_P_SLOTS;
-                    mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
-                    uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {             // one 16-byte chunk (8 keys) at a time
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = a2 * 64 + q * 8 + 2 * j;
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), scale_log2, neg_m));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), scale_log2, neg_m));
-                            sum0 += p0; sum1 += p1;
-                            pk[j] = pack_bf16x2(p0, p1);
-                        }
-                        *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
-                    fence_proxy_async_smem();
-                    mbar_arrive(&p_full[slot]);
-                }
-                if (wg == 1) {                                // tail atom: key 256 + 15 masked keys
-                    const int ga = tile * 5 + 4, slot = ga % ATC_P_SLOTS;
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(tail0), scale_log2, neg_m));
-                    sum0 += p0;
-                    mbar_wait(&p_empty[slot], ((ga / ATC_P_SLOTS) & 1) ^ 1);
-                    uint8_t* prow = sP + slot * ATC_TILE_BYTES + r * 128;
-                    *reinterpret_cast<uint4*>(prow + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(prow + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-                    fence_proxy_async_smem();
-                    mbar_arrive(&p_full[slot]);
-                }
-                prev_sum = sum0 + sum1;
-                prev_row0 = seq * ATC_S + (tile & 1) * 128;
-                prev_col = h * 64 + wg * 32;
+            for (int q = 0; q < 8; ++q) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(sv[8 * q + 0]) * inv, __uint_as_float(sv[8 * q + 1]) * inv);
+                w.y = pack_bf16x2(__uint_as_float(sv[8 * q + 2]) * inv, __uint_as_float(sv[8 * q + 3]) * inv);
+                w.z = pack_bf16x2(__uint_as_float(sv[8 * q + 4]) * inv, __uint_as_float(sv[8 * q + 5]) * inv);
+                w.w = pack_bf16x2(__uint_as_float(sv[8 * q + 6]) * inv, __uint_as_float(sv[8 * q + 7]) * inv);
+                *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = w;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(4 + x, 128);
+            if (leader) {
+                tma_store_2d(&map_out, sP + x * ATC_TILE_BYTES, h * 64, seq * ATC_S + x * 128);
+                tma_store_commit();
             }
         }
-        if (store_leader) tma_store_wait_all<0>();
+        if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -552,11 +535,10 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
                                cudaStream_t stream) {
     const int D = heads * 64;
     const uint64_t rows = static_cast<uint64_t>(n_seq) * ATC_S;
-    CUtensorMap map128, map16;
+    CUtensorMap map128, map16, map_out;
     if (encode_tmap_2d(&map128, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 128, 64)) return -1;
     if (encode_tmap_2d(&map16, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 16, 64)) return -1;
-    CUtensorMap map_out;
-    if (encode_tmap_2d(&map_out, TMAP_BF16, out_bf16, rows, D, static_cast<uint64_t>(D) * 2, 128, 32, 64)) return -1;
+    if (encode_tmap_2d(&map_out, TMAP_BF16, out_bf16, rows, D, static_cast<uint64_t>(D) * 2, 128, 64)) return -1;
     static bool attr_done = false;
     if (!attr_done) {
         HB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
@@ -565,8 +547,8 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
     const int n_items = n_seq * heads;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
-        map128, map16, map_out, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), n_items,
-        heads, scale * 1.4426950408889634f);
+        map128, map16, map_out, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16),
+        n_items, heads, scale * 1.4426950408889634f);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
