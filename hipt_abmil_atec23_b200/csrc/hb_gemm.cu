@@ -9,6 +9,8 @@
 // :114-116 qkv/proj; HIPT_4K/vision_transformer4k.py:169 phi) and, fed with an im2col'd region, the patch-embed
 // convolution (vision_transformer.py:165-169).  nn.Linear.weight is [out,in] = [N,K] K-major, which is exactly the
 // UMMA "B K-major" operand, so weights are used as stored (cast to bf16 once at load).
+#include <stdlib.h>
+
 #include "hb_ptx.cuh"
 #include "hb_internal.h"
 
@@ -20,11 +22,15 @@ constexpr int GEMM_THREADS = 384;    // 12 warps: producer, mma, tmem-alloc, spa
 constexpr int GEMM_EPI_THREADS = 128; // per epilogue warpgroup
 constexpr int STAGE_BYTES_OUT = 128 * 128;   // 128 rows x 128 B staging chunk for the TMA store
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile; each
+// CTA stages its own 128 rows of A and HALF of the W tile, so operand bytes per FLOP per SM drop by a third to a half
+// and more k-blocks fit in flight.
+template <int BN, int CG>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+    static constexpr int B_ROWS = BN / CG;                    // W rows staged by this CTA
+    static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
+    static constexpr int STAGES = (CG == 2) ? 6 : ((BN == 256) ? 4 : (BN == 192 ? 4 : 6));
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 2 * STAGE_BYTES_OUT + 256 + 1024;
 };
@@ -33,13 +39,13 @@ struct GemmCfg {
 enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2, EPI_TOKENS_F32 = 3, EPI_TOKENS_GELU_F32 = 4,
               EPI_BIAS_GELU_FAST_BF16 = 5 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_out, const float* __restrict__ bias,
                  const float* __restrict__ tok_table, float* __restrict__ tok_out, int M, int N, int K,
                  int tokens_per_seq) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_FAST_BF16);
     constexpr bool OUT_TOKENS = (EPI == EPI_TOKENS_F32 || EPI == EPI_TOKENS_GELU_F32);
@@ -59,6 +65,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
+    const int tile0 = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+    const int tile_step = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+    constexpr int TILE_M = GEMM_BM * CG;
+    if constexpr (CG == 2) cluster_sync_all();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -66,21 +77,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (!OUT_TOKENS) tma_prefetch_desc(&map_out);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * GEMM_EPI_THREADS); }
+        // CG = 2: full_bar / acc_empty are used on the leader only and collect arrivals from both CTAs
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG * 2 * GEMM_EPI_THREADS); }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CG == 2) { tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_tiles = N / BN;
-    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    const int m_tiles = (M + TILE_M - 1) / TILE_M;
     const int total_tiles = m_tiles * n_tiles;
     const int k_blocks = K / GEMM_BK;
 
@@ -89,25 +101,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             const uint64_t pol_w = policy_evict_last();
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * GEMM_BM;
-                const int n0 = (tile % n_tiles) * BN;
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                const int m0 = (tile / n_tiles) * TILE_M + cta_rank * GEMM_BM;
+                const int n0 = (tile % n_tiles) * BN + cta_rank * Cfg::B_ROWS;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * GEMM_BK, m0);
-                    tma_load_2d_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
+                    if constexpr (CG == 2) {
+                        // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the pair
+                        tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * GEMM_BK, m0);
+                        tma_load_2d_2sm_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+                        else mbar_arrive_remote(&full_bar[stage], 0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * GEMM_BK, m0);
+                        tma_load_2d_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
             uint32_t stage = 0, phase = 0;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(&acc_empty[as], aphase ^ 1);
                 tc_fence_after();
@@ -120,10 +140,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // advance 16 bf16 = 32 B inside the swizzle span: +2 in the (addr >> 4) field
-                        umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CG == 2) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
-                    if (kb == k_blocks - 1) umma_commit(&acc_full[as]);
+                    if constexpr (CG == 2) {                   // arrive on the same barrier of BOTH CTAs
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kb == k_blocks - 1) umma_commit_2sm(&acc_full[as]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);        // smem slot free once these MMAs retire
+                        if (kb == k_blocks - 1) umma_commit(&acc_full[as]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -141,8 +167,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int sw = row_in_tile & 7;
         constexpr int NCHUNK = BN / CHUNK_COLS;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / n_tiles) * GEMM_BM;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+            const int m0 = (tile / n_tiles) * TILE_M + cta_rank * GEMM_BM;
             const int n0 = (tile % n_tiles) * BN;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             mbar_wait(&acc_full[as], aphase);
@@ -245,36 +271,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             // this thread has issued (and waited for) its last TMEM load of the tile: hand the buffer back
             tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
+            if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0);
+            else mbar_arrive(&acc_empty[as]);
         }
         if (store_leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG == 2) {
+        cluster_sync_all();                                    // the peer's remote arrivals have landed
+        if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI>
-static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
-    auto kern = gemm_bf16_kernel<BN, EPI>;
+template <int BN, int EPI, int CG>
+static int launch_gemm_cg(const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, CG>;
+    auto kern = gemm_bf16_kernel<BN, EPI, CG>;
     static bool attr_done = false;     // per instantiation
     if (!attr_done) {
         HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_done = true;
     }
-    const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
+    const int m_tiles = (g.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
     const int total = m_tiles * (g.N / BN);
-    const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.map_a, g.map_w, g.map_out, g.bias, g.tok_table, g.tok_out,
-                                                           g.M, g.N, g.K, g.tokens_per_seq);
+    const int slots = num_sms() / CG;
+    const int grid = (total < slots ? total : slots) * CG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (CG == 2) ? 1 : 0;
+    HB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.cg2 ? g.map_a : g.map_a, g.cg2 ? g.map_w2 : g.map_w, g.map_out, g.bias,
+                                  g.tok_table, g.tok_out, g.M, g.N, g.K, g.tokens_per_seq));
     count_launch();
-    HB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <int BN, int EPI>
+static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
+    if (g.cg2) return launch_gemm_cg<BN, EPI, 2>(g, stream);
+    return launch_gemm_cg<BN, EPI, 1>(g, stream);
 }
 
 template <int BN>
@@ -288,6 +336,12 @@ static int launch_gemm_bn(const GemmArgs& g, cudaStream_t stream) {
         case EPI_BIAS_GELU_FAST_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_FAST_BF16>(g, stream);
     }
     return set_error("hb_gemm: unknown epilogue %d", g.epi);
+}
+
+static bool gemm_use_cta_pairs() {      // HB_GEMM_CG=1 forces the single-CTA kernel (debug / comparison)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HB_GEMM_CG"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
 }
 
 int gemm_pick_bn(int N) {
@@ -308,6 +362,8 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     g.tok_table = tok_table; g.tok_out = nullptr; g.tokens_per_seq = tokens_per_seq;
     if (encode_tmap_2d(&g.map_a, TMAP_BF16, A, M, K, static_cast<uint64_t>(K) * 2, GEMM_BM, GEMM_BK)) return -1;
     if (encode_tmap_2d(&g.map_w, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn, GEMM_BK)) return -1;
+    if (encode_tmap_2d(&g.map_w2, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn / 2, GEMM_BK)) return -1;
+    g.cg2 = (M > GEMM_BM) && gemm_use_cta_pairs();
     if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16) {
         if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, GEMM_BM, 64)) return -1;
     } else if (epi == EPI_BIAS_RESADD_F32) {

@@ -31,7 +31,8 @@ int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t ro
                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 struct GemmArgs {
-    CUtensorMap map_a, map_w, map_out;
+    CUtensorMap map_a, map_w, map_w2, map_out;   // map_w2: W with a half-height box for the CTA-pair kernel
+    int cg2;                                     // 1: launch as clusters of 2 CTAs (tcgen05 cta_group::2)
     const float* bias;
     const float* tok_table;
     float* tok_out;

@@ -15,8 +15,10 @@ from . import _lib
 
 _lock = threading.Lock()
 
+import os
+
 # default capacities (token sequences per launch)
-VIT256_MAX_PATCHES = 256          # one 4096x4096 region = 256 patches of 257 tokens
+VIT256_MAX_PATCHES = int(os.environ.get("HB_VIT256_MAX_PATCHES", "256"))   # 256 = one 4096x4096 region per launch
 VIT4K_MAX_REGIONS = 64
 
 
