@@ -34,6 +34,10 @@ SIGNATURES = {
     "hb_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "hb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p]),
+    "hb_gemm_lnfold_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hb_gemm_resid_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hb_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p]),
     "hb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
@@ -150,6 +154,29 @@ def gemm_bf16(a, w, bias, epilogue, out=None, tok_table=None, tokens_per_seq=0):
     check(load().hb_gemm_bf16(ptr(a), ptr(w), ptr(bias), epilogue, ptr(out), M, N, K, ptr(tok_table), tokens_per_seq,
                               stream_ptr()))
     return out
+
+
+def gemm_lnfold_bf16(xb, w_gamma, c, d, row_stats, eps, gelu=False):
+    """LayerNorm + Linear (+GELU) as one GEMM on the un-normalised bf16 rows (see hb_gemm_lnfold_bf16)."""
+    require_cuda(xb, "xb")
+    device_check()
+    M, K = xb.shape
+    N = w_gamma.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=xb.device)
+    check(load().hb_gemm_lnfold_bf16(ptr(xb), ptr(w_gamma), ptr(c), ptr(d), ptr(row_stats), eps, int(gelu), ptr(out),
+                                     M, N, K, stream_ptr()))
+    return out
+
+
+def gemm_resid_stats(a, w, bias, x, xb, stats_out, stats_clear=None):
+    """x += a @ w.T + bias in place; xb = bf16(x); stats_out += (row sum, row sum of squares); stats_clear zeroed."""
+    require_cuda(a, "a")
+    device_check()
+    M, K = a.shape
+    N = w.shape[0]
+    check(load().hb_gemm_resid_stats(ptr(a), ptr(w), ptr(bias), ptr(x), ptr(xb), ptr(stats_out), ptr(stats_clear),
+                                     M, N, K, stream_ptr()))
+    return x
 
 
 def layernorm(x, gamma, beta, eps, rows, dim, row_stride=None, want_bf16=True, want_f32=False):

@@ -106,15 +106,23 @@ ProfScope::~ProfScope() {
 using namespace hb;
 
 // ---------------------------------------------------------------------------------------------------- plan object
+// Block pipeline (Block.forward, vision_transformer.py:146-152) with both LayerNorms folded into the GEMMs around them:
+//   qkv  = LNFOLD(xb; Wqkv*gamma1)            A = bf16 residual stream, per-row (mu, rstd) from stats1
+//   att  = softmax(q k^T) v
+//   x   += att Wproj^T + b      (RESID)       writes x fp32, xb bf16, stats2 = row sums of the new x; clears stats1
+//   hid  = gelu(LNFOLD(xb; Wfc1*gamma2))      per-row factors from stats2
+//   x   += hid Wfc2^T + b       (RESID)       writes x, xb, stats1 (for the next block); clears stats2
 struct hb_vit_plan {
     hb_vit_config cfg;
     int depth_limit;
     // workspace carve-up
     float* x;          // [max_rows, dim] fp32 residual stream
-    void* xn;          // [max_rows, dim] bf16 LayerNorm output
+    void* xb;          // [max_rows, dim] bf16 copy of the residual stream (A operand of the LN-folded GEMMs)
     void* qkv;         // [max_rows, 3 dim] bf16
     void* att;         // [max_rows, dim] bf16 attention output
     void* hid;         // [max_rows, mlp] bf16 MLP hidden (also the im2col operand of the patch embed)
+    float* stats1;     // [max_rows, 2] (sum, sum of squares) of x rows before norm1
+    float* stats2;     // [max_rows, 2] same before norm2
     size_t hid_bytes;
     std::vector<const void*> w;
     std::vector<GemmArgs> g_qkv, g_proj, g_fc1, g_fc2;
@@ -122,18 +130,23 @@ struct hb_vit_plan {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t ws_layout(const hb_vit_config* c, size_t* off_x, size_t* off_xn, size_t* off_qkv, size_t* off_att,
-                        size_t* off_hid, size_t* hid_bytes) {
-    const size_t rows = align_up(static_cast<size_t>(c->max_rows), 128);
+struct WsLayout { size_t x, xb, qkv, att, hid, hid_bytes, stats1, stats2, total; };
+
+static WsLayout ws_layout(const hb_vit_config* c) {
+    const size_t rows = align_up(static_cast<size_t>(c->max_rows), 256);
+    WsLayout L;
     size_t o = 0;
-    *off_x = o;   o += align_up(rows * c->dim * 4, 1024);
-    *off_xn = o;  o += align_up(rows * c->dim * 2, 1024);
-    *off_qkv = o; o += align_up(rows * c->dim * 3 * 2, 1024);
-    *off_att = o; o += align_up(rows * c->dim * 2, 1024);
-    *off_hid = o;
-    *hid_bytes = align_up(rows * c->mlp_dim * 2, 1024);
-    o += *hid_bytes;
-    return o;
+    L.x = o;   o += align_up(rows * c->dim * 4, 1024);
+    L.xb = o;  o += align_up(rows * c->dim * 2, 1024);
+    L.qkv = o; o += align_up(rows * c->dim * 3 * 2, 1024);
+    L.att = o; o += align_up(rows * c->dim * 2, 1024);
+    L.hid = o;
+    L.hid_bytes = align_up(rows * c->mlp_dim * 2, 1024);
+    o += L.hid_bytes;
+    L.stats1 = o; o += align_up(rows * 8, 1024);
+    L.stats2 = o; o += align_up(rows * 8, 1024);
+    L.total = o;
+    return L;
 }
 
 extern "C" {
@@ -156,8 +169,33 @@ int hb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
 
 int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int epilogue, void* out, int M, int N,
                  int K, const float* tok_table, int tokens_per_seq, void* stream) {
+    if (epilogue == HB_EPI_LNFOLD_BF16 || epilogue == HB_EPI_LNFOLD_GELU_BF16 || epilogue == HB_EPI_RESID_STATS_F32)
+        return set_error("hb_gemm_bf16: use hb_gemm_lnfold_bf16 / hb_gemm_resid_stats for epilogue %d", epilogue);
     GemmArgs g;
     if (gemm_prepare(g, a_bf16, w_bf16, bias, epilogue, out, M, N, K, tok_table, tokens_per_seq)) return -1;
+    return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+int hb_gemm_lnfold_bf16(const void* xb_bf16, const void* w_gamma_bf16, const float* c, const float* d,
+                        const float* row_stats, float eps, int gelu, void* out_bf16, int M, int N, int K, void* stream) {
+    GemmAux aux = {};
+    aux.colvec2 = c;
+    aux.row_stats = row_stats;
+    aux.inv_dim = 1.0f / static_cast<float>(K);
+    aux.eps = eps;
+    GemmArgs g;
+    if (gemm_prepare(g, xb_bf16, w_gamma_bf16, d, gelu ? HB_EPI_LNFOLD_GELU_BF16 : HB_EPI_LNFOLD_BF16, out_bf16, M, N, K,
+                     nullptr, 0, &aux)) return -1;
+    return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+int hb_gemm_resid_stats(const void* a_bf16, const void* w_bf16, const float* bias, float* x_f32, void* xb_bf16,
+                        float* stats_out, float* stats_clear, int M, int N, int K, void* stream) {
+    GemmAux aux = {};
+    aux.stats_out = stats_out;
+    aux.stats_clear = stats_clear;
+    GemmArgs g;
+    if (gemm_prepare(g, a_bf16, w_bf16, bias, HB_EPI_RESID_STATS_F32, x_f32, M, N, K, nullptr, 0, &aux, xb_bf16)) return -1;
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
 
@@ -201,10 +239,7 @@ int hb_prof_read(double* ms_by_kind, long long* count_by_kind, int n_kinds) {
     return 0;
 }
 
-size_t hb_vit_workspace_bytes(const hb_vit_config* cfg) {
-    size_t a, b, c, d, e, f;
-    return ws_layout(cfg, &a, &b, &c, &d, &e, &f);
-}
+size_t hb_vit_workspace_bytes(const hb_vit_config* cfg) { return ws_layout(cfg).total; }
 
 int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host, int n_weights, void* workspace,
                        size_t workspace_bytes, hb_vit_plan** plan_out) {
@@ -212,13 +247,12 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
     if (cfg->dim != 384 && cfg->dim != 192) return set_error("hb_vit_plan_create: dim %d not supported", cfg->dim);
     if (cfg->dim % cfg->heads != 0 || (cfg->dim / cfg->heads != 64 && cfg->dim / cfg->heads != 32))
         return set_error("hb_vit_plan_create: head_dim must be 64 or 32");
-    if (n_weights != 3 + 12 * cfg->depth)
-        return set_error("hb_vit_plan_create: expected %d weight pointers, got %d", 3 + 12 * cfg->depth, n_weights);
+    if (n_weights != 3 + 10 * cfg->depth)
+        return set_error("hb_vit_plan_create: expected %d weight pointers, got %d", 3 + 10 * cfg->depth, n_weights);
     for (int i = 0; i < n_weights; ++i)
         if (!weights_host[i]) return set_error("hb_vit_plan_create: weight pointer %d is null", i);
-    size_t ox, oxn, oqkv, oatt, ohid, hid_bytes;
-    const size_t need = ws_layout(cfg, &ox, &oxn, &oqkv, &oatt, &ohid, &hid_bytes);
-    if (workspace_bytes < need) return set_error("hb_vit_plan_create: workspace %zu < %zu bytes", workspace_bytes, need);
+    const WsLayout L = ws_layout(cfg);
+    if (workspace_bytes < L.total) return set_error("hb_vit_plan_create: workspace %zu < %zu bytes", workspace_bytes, L.total);
     if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error("hb_vit_plan_create: workspace must be 1 KiB aligned");
 
     hb_vit_plan* p = new (std::nothrow) hb_vit_plan();
@@ -226,22 +260,29 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
     p->cfg = *cfg;
     p->depth_limit = cfg->depth;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    p->x = reinterpret_cast<float*>(ws + ox);
-    p->xn = ws + oxn;
-    p->qkv = ws + oqkv;
-    p->att = ws + oatt;
-    p->hid = ws + ohid;
-    p->hid_bytes = hid_bytes;
+    p->x = reinterpret_cast<float*>(ws + L.x);
+    p->xb = ws + L.xb;
+    p->qkv = ws + L.qkv;
+    p->att = ws + L.att;
+    p->hid = ws + L.hid;
+    p->hid_bytes = L.hid_bytes;
+    p->stats1 = reinterpret_cast<float*>(ws + L.stats1);
+    p->stats2 = reinterpret_cast<float*>(ws + L.stats2);
     p->w.assign(weights_host, weights_host + n_weights);
     const int D = cfg->dim, H = cfg->mlp_dim, R = cfg->max_rows;
     p->g_qkv.resize(cfg->depth); p->g_proj.resize(cfg->depth); p->g_fc1.resize(cfg->depth); p->g_fc2.resize(cfg->depth);
     for (int i = 0; i < cfg->depth; ++i) {
-        const void* const* w = &p->w[3 + 12 * i];
+        const void* const* w = &p->w[3 + 10 * i];
+        GemmAux a1 = {}, a2 = {}, r1 = {}, r2 = {};
+        a1.colvec2 = static_cast<const float*>(w[1]); a1.row_stats = p->stats1; a1.inv_dim = 1.0f / D; a1.eps = cfg->ln_eps;
+        a2.colvec2 = static_cast<const float*>(w[6]); a2.row_stats = p->stats2; a2.inv_dim = 1.0f / D; a2.eps = cfg->ln_eps;
+        r1.stats_out = p->stats2; r1.stats_clear = p->stats1;
+        r2.stats_out = p->stats1; r2.stats_clear = p->stats2;
         int rc = 0;
-        rc |= gemm_prepare(p->g_qkv[i], p->xn, w[2], static_cast<const float*>(w[3]), HB_EPI_BIAS_BF16, p->qkv, R, 3 * D, D, nullptr, 0);
-        rc |= gemm_prepare(p->g_proj[i], p->att, w[4], static_cast<const float*>(w[5]), HB_EPI_BIAS_RESADD_F32, p->x, R, D, D, nullptr, 0);
-        rc |= gemm_prepare(p->g_fc1[i], p->xn, w[8], static_cast<const float*>(w[9]), HB_EPI_BIAS_GELU_FAST_BF16, p->hid, R, H, D, nullptr, 0);
-        rc |= gemm_prepare(p->g_fc2[i], p->hid, w[10], static_cast<const float*>(w[11]), HB_EPI_BIAS_RESADD_F32, p->x, R, D, H, nullptr, 0);
+        rc |= gemm_prepare(p->g_qkv[i], p->xb, w[0], static_cast<const float*>(w[2]), HB_EPI_LNFOLD_BF16, p->qkv, R, 3 * D, D, nullptr, 0, &a1);
+        rc |= gemm_prepare(p->g_proj[i], p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_STATS_F32, p->x, R, D, D, nullptr, 0, &r1, p->xb);
+        rc |= gemm_prepare(p->g_fc1[i], p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU_BF16, p->hid, R, H, D, nullptr, 0, &a2);
+        rc |= gemm_prepare(p->g_fc2[i], p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_STATS_F32, p->x, R, D, H, nullptr, 0, &r2, p->xb);
         if (rc) { delete p; return -1; }
     }
     *plan_out = p;
@@ -258,10 +299,10 @@ int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit) {
 
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes) {
     if (!plan || !ptr || !bytes) return set_error("null argument");
-    const size_t rows = align_up(static_cast<size_t>(plan->cfg.max_rows), 128);
+    const size_t rows = align_up(static_cast<size_t>(plan->cfg.max_rows), 256);
     switch (which) {
         case 0: *ptr = plan->x; *bytes = rows * plan->cfg.dim * 4; return 0;
-        case 1: *ptr = plan->xn; *bytes = rows * plan->cfg.dim * 2; return 0;
+        case 1: *ptr = plan->xb; *bytes = rows * plan->cfg.dim * 2; return 0;
         case 2: *ptr = plan->qkv; *bytes = rows * plan->cfg.dim * 6; return 0;
         case 3: *ptr = plan->att; *bytes = rows * plan->cfg.dim * 2; return 0;
         case 4: *ptr = plan->hid; *bytes = plan->hid_bytes; return 0;
@@ -271,7 +312,7 @@ int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes) 
 
 }  // extern "C"
 
-// x already holds the token rows; runs the transformer blocks and the final LayerNorm on the CLS rows.
+// x / xb / stats1 already hold the token rows; runs the transformer blocks and the final LayerNorm on the CLS rows.
 static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, void* cls_bf16, cudaStream_t st) {
     const hb_vit_config& c = p->cfg;
     const int M = n_seq * seq_len;
@@ -279,17 +320,12 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
     const int kb = (D == 192) ? HB_PROF_4K_OFFSET : 0;     // profiler kind base: ViT-256 vs ViT-4K
     for (int i = 0; i < p->depth_limit; ++i) {
-        const void* const* w = &p->w[3 + 12 * i];
-        { ProfScope ps(kb + HB_PROF_LAYERNORM, st);
-          if (layernorm_launch(p->x, D, static_cast<const float*>(w[0]), static_cast<const float*>(w[1]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1; }
         GemmArgs g = p->g_qkv[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_QKV_GEMM, st); if (gemm_launch(g, st)) return -1; }
         { ProfScope ps(kb + HB_PROF_ATTENTION, st);
           if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st)) return -1; }
         g = p->g_proj[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_PROJ_GEMM, st); if (gemm_launch(g, st)) return -1; }
-        { ProfScope ps(kb + HB_PROF_LAYERNORM, st);
-          if (layernorm_launch(p->x, D, static_cast<const float*>(w[6]), static_cast<const float*>(w[7]), c.ln_eps, p->xn, nullptr, M, D, st)) return -1; }
         g = p->g_fc1[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_FC1_GEMM, st); if (gemm_launch(g, st)) return -1; }
         g = p->g_fc2[i]; g.M = M;
@@ -299,6 +335,13 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
     ProfScope ps(kb + HB_PROF_FINAL_LN, st);
     return layernorm_launch(p->x, static_cast<size_t>(seq_len) * D, static_cast<const float*>(p->w[1]),
                             static_cast<const float*>(p->w[2]), c.ln_eps, cls_bf16, cls_f32, n_seq, D, st);
+}
+
+// zero both statistics arrays for the rows of this call (they are accumulated with atomics)
+static int clear_stats(hb_vit_plan* p, int rows, cudaStream_t st) {
+    HB_CUDA_OK(cudaMemsetAsync(p->stats1, 0, static_cast<size_t>(rows) * 8, st));
+    HB_CUDA_OK(cudaMemsetAsync(p->stats2, 0, static_cast<size_t>(rows) * 8, st));
+    return 0;
 }
 
 extern "C" {
@@ -315,13 +358,16 @@ int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, si
         return set_error("hb_vit256_forward: im2col operand does not fit the workspace");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = plan->cfg.dim;
+    if (clear_stats(plan, n_patches * seq_len, st)) return -1;
     { ProfScope ps(HB_PROF_IM2COL, st);
       if (im2col_launch(image, image_is_f32, patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, plan->hid, st)) return -1; }
+    GemmAux aux = {};
+    aux.stats_out = plan->stats1;
     GemmArgs g;
-    if (gemm_prepare(g, plan->hid, embed_w_bf16, embed_b, HB_EPI_TOKENS_F32, plan->x, n_patches * T, D, 768, pos_table, T)) return -1;
+    if (gemm_prepare(g, plan->hid, embed_w_bf16, embed_b, HB_EPI_TOKENS_F32, plan->x, n_patches * T, D, 768, pos_table, T, &aux, plan->xb)) return -1;
     { ProfScope ps(HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
     { ProfScope ps(HB_PROF_CLS_ROWS, st);
-      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_patches, seq_len, D, st)) return -1; }
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, plan->xb, plan->stats1, n_patches, seq_len, D, st)) return -1; }
     return run_blocks(plan, n_patches, seq_len, cls_f32, cls_bf16, st);
 }
 
@@ -334,11 +380,14 @@ int hb_vit4k_forward(hb_vit_plan* plan, const void* cls256_bf16, int n_regions, 
         return set_error("hb_vit4k_forward: %d regions exceed the plan capacity of %d rows", n_regions, plan->cfg.max_rows);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = plan->cfg.dim;
+    if (clear_stats(plan, n_regions * seq_len, st)) return -1;
+    GemmAux aux = {};
+    aux.stats_out = plan->stats1;
     GemmArgs g;
-    if (gemm_prepare(g, cls256_bf16, phi_w_bf16, phi_b, HB_EPI_TOKENS_GELU_F32, plan->x, n_regions * tokens_per_region, D, in_dim, pos_table, tokens_per_region)) return -1;
+    if (gemm_prepare(g, cls256_bf16, phi_w_bf16, phi_b, HB_EPI_TOKENS_GELU_F32, plan->x, n_regions * tokens_per_region, D, in_dim, pos_table, tokens_per_region, &aux, plan->xb)) return -1;
     { ProfScope ps(HB_PROF_4K_OFFSET + HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
     { ProfScope ps(HB_PROF_4K_OFFSET + HB_PROF_CLS_ROWS, st);
-      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, n_regions, seq_len, D, st)) return -1; }
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, plan->xb, plan->stats1, n_regions, seq_len, D, st)) return -1; }
     return run_blocks(plan, n_regions, seq_len, out_f32, nullptr, st);
 }
 

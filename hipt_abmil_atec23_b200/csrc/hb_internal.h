@@ -1,6 +1,7 @@
 // hb_internal.h — host-side plumbing shared by the translation units of libhipt_b200.so (not part of the C-ABI).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -30,8 +31,18 @@ enum TmapDtype { TMAP_BF16 = 0, TMAP_F32 = 1, TMAP_U8 = 2 };
 int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
+struct GemmAux {                                 // epilogue side inputs / outputs, passed to the kernel by value
+    const float* colvec2;                        // LNFOLD: c[N] = sum_k gamma_k W_jk (bias slot carries d[N])
+    const float* row_stats;                      // LNFOLD: [M][2] (sum, sum of squares) of the fp32 rows behind A
+    float* stats_out;                            // RESID / TOKENS: (sum, sum of squares) of the produced rows, accumulated
+    float* stats_clear;                          // RESID: the other LayerNorm's statistics array, zeroed on the way
+    __nv_bfloat16* xb_out;                       // TOKENS: bf16 copy of the produced rows (RESID stores it by TMA)
+    float inv_dim, eps;                          // LNFOLD: 1 / normalised width, LayerNorm epsilon
+};
+
 struct GemmArgs {
-    CUtensorMap map_a, map_w, map_w2, map_out;   // map_w2: W with a half-height box for the CTA-pair kernel
+    CUtensorMap map_a, map_w, map_w2, map_out, map_xb;   // map_w2: W with a half-height box for the CTA-pair kernel
+    GemmAux aux;
     int cg2;                                     // 1: launch as clusters of 2 CTAs (tcgen05 cta_group::2)
     const float* bias;
     const float* tok_table;
@@ -40,7 +51,7 @@ struct GemmArgs {
 };
 int gemm_pick_bn(int N);
 int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, int epi, void* out, int M, int N, int K,
-                 const float* tok_table, int tokens_per_seq);
+                 const float* tok_table, int tokens_per_seq, const GemmAux* aux = nullptr, void* xb_out = nullptr);
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
 
 // elementwise / row kernels
@@ -50,8 +61,8 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
                      cudaStream_t stream);
 int im2col_launch(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
                   int grid_cols, int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream);
-int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, int n_seq, int seq_len, int dim,
-                    cudaStream_t stream);
+int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, void* xb_bf16, float* stats, int n_seq,
+                    int seq_len, int dim, cudaStream_t stream);
 
 int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
                         int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,

@@ -181,19 +181,33 @@ int im2col_launch(const void* image, int image_is_f32, size_t patch_stride, size
 }
 
 // ------------------------------------------------------------------------------------------------ CLS rows
+// One warp per sequence: x[seq, 0, :] = cls_token + pos[0], plus the bf16 copy and the row's (sum, sum of squares)
+// that the LayerNorm-folded GEMM epilogues consume.
 __global__ void cls_rows_kernel(const float* __restrict__ cls_token, const float* __restrict__ pos_table,
-                                float* __restrict__ x, int n_seq, int seq_len, int dim) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_seq * dim) return;
-    const int s = idx / dim, d = idx - s * dim;
-    x[static_cast<size_t>(s) * seq_len * dim + d] = cls_token[d] + pos_table[d];
+                                float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats,
+                                int n_seq, int seq_len, int dim) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_seq) return;
+    const size_t row = static_cast<size_t>(warp) * seq_len;
+    float s = 0.f, q = 0.f;
+    for (int d = lane; d < dim; d += 32) {
+        const float v = cls_token[d] + pos_table[d];
+        x[row * dim + d] = v;
+        if (xb) xb[row * dim + d] = __float2bfloat16(v);
+        s += v;
+        q = fmaf(v, v, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (stats && lane == 0) { stats[row * 2] = s; stats[row * 2 + 1] = q; }
 }
 
-int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, int n_seq, int seq_len, int dim,
-                    cudaStream_t stream) {
+int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, void* xb_bf16, float* stats, int n_seq,
+                    int seq_len, int dim, cudaStream_t stream) {
     if (n_seq <= 0) return 0;
-    const int total = n_seq * dim;
-    cls_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cls_token, pos_table, x, n_seq, seq_len, dim);
+    const int blocks = (n_seq * 32 + 255) / 256;
+    cls_rows_kernel<<<blocks, 256, 0, stream>>>(cls_token, pos_table, x, static_cast<__nv_bfloat16*>(xb_bf16), stats,
+                                                n_seq, seq_len, dim);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -77,13 +77,24 @@ class VitEngine:
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         bf16 = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
         w = [f32(m.cls_token).reshape(-1), f32(m.norm.weight), f32(m.norm.bias)]
+
+        def fold(norm, lin):
+            """LayerNorm folded into the Linear that consumes it (hb_gemm_lnfold_bf16): bf16(W * gamma), the row sums c
+            of that ROUNDED weight (so the mean term cancels exactly against the MMA), and d = W beta + bias."""
+            W = lin.weight.detach().double().cpu()
+            g = norm.weight.detach().double().cpu()
+            be = norm.bias.detach().double().cpu()
+            b = lin.bias.detach().double().cpu() if lin.bias is not None else torch.zeros(W.shape[0], dtype=torch.float64)
+            wg = (W * g[None, :]).to(torch.bfloat16)
+            c = wg.double().sum(dim=1)
+            d = W @ be + b
+            return wg.to(dev).contiguous(), c.float().to(dev).contiguous(), d.float().to(dev).contiguous()
+
         for blk in m.blocks:
-            qkv_b = blk.attn.qkv.bias
-            if qkv_b is None:
-                qkv_b = torch.zeros(3 * self.dim)
-            w += [f32(blk.norm1.weight), f32(blk.norm1.bias), bf16(blk.attn.qkv.weight), f32(qkv_b),
-                  bf16(blk.attn.proj.weight), f32(blk.attn.proj.bias), f32(blk.norm2.weight), f32(blk.norm2.bias),
-                  bf16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias), bf16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)]
+            qw, qc, qd = fold(blk.norm1, blk.attn.qkv)
+            fw, fc, fd = fold(blk.norm2, blk.mlp.fc1)
+            w += [qw, qc, qd, bf16(blk.attn.proj.weight), f32(blk.attn.proj.bias),
+                  fw, fc, fd, bf16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)]
         self.weights = w                              # keeps the device copies alive
         if self.kind == "vit4k":
             self.phi_w = bf16(m.phi[0].weight)
@@ -196,7 +207,7 @@ class VitEngine:
         _lib.check(self.lib.hb_vit_plan_set_depth_limit(self.plan, n))
 
     def buffer(self, which, rows, cols, dtype):
-        """View of a workspace buffer (0 x fp32, 1 LN out, 2 qkv, 3 attention out, 4 hidden) as [rows, cols]."""
+        """View of a workspace buffer (0 x fp32, 1 bf16 copy of x, 2 qkv, 3 attention out, 4 hidden) as [rows, cols]."""
         p, nb = C.c_void_p(), C.c_size_t()
         _lib.check(self.lib.hb_vit_plan_buffer(self.plan, which, C.byref(p), C.byref(nb)))
         off = p.value - self._ws_raw.data_ptr()

@@ -29,6 +29,9 @@ extern "C" {
 #define HB_EPI_TOKENS_F32 3       /* token rows: out_f32[(r/T)*(T+1)+1+r%T, :] = A W^T + bias + table[1+r%T, :] */
 #define HB_EPI_TOKENS_GELU_F32 4  /* same with gelu_erf applied before the table add               */
 #define HB_EPI_BIAS_GELU_FAST_BF16 5 /* as 1 with the tanh-form GELU fitted to erf (|err| <= 3e-4 |x|), MLP hot path */
+#define HB_EPI_LNFOLD_BF16 6         /* hb_gemm_lnfold_bf16 */
+#define HB_EPI_LNFOLD_GELU_BF16 7    /* hb_gemm_lnfold_bf16 with gelu */
+#define HB_EPI_RESID_STATS_F32 8     /* hb_gemm_resid_stats */
 
 int hb_abi_version(void);
 const char* hb_last_error(void);
@@ -66,6 +69,19 @@ int hb_prof_read(double* ms_by_kind, long long* count_by_kind, int n_kinds);
 int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int epilogue, void* out, int M, int N,
                  int K, const float* tok_table, int tokens_per_seq, void* stream);
 
+/* LayerNorm followed by Linear (norm1 -> attn.qkv, norm2 -> mlp.fc1 [+ GELU]; vision_transformer.py:147,151) as ONE GEMM:
+ * xb_bf16 [M,K] is the UN-normalised residual stream in bf16, w_gamma_bf16 [N,K] = bf16(W * gamma), c[j] = sum_k of
+ * that rounded weight's row j, d[j] = sum_k beta_k W_jk + bias_j, row_stats [M,2] = (sum, sum of squares) of the fp32
+ * rows.  out[r,j] = act(rstd_r * acc[r,j] - rstd_r * mu_r * c[j] + d[j]). */
+int hb_gemm_lnfold_bf16(const void* xb_bf16, const void* w_gamma_bf16, const float* c, const float* d,
+                        const float* row_stats, float eps, int gelu, void* out_bf16, int M, int N, int K, void* stream);
+
+/* Residual update x = x + drop_path(Linear(a)) (vision_transformer.py:149,151) with the bookkeeping the next folded
+ * LayerNorm needs: x_f32 [M,N] updated in place, xb_bf16 [M,N] = bf16(x), stats_out [M,2] += (sum, sum of squares)
+ * of the new rows (must be zero on entry), stats_clear [M,2] (may be NULL) zeroed. */
+int hb_gemm_resid_stats(const void* a_bf16, const void* w_bf16, const float* bias, float* x_f32, void* xb_bf16,
+                        float* stats_out, float* stats_clear, int M, int N, int K, void* stream);
+
 /* nn.LayerNorm(dim, eps): vision_transformer.py:138,142,195.  x fp32 rows at x_row_stride (elements);
  * writes out_bf16 and/or out_f32 (either may be NULL), densely packed [rows, dim].  dim in {384, 192}. */
 int hb_layernorm(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps, void* out_bf16,
@@ -100,16 +116,15 @@ typedef struct hb_vit_config {
     float ln_eps;  /* 1e-6 */
 } hb_vit_config;
 
-/* weights[]: [0] cls_token f32[dim], [1] norm.weight, [2] norm.bias, then for block i at 3+12*i:
- * norm1.weight, norm1.bias, attn.qkv.weight (bf16 [3dim,dim]), attn.qkv.bias, attn.proj.weight (bf16), attn.proj.bias,
- * norm2.weight, norm2.bias, mlp.fc1.weight (bf16 [mlp,dim]), mlp.fc1.bias, mlp.fc2.weight (bf16 [dim,mlp]), mlp.fc2.bias.
- * All other entries fp32. */
+/* weights[]: [0] cls_token f32[dim], [1] norm.weight, [2] norm.bias, then for block i at 3+10*i (LayerNorms folded, see
+ * hb_gemm_lnfold_bf16): qkv w_gamma (bf16 [3dim,dim]), qkv c, qkv d, attn.proj.weight (bf16), attn.proj.bias,
+ * fc1 w_gamma (bf16 [mlp,dim]), fc1 c, fc1 d, mlp.fc2.weight (bf16 [dim,mlp]), mlp.fc2.bias.  Non-weight entries fp32. */
 size_t hb_vit_workspace_bytes(const hb_vit_config* cfg);
 int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host, int n_weights, void* workspace,
                        size_t workspace_bytes, hb_vit_plan** plan_out);
 void hb_vit_plan_destroy(hb_vit_plan* plan);
 /* debug / test hooks: run only the first `depth_limit` blocks (<=0: all); fetch a workspace buffer
- * (0 = x fp32 residual stream, 1 = LN out bf16, 2 = qkv bf16, 3 = attention out bf16, 4 = MLP hidden bf16) */
+ * (0 = x fp32 residual stream, 1 = bf16 copy of x, 2 = qkv bf16, 3 = attention out bf16, 4 = MLP hidden bf16) */
 int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit);
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes);
 

@@ -37,6 +37,6 @@ def test_config_struct_layout_matches_header():
     assert ctypes.sizeof(HbVitConfig) == 24
     lib = __import__("hipt_abmil_atec23_b200._lib", fromlist=["load"]).load()
     cfg = HbVitConfig(384, 6, 12, 1536, 256 * 257, 1e-6)
-    rows = 65792
-    expect = rows * 384 * 4 + rows * 384 * 2 + rows * 384 * 6 + rows * 384 * 2 + rows * 1536 * 2
+    rows = 65792                                       # = 257 * 256: already a multiple of the 256-row pair tile
+    expect = rows * 384 * 4 + rows * 384 * 2 + rows * 384 * 6 + rows * 384 * 2 + rows * 1536 * 2 + 2 * rows * 8
     assert lib.hb_vit_workspace_bytes(ctypes.byref(cfg)) == expect

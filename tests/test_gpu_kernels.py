@@ -64,6 +64,54 @@ def test_gemm_resadd_f32(M, N, K):
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("M,N,K,gelu", [(257, 1152, 384, False), (65792, 1152, 384, False), (65792, 1536, 384, True),
+                                        (1000, 576, 192, False), (300, 768, 192, True)])
+def test_gemm_layernorm_folded(M, N, K, gelu):
+    """LayerNorm(eps 1e-6) + Linear (+GELU) as one GEMM over the un-normalised bf16 rows, against fp32
+    F.layer_norm -> F.linear -> F.gelu on the same fp32 rows."""
+    L = _lib()
+    x = (_rand((M, K), 50, 1.5) + 0.3 * _rand((1, K), 51)).cuda()          # per-channel offsets: non-zero row means
+    gamma = (1.0 + 0.2 * _rand((K,), 52)).cuda()
+    beta = (0.1 * _rand((K,), 53)).cuda()
+    W = _rand((N, K), 54, 0.05).cuda()
+    b = _rand((N,), 55, 0.1).cuda()
+    wg = (W * gamma[None, :]).bfloat16()
+    c = wg.float().sum(1)
+    d = W @ beta + b
+    stats = torch.stack([x.sum(1), (x * x).sum(1)], dim=1).contiguous()
+    out = L.gemm_lnfold_bf16(x.bfloat16(), wg, c, d, stats, 1e-6, gelu=gelu)
+    ref = F.linear(F.layer_norm(x, (K,), gamma, beta, 1e-6), W, b)
+    if gelu:
+        ref = F.gelu(ref)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 3e-2 * max(1.0, ref.abs().max().item()), err
+    assert F.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() > 0.9999
+
+
+@pytest.mark.parametrize("M,N,K", [(257, 384, 384), (1000, 384, 1536), (65792, 384, 1536), (65792, 384, 384), (257, 192, 768)])
+def test_gemm_residual_with_row_stats(M, N, K):
+    L = _lib()
+    a = _rand((M, K), 60).cuda().bfloat16()
+    w = _rand((N, K), 61, 0.05).cuda().bfloat16()
+    b = _rand((N,), 62, 0.1).cuda()
+    x0 = _rand((M, N), 63).cuda()
+    x = x0.clone()
+    xb = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros((M, 2), device="cuda")
+    other = torch.full((M, 2), 5.0, device="cuda")
+    L.gemm_resid_stats(a, w, b, x, xb, stats, other)
+    ref = x0 + a.float() @ w.float().t() + b
+    assert (x - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(xb, x.bfloat16())
+    assert torch.allclose(stats[:, 0], x.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (x * x).sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.all(other == 0)
+    # run-to-run determinism of the statistics (one atomic per (row, n-tile), two n-tiles: order independent)
+    x2 = x0.clone(); stats2 = torch.zeros((M, 2), device="cuda")
+    L.gemm_resid_stats(a, w, b, x2, xb, stats2, None)
+    assert torch.equal(stats2, stats) and torch.equal(x2, x)
+
+
 @pytest.mark.parametrize("n_seq,T,N,K,gelu", [(3, 256, 384, 768, False), (2, 256, 192, 384, True), (3, 35, 192, 384, True)])
 def test_gemm_tokens(n_seq, T, N, K, gelu):
     L = _lib()
