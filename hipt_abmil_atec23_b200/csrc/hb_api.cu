@@ -2,6 +2,7 @@
 // kernels of a ViT forward (HIPT_4K/vision_transformer.py:248-253, vision_transformer4k.py:241-246).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -115,6 +116,7 @@ using namespace hb;
 struct hb_vit_plan {
     hb_vit_config cfg;
     int depth_limit;
+    bool cls_only_last;
     // workspace carve-up
     float* x;          // [max_rows, dim] fp32 residual stream
     void* xb;          // [max_rows, dim] bf16 copy of the residual stream (A operand of the LN-folded GEMMs)
@@ -259,6 +261,10 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
     if (!p) return set_error("hb_vit_plan_create: out of host memory");
     p->cfg = *cfg;
     p->depth_limit = cfg->depth;
+    {
+        const char* e = getenv("HB_VIT_FULL_LAST_BLOCK");   // debug: compute every token in the last block too
+        p->cls_only_last = !(e && e[0] == '1');
+    }
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     p->x = reinterpret_cast<float*>(ws + L.x);
     p->xb = ws + L.xb;
@@ -319,9 +325,29 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
     const int D = c.dim, hd = D / c.heads;
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
     const int kb = (D == 192) ? HB_PROF_4K_OFFSET : 0;     // profiler kind base: ViT-256 vs ViT-4K
+    // forward() returns x[:, 0] only, so after the K / V of the LAST block exist nothing but the CLS rows matters:
+    // its attention, proj, fc1 and fc2 run on n_seq rows instead of n_seq * seq_len.
+    const bool cls_tail = p->cls_only_last && p->depth_limit == c.depth;
     for (int i = 0; i < p->depth_limit; ++i) {
         GemmArgs g = p->g_qkv[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_QKV_GEMM, st); if (gemm_launch(g, st)) return -1; }
+        if (cls_tail && i == c.depth - 1) {
+            const void* const* w = &p->w[3 + 10 * i];
+            { ProfScope ps(kb + HB_PROF_ATTENTION, st);
+              if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st, 1)) return -1; }
+            const size_t pitch = static_cast<size_t>(seq_len) * D * 4;
+            GemmAux r1 = {}, a2 = {}, r2 = {};
+            r1.stats_out = p->stats2;                       // compact: row r = sequence r (stats2 is zero here)
+            a2.colvec2 = static_cast<const float*>(w[6]); a2.row_stats = p->stats2; a2.inv_dim = 1.0f / D; a2.eps = c.ln_eps;
+            GemmArgs gp, g1, g2;
+            if (gemm_prepare(gp, p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_STATS_F32, p->x, n_seq, D, D, nullptr, 0, &r1, p->xb, pitch)) return -1;
+            if (gemm_prepare(g1, p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU_BF16, p->hid, n_seq, c.mlp_dim, D, nullptr, 0, &a2)) return -1;
+            if (gemm_prepare(g2, p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_STATS_F32, p->x, n_seq, D, c.mlp_dim, nullptr, 0, &r2, p->xb, pitch)) return -1;
+            { ProfScope ps(kb + HB_PROF_PROJ_GEMM, st); if (gemm_launch(gp, st)) return -1; }
+            { ProfScope ps(kb + HB_PROF_FC1_GEMM, st); if (gemm_launch(g1, st)) return -1; }
+            { ProfScope ps(kb + HB_PROF_FC2_GEMM, st); if (gemm_launch(g2, st)) return -1; }
+            break;
+        }
         { ProfScope ps(kb + HB_PROF_ATTENTION, st);
           if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st)) return -1; }
         g = p->g_proj[i]; g.M = M;

@@ -127,7 +127,9 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[HD / 16][4], uin
 template <int HD>
 __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         __nv_bfloat16* __restrict__ out, int seq_len, int heads,
-                                                        float scale_log2) {
+                                                        float scale_log2, int cls_only) {
+    // cls_only: only query row 0 of each sequence is computed and written to a COMPACT [n_seq, D] output — all that
+    // the last transformer block needs, because forward() returns x[:, 0] (vision_transformer.py:252-253).
     extern __shared__ __align__(128) uint8_t smem_attn[];
     constexpr int CH = HD / 8;                              // 16 B chunks per row
     const int s_pad = (seq_len + 15) & ~15;
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* 
         const int rem = idx - which * per_mat;
         const int r = rem / CH, c = rem - r * CH;
         const uint32_t dst = sQ + which * mat_bytes + swz_off<HD>(r, c);
+        if (cls_only && which == 0 && r >= 16) continue;
         if (r < seq_len) {
             cp_async_16(dst, base + static_cast<size_t>(r) * 3 * D + which * D + c * 8);
         } else {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* 
     cp_async_wait_all();
     __syncthreads();
 
-    const int q_tiles = s_pad / 16;
+    const int q_tiles = cls_only ? 1 : s_pad / 16;
     const int full_chunks = s_pad / 64;
     const int tail_groups = (s_pad - full_chunks * 64) / 16;    // 0..3 groups of 16 keys
     const bool full_has_pad = (full_chunks * 64 > seq_len);     // only when tail_groups == 0 and seq_len % 64 != 0
@@ -188,6 +191,15 @@ __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* 
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
         const int r0 = qt * 16 + (lane >> 2), r1 = r0 + 8;
+        if (cls_only) {
+            if ((lane >> 2) == 0) {
+                __nv_bfloat16* orow = out + static_cast<size_t>(seq) * D + h * HD + (lane & 3) * 2;
+#pragma unroll
+                for (int d = 0; d < HD / 8; ++d)
+                    *reinterpret_cast<uint32_t*>(orow + d * 8) = pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0);
+            }
+            continue;
+        }
         __nv_bfloat16* obase = out + static_cast<size_t>(seq) * seq_len * D + h * HD + (lane & 3) * 2;
 #pragma unroll
         for (int d = 0; d < HD / 8; ++d) {
@@ -555,10 +567,10 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
 }
 
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int cls_only) {
     if (n_seq <= 0) return 0;
     if (seq_len <= 0 || heads <= 0) return set_error("hb_attention: bad shape");
-    if (seq_len == ATC_S && head_dim == 64 && !attention_force_legacy())
+    if (seq_len == ATC_S && head_dim == 64 && !attention_force_legacy() && !cls_only)
         return attention_tc_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream);
     const int s_pad = (seq_len + 15) & ~15;
     const size_t smem = static_cast<size_t>(3) * s_pad * head_dim * 2;
@@ -567,18 +579,19 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
     int warps = (q_tiles + 1) / 2;
     if (warps > 9) warps = 9;
     if (warps < 1) warps = 1;
+    if (cls_only) warps = 4;                         // all four stage K / V, warp 0 computes the single query tile
     const float scale_log2 = scale * 1.4426950408889634f;
     const unsigned grid = static_cast<unsigned>(n_seq) * heads;
     if (head_dim == 64) {
         auto k = attention_kernel<64>;
         HB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
-                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2);
+                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only);
     } else if (head_dim == 32) {
         auto k = attention_kernel<32>;
         HB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
-                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2);
+                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only);
     } else {
         return set_error("hb_attention: head_dim %d not supported (64 or 32)", head_dim);
     }

@@ -333,27 +333,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             tmem_ld_wait();
                             const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 64 + h * 32);
                             const float4* c4 = LNFOLD ? reinterpret_cast<const float4*>(aux.colvec2 + n0 + c * 64 + h * 32) : b4;
+                            [[maybe_unused]] const f32x2_t rstd2 = f2_pack(rstd, rstd), nrm2 = f2_pack(nrm, nrm);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 b = __ldg(b4 + j);
-                                float f0, f1, f2, f3;
-                                if constexpr (LNFOLD) {
+                                f32x2_t y0 = f2_pack(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]));
+                                f32x2_t y1 = f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                                if constexpr (LNFOLD) {      // rstd * acc + (nrm * c + d)
                                     const float4 cc = __ldg(c4 + j);
-                                    f0 = fmaf(rstd, __uint_as_float(v[4 * j + 0]), fmaf(nrm, cc.x, b.x));
-                                    f1 = fmaf(rstd, __uint_as_float(v[4 * j + 1]), fmaf(nrm, cc.y, b.y));
-                                    f2 = fmaf(rstd, __uint_as_float(v[4 * j + 2]), fmaf(nrm, cc.z, b.z));
-                                    f3 = fmaf(rstd, __uint_as_float(v[4 * j + 3]), fmaf(nrm, cc.w, b.w));
+                                    y0 = f2_fma(rstd2, y0, f2_fma(nrm2, f2_pack(cc.x, cc.y), f2_pack(b.x, b.y)));
+                                    y1 = f2_fma(rstd2, y1, f2_fma(nrm2, f2_pack(cc.z, cc.w), f2_pack(b.z, b.w)));
                                 } else {
-                                    f0 = __uint_as_float(v[4 * j + 0]) + b.x; f1 = __uint_as_float(v[4 * j + 1]) + b.y;
-                                    f2 = __uint_as_float(v[4 * j + 2]) + b.z; f3 = __uint_as_float(v[4 * j + 3]) + b.w;
+                                    y0 = f2_add(y0, f2_pack(b.x, b.y));
+                                    y1 = f2_add(y1, f2_pack(b.z, b.w));
                                 }
-                                if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-                                    f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
-                                } else if constexpr (EPI == EPI_BIAS_GELU_FAST_BF16 || EPI == EPI_LNFOLD_GELU_BF16) {
-                                    f0 = gelu_fast(f0); f1 = gelu_fast(f1); f2 = gelu_fast(f2); f3 = gelu_fast(f3);
+                                if constexpr (EPI == EPI_BIAS_GELU_FAST_BF16 || EPI == EPI_LNFOLD_GELU_BF16) {
+                                    pk[h * 16 + 2 * j] = gelu_fast2_bf16(y0);
+                                    pk[h * 16 + 2 * j + 1] = gelu_fast2_bf16(y1);
+                                } else {
+                                    float f0, f1, f2, f3;
+                                    f2_unpack(y0, f0, f1);
+                                    f2_unpack(y1, f2, f3);
+                                    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                                        f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+                                    }
+                                    pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
+                                    pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
                                 }
-                                pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
-                                pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
                             }
                         }
                         // the TMA store that last read this warpgroup's staging buffer must have drained it
@@ -498,7 +504,7 @@ int gemm_pick_bn(int N) {
 }
 
 int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, int epi, void* out, int M, int N, int K,
-                 const float* tok_table, int tokens_per_seq, const GemmAux* aux, void* xb_out) {
+                 const float* tok_table, int tokens_per_seq, const GemmAux* aux, void* xb_out, size_t out_pitch_bytes) {
     if (M <= 0 || N <= 0 || K <= 0) return set_error("hb_gemm: bad shape M=%d N=%d K=%d", M, N, K);
     if (K % GEMM_BK != 0) return set_error("hb_gemm: K=%d must be a multiple of %d", K, GEMM_BK);
     const int bn = gemm_pick_bn(N);
@@ -520,7 +526,9 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
             return set_error("hb_gemm: the LayerNorm-folded epilogue needs the column vector c and the row statistics");
         if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, GEMM_BM, 64)) return -1;
     } else if (epi == EPI_BIAS_RESADD_F32 || epi == EPI_RESID_STATS_F32) {
-        if (encode_tmap_2d(&g.map_out, TMAP_F32, out, M, N, static_cast<uint64_t>(N) * 4, GEMM_BM, 32)) return -1;
+        // out_pitch_bytes: the fp32 rows may be strided (the CLS rows of a [n_seq, seq_len, N] residual stream)
+        const uint64_t pitch = out_pitch_bytes ? out_pitch_bytes : static_cast<uint64_t>(N) * 4;
+        if (encode_tmap_2d(&g.map_out, TMAP_F32, out, M, N, pitch, GEMM_BM, 32)) return -1;
         if (epi == EPI_RESID_STATS_F32) {
             if (!xb_out) return set_error("hb_gemm: the residual epilogue needs the bf16 output");
             if (encode_tmap_2d(&g.map_xb, TMAP_BF16, xb_out, M, N, static_cast<uint64_t>(N) * 2, GEMM_BM, 32, 64)) return -1;

@@ -51,14 +51,15 @@ struct GemmArgs {
 };
 int gemm_pick_bn(int N);
 int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, int epi, void* out, int M, int N, int K,
-                 const float* tok_table, int tokens_per_seq, const GemmAux* aux = nullptr, void* xb_out = nullptr);
+                 const float* tok_table, int tokens_per_seq, const GemmAux* aux = nullptr, void* xb_out = nullptr,
+                 size_t out_pitch_bytes = 0);
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
 
 // elementwise / row kernels
 int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps,
                      void* out_bf16, float* out_f32, int rows, int dim, cudaStream_t stream);
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int cls_only = 0);
 int im2col_launch(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
                   int grid_cols, int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream);
 int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, void* xb_bf16, float* stats, int n_seq,

@@ -288,4 +288,47 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes per issue slot in the epilogues
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// gelu_fast on two values at once; returns them packed as bf16x2 (lo in the low half)
+__device__ __forceinline__ uint32_t gelu_fast2_bf16(f32x2_t x) {
+    f32x2_t x2 = f2_mul(x, x);
+    float a, b;
+    f2_unpack(x2, a, b);
+    x2 = f2_pack(fminf(a, 50.0f), fminf(b, 50.0f));
+    f32x2_t p = f2_fma(x2, f2_pack(-0.00035151678813682844f, -0.00035151678813682844f),
+                       f2_pack(0.03700564602178616f, 0.03700564602178616f));
+    p = f2_fma(p, x2, f2_pack(0.7975078842899392f, 0.7975078842899392f));
+    f2_unpack(f2_mul(p, x), a, b);
+    float ta, tb;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+    const f32x2_t hx = f2_mul(x, f2_pack(0.5f, 0.5f));
+    f2_unpack(f2_fma(hx, f2_pack(ta, tb), hx), a, b);
+    return pack_bf16x2(a, b);
+}
+
 }  // namespace hb

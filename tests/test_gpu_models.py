@@ -49,8 +49,10 @@ def test_vit256_per_block_against_reference(gold, hipt):
             eng.set_depth_limit(depth)
             eng.forward_patches(x)
             torch.cuda.synchronize()
-            tok = eng.buffer(0, 2 * 257, 384, torch.float32).view(2, 257, 384)[:, :3].cpu()
-            ref = g["tokens_first3_per_block"][depth]
+            # the last block updates only the CLS rows (forward() returns x[:, 0]): compare 1 token at full depth
+            nt = 1 if depth == 12 else 3
+            tok = eng.buffer(0, 2 * 257, 384, torch.float32).view(2, 257, 384)[:, :nt].cpu()
+            ref = g["tokens_first3_per_block"][depth][:, :nt]
             err = (tok - ref).abs().max().item()
             print(f"depth {depth}: max abs {err:.4e}, cos {_cos(tok, ref):.6f}")
             assert _cos(tok, ref) > 0.9995, depth
