@@ -9,7 +9,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libhipt_b200.so")
+LIB_PATH = os.environ.get("HB_LIB_PATH") or os.path.join(_PKG, "lib", "libhipt_b200.so")   # override: kernel experiments
 
 HB_EPI_BIAS_BF16 = 0
 HB_EPI_BIAS_GELU_BF16 = 1

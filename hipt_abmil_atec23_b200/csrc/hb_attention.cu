@@ -235,7 +235,7 @@ constexpr int ATC_S = 257;
 constexpr int ATC_SPAD = 272;
 constexpr int ATC_KV_BYTES = ATC_SPAD * 128;            // 34816: [272 keys][64 bf16]
 constexpr int ATC_TILE_BYTES = 128 * 128;               // 16384: one 128-row x 128-byte swizzled tile
-constexpr int ATC_SMEM = 4 * ATC_KV_BYTES + 4 * ATC_TILE_BYTES + 512 + 1024;
+constexpr int ATC_SMEM = 3 * ATC_KV_BYTES + 6 * ATC_TILE_BYTES + 512 + 1024;
 constexpr int ATC_TMEM_COLS = 512;
 
 __device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
@@ -251,9 +251,13 @@ __device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
         : "memory");
 }
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef ATC_EXP_NOMUFU
+    return fmaf(x, 0.001f, 1.0f);        // timing experiment only
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -264,34 +268,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                     __nv_bfloat16* __restrict__ out, int n_items, int heads, float scale_log2) {
     extern __shared__ uint8_t smem_raw_atc[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_atc) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem;                                   // [2 stages][34816]
-    uint8_t* sV = sK + 2 * ATC_KV_BYTES;                  // [2 stages][34816]
+    uint8_t* sK = smem;                                   // [34816]            K is dead once Q K^T is done: one buffer
+    uint8_t* sV = sK + ATC_KV_BYTES;                      // [2 stages][34816]
     uint8_t* sQ = sV + 2 * ATC_KV_BYTES;                  // [2 pipelines][16384]
-    uint8_t* sP = sQ + 2 * ATC_TILE_BYTES;                // [2 pipelines][16384]  P atom slot, then O staging
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATC_TILE_BYTES);
-    uint64_t* kv_full = bars;            // [2 stages]
-    uint64_t* kv_empty = bars + 2;       // [2 stages]  2 MMA commits + tail warp
-    uint64_t* q_full = bars + 4;         // [2 pipelines]
-    uint64_t* q_empty = bars + 6;        // [2]  MMA commit + 128 softmax threads (they read their Q row for key 256)
-    uint64_t* s_full = bars + 8;         // [2]
-    uint64_t* o_full = bars + 10;        // [2]
-    uint64_t* o_free = bars + 12;        // [2]  128 softmax threads: O (= the S region) may be overwritten
-    uint64_t* p_full = bars + 14;        // [2]  128 softmax threads
-    uint64_t* p_empty = bars + 16;       // [2]  MMA commit
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint8_t* sP = sQ + 2 * ATC_TILE_BYTES;                // [2 pipelines][2 slots][16384]  P atoms; slot 0 also stages O
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATC_TILE_BYTES);
+    uint64_t* k_full = bars;             // [1]
+    uint64_t* k_empty = bars + 1;        // [1]  2 MMA commits + 256 softmax threads (key-256 dot) + tail warp
+    uint64_t* v_full = bars + 2;         // [2 stages]
+    uint64_t* v_empty = bars + 4;        // [2 stages]  2 MMA commits + tail warp
+    uint64_t* q_full = bars + 6;         // [2 pipelines]
+    uint64_t* q_empty = bars + 8;        // [2]  MMA commit + 128 softmax threads (they read their Q row for key 256)
+    uint64_t* s_full = bars + 10;        // [2]
+    uint64_t* o_full = bars + 12;        // [2]
+    uint64_t* o_free = bars + 14;        // [2]  128 softmax threads: O (= the S region) may be overwritten
+    uint64_t* p_full = bars + 16;        // [2 pipelines][2 slots]  128 softmax threads
+    uint64_t* p_empty = bars + 20;       // [2][2]  MMA commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = heads * 64;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); tma_prefetch_desc(&map_out); }
     if (warp == 1 && lane == 0) {
+        mbar_init(k_full, 1); mbar_init(k_empty, 2 + 256 + 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 3);
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 3);
             mbar_init(&q_full[i], 1);  mbar_init(&q_empty[i], 129);
             mbar_init(&s_full[i], 1);
             mbar_init(&o_full[i], 1);  mbar_init(&o_free[i], 128);
-            mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
         }
+        for (int i = 0; i < 4; ++i) { mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1); }
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, ATC_TMEM_COLS); tmem_relinquish(); }
@@ -311,22 +318,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 const int seq = item / heads, h = item - seq * heads;
                 const int row0 = seq * ATC_S;
                 const int st = it & 1;
-                mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * ATC_KV_BYTES);
-                uint8_t* k = sK + st * ATC_KV_BYTES;
-                uint8_t* v = sV + st * ATC_KV_BYTES;
-                tma_load_2d(k, &map128, &kv_full[st], D + h * 64, row0);
-                tma_load_2d(k + ATC_TILE_BYTES, &map128, &kv_full[st], D + h * 64, row0 + 128);
-                tma_load_2d(k + 2 * ATC_TILE_BYTES, &map16, &kv_full[st], D + h * 64, row0 + 256);
-                tma_load_2d(v, &map128, &kv_full[st], 2 * D + h * 64, row0);
-                tma_load_2d(v + ATC_TILE_BYTES, &map128, &kv_full[st], 2 * D + h * 64, row0 + 128);
-                tma_load_2d(v + 2 * ATC_TILE_BYTES, &map16, &kv_full[st], 2 * D + h * 64, row0 + 256);
+                mbar_wait(k_empty, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full, ATC_KV_BYTES);
+                tma_load_2d(sK, &map128, k_full, D + h * 64, row0);
+                tma_load_2d(sK + ATC_TILE_BYTES, &map128, k_full, D + h * 64, row0 + 128);
+                tma_load_2d(sK + 2 * ATC_TILE_BYTES, &map16, k_full, D + h * 64, row0 + 256);
 #pragma unroll
                 for (int x = 0; x < 2; ++x) {
                     mbar_wait(&q_empty[x], (it & 1) ^ 1);
                     mbar_arrive_expect_tx(&q_full[x], ATC_TILE_BYTES);
                     tma_load_2d(sQ + x * ATC_TILE_BYTES, &map128, &q_full[x], h * 64, row0 + x * 128);
                 }
+                mbar_wait(&v_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&v_full[st], ATC_KV_BYTES);
+                uint8_t* v = sV + st * ATC_KV_BYTES;
+                tma_load_2d(v, &map128, &v_full[st], 2 * D + h * 64, row0);
+                tma_load_2d(v + ATC_TILE_BYTES, &map128, &v_full[st], 2 * D + h * 64, row0 + 128);
+                tma_load_2d(v + 2 * ATC_TILE_BYTES, &map16, &v_full[st], 2 * D + h * 64, row0 + 256);
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -337,35 +345,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
             const uint32_t t_acc = tmem_base + x * 256;
             const uint64_t dq = umma_desc_k128(smem_u32(sQ + x * ATC_TILE_BYTES));
-            const uint64_t dp = umma_desc_k128(smem_u32(sP + x * ATC_TILE_BYTES));
+            const uint64_t dk = umma_desc_k128(smem_u32(sK));
+            uint32_t use0 = 0, use1 = 0;                                           // uses of P slot 0 / 1 so far
             for (int it = 0; it < my_items; ++it) {
                 const int st = it & 1;
-                mbar_wait(&kv_full[st], (it >> 1) & 1);
+                mbar_wait(k_full, it & 1);
                 mbar_wait(&q_full[x], it & 1);
                 if (it > 0) mbar_wait(&o_free[x], (it - 1) & 1);
                 tc_fence_after();
-                const uint64_t dk = umma_desc_k128(smem_u32(sK + st * ATC_KV_BYTES));
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(t_acc, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
                 umma_commit(&s_full[x]);
                 umma_commit(&q_empty[x]);
+                umma_commit(k_empty);
+                mbar_wait(&v_full[st], (it >> 1) & 1);
                 const uint32_t v_base = smem_u32(sV + st * ATC_KV_BYTES);
                 for (int a = 0; a < 5; ++a) {
-                    mbar_wait(&p_full[x], (it * 5 + a) & 1);
+                    const int slot = a & 1;
+                    const uint32_t use = slot ? use1++ : use0++;
+                    mbar_wait(&p_full[x * 2 + slot], use & 1);
                     tc_fence_after();
+                    const uint64_t dp = umma_desc_k128(smem_u32(sP + (x * 2 + slot) * ATC_TILE_BYTES));
                     const int ksteps = (a < 4) ? 4 : 1;
                     for (int kk = 0; kk < ksteps; ++kk) {
                         const uint64_t dv = umma_desc_k128(v_base + (a * 64 + kk * 16) * 128);
                         umma_bf16_ss(t_acc, dp + 2 * kk, dv, idesc_pv, (a | kk) != 0);
                     }
-                    umma_commit(&p_empty[x]);
+                    umma_commit(&p_empty[x * 2 + slot]);
                 }
                 umma_commit(&o_full[x]);
-                umma_commit(&kv_empty[st]);
+                umma_commit(&v_empty[st]);
             }
         }
     } else if (warp == 3) {
         // ------------------------------------------------------------------------------------------ query row 256
+        // One warp, mma.sync: all 272 scores of the row first (K can then be released), one softmax pass in
+        // registers, then P V.  Only fragment row 0 (lanes 0-3) is real; the other rows compute on zeros.
+        const int t2 = (lane & 3) * 2;
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const int seq = item / heads, h = item - seq * heads;
@@ -383,31 +399,81 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                     qf[kk][1] = 0u; qf[kk][3] = 0u;
                 }
             }
-            mbar_wait(&kv_full[st], (it >> 1) & 1);
+            mbar_wait(k_full, it & 1);
 #ifdef ATC_SKIP_TAIL
             __syncwarp();
-            if (lane == 0) mbar_arrive(&kv_empty[st]);
+            if (lane == 0) { mbar_arrive(k_empty); mbar_wait(&v_full[st], (it >> 1) & 1); mbar_arrive(&v_empty[st]); }
             continue;
 #endif
-            const uint32_t k_addr = smem_u32(sK + st * ATC_KV_BYTES), v_addr = smem_u32(sV + st * ATC_KV_BYTES);
+            const uint32_t k_addr = smem_u32(sK);
+            float sc[34][2];
+#pragma unroll
+            for (int g = 0; g < 17; ++g) {
+                float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int key = g * 16 + (lane & 7) + ((lane >> 4) << 3);
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(k_addr + swz_off<64>(key, kk * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+                    mma_bf16_16816(c0, qf[kk], b0, b1);
+                    mma_bf16_16816(c1, qf[kk], b2, b3);
+                }
+                sc[2 * g][0] = c0[0]; sc[2 * g][1] = c0[1];
+                sc[2 * g + 1][0] = c1[0]; sc[2 * g + 1][1] = c1[1];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(k_empty);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 34; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (j * 8 + t2 + e >= ATC_S) sc[j][e] = -INFINITY;
+                    mx = fmaxf(mx, sc[j][e]);
+                }
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float neg_m = -mx * scale_log2;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 34; ++j) {
+                sc[j][0] = ex2_approx(fmaf(sc[j][0], scale_log2, neg_m));
+                sc[j][1] = ex2_approx(fmaf(sc[j][1], scale_log2, neg_m));
+                sum += sc[j][0] + sc[j][1];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            mbar_wait(&v_full[st], (it >> 1) & 1);
+            const uint32_t v_addr = smem_u32(sV + st * ATC_KV_BYTES);
             float o[8][4];
 #pragma unroll
             for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
-            float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-            for (int c = 0; c < 4; ++c) attn_chunk<64, 4, false>(qf, k_addr, v_addr, c * 64, ATC_S, scale_log2, o, m, l, lane);
-            attn_chunk<64, 1, true>(qf, k_addr, v_addr, 256, ATC_S, scale_log2, o, m, l, lane);
-            float l0 = l[0];
-            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+#pragma unroll
+            for (int g = 0; g < 17; ++g) {
+                uint32_t pa[4];
+                pa[0] = pack_bf16x2(sc[2 * g][0], sc[2 * g][1]);
+                pa[1] = 0u;
+                pa[2] = pack_bf16x2(sc[2 * g + 1][0], sc[2 * g + 1][1]);
+                pa[3] = 0u;
+                const int key = g * 16 + (lane & 15);
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(v_addr + swz_off<64>(key, dd * 2 + (lane >> 4)), b0, b1, b2, b3);
+                    mma_bf16_16816(o[2 * dd], pa, b0, b1);
+                    mma_bf16_16816(o[2 * dd + 1], pa, b2, b3);
+                }
+            }
             if ((lane >> 2) == 0) {
-                const float inv = 1.0f / l0;
-                __nv_bfloat16* orow = out + row * D + h * 64 + (lane & 3) * 2;
+                const float inv = 1.0f / sum;
+                __nv_bfloat16* orow = out + row * D + h * 64 + t2;
 #pragma unroll
                 for (int d = 0; d < 8; ++d)
                     *reinterpret_cast<uint32_t*>(orow + d * 8) = pack_bf16x2(o[d][0] * inv, o[d][1] * inv);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&kv_empty[st]);
+            if (lane == 0) mbar_arrive(&v_empty[st]);
         }
     } else {
         // ------------------------------------------------------------------------------------------ softmax warpgroups
@@ -417,17 +483,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
         const int sw = r & 7;
         const bool leader = ((warp & 3) == 0 && lane == 0);
         uint8_t* q_row = sQ + x * ATC_TILE_BYTES + r * 128;
-        uint8_t* p_row = sP + x * ATC_TILE_BYTES + r * 128;
+        uint8_t* p_row0 = sP + (x * 2) * ATC_TILE_BYTES + r * 128;
+        uint8_t* p_row1 = p_row0 + ATC_TILE_BYTES;
+        uint32_t use0 = 0, use1 = 0;                          // uses of P slot 0 / 1 so far
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const int seq = item / heads, h = item - seq * heads;
-            const int st = it & 1;
             // ---- score against key 256: q_r . k_256 (row 256 of K is row 0 of its own swizzle atom: unswizzled)
-            mbar_wait(&kv_full[st], (it >> 1) & 1);
+            mbar_wait(k_full, it & 1);
             mbar_wait(&q_full[x], it & 1);
             float s256 = 0.f;
             {
-                const uint4* k256 = reinterpret_cast<const uint4*>(sK + st * ATC_KV_BYTES + 2 * ATC_TILE_BYTES);
+                const uint4* k256 = reinterpret_cast<const uint4*>(sK + 2 * ATC_TILE_BYTES);
                 float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -441,6 +508,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 s256 = acc0 + acc1;
             }
             mbar_arrive(&q_empty[x]);
+            mbar_arrive(k_empty);
 
             // ---- pass 1: row max over the 256 MMA scores (first 128 stay in registers) and key 256
             mbar_wait(&s_full[x], it & 1);
@@ -456,6 +524,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 m0 = fmaxf(m0, __uint_as_float(sv[j]));     m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
                 m2 = fmaxf(m2, __uint_as_float(sv[j + 2])); m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
             }
+#ifndef ATC_SKIP_RELOAD
 #pragma unroll
             for (int c = 4; c < 8; ++c) {
                 uint32_t tmp[32];
@@ -467,16 +536,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                     m2 = fmaxf(m2, __uint_as_float(tmp[j + 2])); m3 = fmaxf(m3, __uint_as_float(tmp[j + 3]));
                 }
             }
+#endif
             const float neg_m = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2;
 
-            // the TMA store of the previous tile must have drained the P slot (it doubles as the O staging buffer)
+            // the TMA store of the previous tile must have drained P slot 0 (it doubles as the O staging buffer)
             if (leader) tma_store_wait_read<0>();
             named_bar_sync(4 + x, 128);
 
-            // ---- pass 2: P atoms.  exp2 into registers first, then wait for the slot, store, publish.
+            // ---- pass 2: P atoms alternate between the two slots.  exp2 into registers, wait for the slot, publish.
             float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
+#ifndef ATC_SKIP_RELOAD
                 if (a == 2) {                                 // keys 128..255 come back from TMEM
                     tmem_ld_x32_ptr(t_row + 128, sv);
                     tmem_ld_x32_ptr(t_row + 160, sv + 32);
@@ -484,6 +555,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                     tmem_ld_x32_ptr(t_row + 224, sv + 96);
                     tmem_ld_wait();
                 }
+#endif
                 uint32_t pk[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -493,25 +565,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                     sum0 += p0; sum1 += p1;
                     pk[j] = pack_bf16x2(p0, p1);
                 }
-                mbar_wait(&p_empty[x], ((it * 5 + a) & 1) ^ 1);
+                const int slot = a & 1;
+                const uint32_t use = slot ? use1++ : use0++;
+                mbar_wait(&p_empty[x * 2 + slot], (use & 1) ^ 1);
+                uint8_t* p_row = slot ? p_row1 : p_row0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                     *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 fence_proxy_async_smem();
-                mbar_arrive(&p_full[x]);
+                mbar_arrive(&p_full[x * 2 + slot]);
             }
-            {                                                 // tail atom: key 256 (+ 15 zero columns)
+            {                                                 // tail atom (slot 0): key 256 (+ 15 zero columns)
                 const float p0 = ex2_approx(fmaf(s256, scale_log2, neg_m));
                 sum0 += p0;
-                mbar_wait(&p_empty[x], ((it * 5 + 4) & 1) ^ 1);
-                *reinterpret_cast<uint4*>(p_row + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p_row + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t use = use0++;
+                mbar_wait(&p_empty[x * 2], (use & 1) ^ 1);
+                *reinterpret_cast<uint4*>(p_row0 + ((0 ^ sw) << 4)) = make_uint4(pack_bf16x2(p0, 0.f), 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p_row0 + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                 fence_proxy_async_smem();
-                mbar_arrive(&p_full[x]);
+                mbar_arrive(&p_full[x * 2]);
             }
             const float inv = 1.0f / (sum0 + sum1);
 
-            // ---- epilogue: O (first 64 columns of the S region) -> bf16 -> swizzled staging (the P slot) -> TMA store
+            // ---- epilogue: O (first 64 columns of the S region) -> bf16 -> swizzled staging (P slot 0) -> TMA store
             mbar_wait(&o_full[x], it & 1);
             tc_fence_after();
             tmem_ld_x32_ptr(t_row, sv);
@@ -526,12 +602,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 w.y = pack_bf16x2(__uint_as_float(sv[8 * q + 2]) * inv, __uint_as_float(sv[8 * q + 3]) * inv);
                 w.z = pack_bf16x2(__uint_as_float(sv[8 * q + 4]) * inv, __uint_as_float(sv[8 * q + 5]) * inv);
                 w.w = pack_bf16x2(__uint_as_float(sv[8 * q + 6]) * inv, __uint_as_float(sv[8 * q + 7]) * inv);
-                *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = w;
+                *reinterpret_cast<uint4*>(p_row0 + ((q ^ sw) << 4)) = w;
             }
             fence_proxy_async_smem();
             named_bar_sync(4 + x, 128);
             if (leader) {
-                tma_store_2d(&map_out, sP + x * ATC_TILE_BYTES, h * 64, seq * ATC_S + x * 128);
+                tma_store_2d(&map_out, sP + (x * 2) * ATC_TILE_BYTES, h * 64, seq * ATC_S + x * 128);
                 tma_store_commit();
             }
         }
