@@ -17,6 +17,10 @@ HB_EPI_BIAS_RESADD_F32 = 2
 HB_EPI_TOKENS_F32 = 3
 HB_EPI_TOKENS_GELU_F32 = 4
 HB_EPI_BIAS_GELU_FAST_BF16 = 5
+HB_EPI_LNFOLD_BF16 = 6
+HB_EPI_LNFOLD_GELU_BF16 = 7
+HB_EPI_RESID_STATS_F32 = 8
+HB_EPI_LNFOLD_GELU2_BF16 = 9
 
 
 class HbVitConfig(C.Structure):
@@ -156,8 +160,8 @@ def gemm_bf16(a, w, bias, epilogue, out=None, tok_table=None, tokens_per_seq=0):
     return out
 
 
-def gemm_lnfold_bf16(xb, w_gamma, c, d, row_stats, eps, gelu=False):
-    """LayerNorm + Linear (+GELU) as one GEMM on the un-normalised bf16 rows (see hb_gemm_lnfold_bf16)."""
+def gemm_lnfold_bf16(xb, w_gamma, c, d, row_stats, eps, gelu=0):
+    """LayerNorm + Linear (+GELU) as one GEMM on the un-normalised bf16 rows (see hb_gemm_lnfold_bf16); gelu: 0 / 1 / 2 (2 x GELU)."""
     require_cuda(xb, "xb")
     device_check()
     M, K = xb.shape

@@ -111,8 +111,8 @@ using namespace hb;
 //   qkv  = LNFOLD(xb; Wqkv*gamma1)            A = bf16 residual stream, per-row (mu, rstd) from stats1
 //   att  = softmax(q k^T) v
 //   x   += att Wproj^T + b      (RESID)       writes x fp32, xb bf16, stats2 = row sums of the new x; clears stats1
-//   hid  = gelu(LNFOLD(xb; Wfc1*gamma2))      per-row factors from stats2
-//   x   += hid Wfc2^T + b       (RESID)       writes x, xb, stats1 (for the next block); clears stats2
+//   hid  = 2 gelu(LNFOLD(xb; Wfc1*gamma2))    per-row factors from stats2 (the 0.5 lives in the fc2 weights)
+//   x   += hid (Wfc2/2)^T + b   (RESID)       writes x, xb, stats1 (for the next block); clears stats2
 struct hb_vit_plan {
     hb_vit_config cfg;
     int depth_limit;
@@ -171,7 +171,8 @@ int hb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
 
 int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int epilogue, void* out, int M, int N,
                  int K, const float* tok_table, int tokens_per_seq, void* stream) {
-    if (epilogue == HB_EPI_LNFOLD_BF16 || epilogue == HB_EPI_LNFOLD_GELU_BF16 || epilogue == HB_EPI_RESID_STATS_F32)
+    if (epilogue == HB_EPI_LNFOLD_BF16 || epilogue == HB_EPI_LNFOLD_GELU_BF16 || epilogue == HB_EPI_LNFOLD_GELU2_BF16 ||
+        epilogue == HB_EPI_RESID_STATS_F32)
         return set_error("hb_gemm_bf16: use hb_gemm_lnfold_bf16 / hb_gemm_resid_stats for epilogue %d", epilogue);
     GemmArgs g;
     if (gemm_prepare(g, a_bf16, w_bf16, bias, epilogue, out, M, N, K, tok_table, tokens_per_seq)) return -1;
@@ -186,7 +187,7 @@ int hb_gemm_lnfold_bf16(const void* xb_bf16, const void* w_gamma_bf16, const flo
     aux.inv_dim = 1.0f / static_cast<float>(K);
     aux.eps = eps;
     GemmArgs g;
-    if (gemm_prepare(g, xb_bf16, w_gamma_bf16, d, gelu ? HB_EPI_LNFOLD_GELU_BF16 : HB_EPI_LNFOLD_BF16, out_bf16, M, N, K,
+    if (gemm_prepare(g, xb_bf16, w_gamma_bf16, d, gelu == 2 ? HB_EPI_LNFOLD_GELU2_BF16 : gelu ? HB_EPI_LNFOLD_GELU_BF16 : HB_EPI_LNFOLD_BF16, out_bf16, M, N, K,
                      nullptr, 0, &aux)) return -1;
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
@@ -287,7 +288,7 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
         int rc = 0;
         rc |= gemm_prepare(p->g_qkv[i], p->xb, w[0], static_cast<const float*>(w[2]), HB_EPI_LNFOLD_BF16, p->qkv, R, 3 * D, D, nullptr, 0, &a1);
         rc |= gemm_prepare(p->g_proj[i], p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_STATS_F32, p->x, R, D, D, nullptr, 0, &r1, p->xb);
-        rc |= gemm_prepare(p->g_fc1[i], p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU_BF16, p->hid, R, H, D, nullptr, 0, &a2);
+        rc |= gemm_prepare(p->g_fc1[i], p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU2_BF16, p->hid, R, H, D, nullptr, 0, &a2);
         rc |= gemm_prepare(p->g_fc2[i], p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_STATS_F32, p->x, R, D, H, nullptr, 0, &r2, p->xb);
         if (rc) { delete p; return -1; }
     }
@@ -341,7 +342,7 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
             a2.colvec2 = static_cast<const float*>(w[6]); a2.row_stats = p->stats2; a2.inv_dim = 1.0f / D; a2.eps = c.ln_eps;
             GemmArgs gp, g1, g2;
             if (gemm_prepare(gp, p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_STATS_F32, p->x, n_seq, D, D, nullptr, 0, &r1, p->xb, pitch)) return -1;
-            if (gemm_prepare(g1, p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU_BF16, p->hid, n_seq, c.mlp_dim, D, nullptr, 0, &a2)) return -1;
+            if (gemm_prepare(g1, p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU2_BF16, p->hid, n_seq, c.mlp_dim, D, nullptr, 0, &a2)) return -1;
             if (gemm_prepare(g2, p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_STATS_F32, p->x, n_seq, D, c.mlp_dim, nullptr, 0, &r2, p->xb, pitch)) return -1;
             { ProfScope ps(kb + HB_PROF_PROJ_GEMM, st); if (gemm_launch(gp, st)) return -1; }
             { ProfScope ps(kb + HB_PROF_FC1_GEMM, st); if (gemm_launch(g1, st)) return -1; }

@@ -4,7 +4,8 @@
 //   warp 1     : MMA issuer    (one elected thread, tcgen05.mma kind::f16, K = 16 per instruction, accumulators in TMEM,
 //                               double buffered against the epilogue)
 //   warp 2     : TMEM allocator
-//   warps 4-11 : epilogue      (two warpgroups; tcgen05.ld -> fused epilogue -> swizzled smem -> TMA store)
+//   warp 3     : residual-tile loader (RESID epilogue: fp32 residual tiles prefetched by TMA into a ring)
+//   warps 4-19 : epilogue      (four warpgroups; tcgen05.ld -> fused epilogue -> swizzled smem -> TMA store)
 //
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile; each
 // CTA stages its own 128 rows of A and HALF of the W tile, the leader issues the MMAs for both.
@@ -32,30 +33,48 @@
 
 namespace hb {
 
+#ifdef HB_EXP_TRACE
+__device__ long long g_trace[4 * 1024];
+#define TRACE(role, it, k) do { if (blockIdx.x == 0 && (it) < 120) g_trace[(role) * 1024 + (it) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRACE(role, it, k) do { } while (0)
+#endif
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle span
-constexpr int GEMM_THREADS = 384;    // 12 warps: producer, mma, tmem-alloc, spare, 2 x 4 epilogue
+constexpr int GEMM_EPI_WGS = 4;      // epilogue warpgroups
 constexpr int GEMM_EPI_THREADS = 128; // per epilogue warpgroup
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_WGS * GEMM_EPI_THREADS;   // 20 warps: producer, mma, tmem-alloc, residual loader, 4 x 4 epilogue
 constexpr int STAGE_BYTES_OUT = 128 * 128;   // 128 rows x 128 B staging chunk for the TMA store
+constexpr int RESID_RING = 4;        // residual tiles (fp32 128 x 32) prefetched ahead of the epilogue
 constexpr int SMEM_LIMIT = 232448;   // 227 KB
+constexpr uint32_t BAR_EPI_ALL = 5;  // named barrier over every epilogue thread (1..4: one per warpgroup)
 
 // Epilogue kinds (mirrored in include/hipt_b200.h as HB_EPI_*)
 enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2, EPI_TOKENS_F32 = 3, EPI_TOKENS_GELU_F32 = 4,
-              EPI_BIAS_GELU_FAST_BF16 = 5, EPI_LNFOLD_BF16 = 6, EPI_LNFOLD_GELU_BF16 = 7, EPI_RESID_STATS_F32 = 8 };
+              EPI_BIAS_GELU_FAST_BF16 = 5, EPI_LNFOLD_BF16 = 6, EPI_LNFOLD_GELU_BF16 = 7, EPI_RESID_STATS_F32 = 8,
+              EPI_LNFOLD_GELU2_BF16 = 9 };
 
 template <int BN, int CG, int EPI>
 struct GemmCfg {
+    static constexpr bool RESID = (EPI == EPI_RESID_STATS_F32);
+    static constexpr bool TOKENS = (EPI == EPI_TOKENS_F32 || EPI == EPI_TOKENS_GELU_F32);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_ROWS = BN / CG;                    // W rows staged by this CTA
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
-    // per epilogue warpgroup: one 16 KB staging tile; the residual epilogue needs two fp32 residual tiles + 8 KB bf16
-    static constexpr int OUT_BYTES_PER_WG = (EPI == EPI_RESID_STATS_F32) ? (2 * STAGE_BYTES_OUT + 8192) : STAGE_BYTES_OUT;
-    static constexpr int TAIL_BYTES = 2048 /* row-stat exchange */ + 512 /* barriers */;
-    static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - 2 * OUT_BYTES_PER_WG - TAIL_BYTES;
+    // output side: one 16 KB staging tile per warpgroup; the residual epilogue instead has a ring of fp32 residual
+    // tiles (updated in place and stored from there) plus an 8 KB bf16 staging tile per warpgroup; token rows go
+    // straight to global memory
+    static constexpr int OUT_BYTES = RESID ? (RESID_RING * STAGE_BYTES_OUT + GEMM_EPI_WGS * 8192)
+                                           : (TOKENS ? 0 : GEMM_EPI_WGS * STAGE_BYTES_OUT);
+    static constexpr int VEC_BYTES = (RESID || TOKENS || EPI == EPI_BIAS_RESADD_F32) ? GEMM_EPI_WGS * 128 * 4 : 16 * 256 * 4;                                        // bias / c slices per warp(group)
+    static constexpr int STAT_BYTES = (RESID || TOKENS) ? 2 * GEMM_EPI_WGS * 128 * 8 : 0; // row-stat exchange
+    static constexpr int TAIL_BYTES = VEC_BYTES + STAT_BYTES + 512 /* barriers */;
+    static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - OUT_BYTES - TAIL_BYTES;
     static constexpr int STAGES_FIT = RING_BUDGET / (A_BYTES + B_BYTES);
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + 2 * OUT_BYTES_PER_WG + TAIL_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + TAIL_BYTES;
     static_assert(STAGES >= 2, "operand ring too shallow");
 };
 
@@ -68,25 +87,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     using Cfg = GemmCfg<BN, CG, EPI>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_FAST_BF16 ||
-                               EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16);
-    constexpr bool LNFOLD = (EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16);
-    constexpr bool OUT_TOKENS = (EPI == EPI_TOKENS_F32 || EPI == EPI_TOKENS_GELU_F32);
-    constexpr bool RESID = (EPI == EPI_RESID_STATS_F32);
+                               EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16 || EPI == EPI_LNFOLD_GELU2_BF16);
+    constexpr bool LNFOLD = (EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16 || EPI == EPI_LNFOLD_GELU2_BF16);
+    constexpr bool OUT_TOKENS = Cfg::TOKENS;
+    constexpr bool RESID = Cfg::RESID;
     constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;      // 128 B of output per row per chunk
+    constexpr int NCHUNK = BN / CHUNK_COLS;
+    constexpr int NWG = GEMM_EPI_WGS;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked below), and deriving
+    // every pointer from the array itself keeps the shared state space (LDS/STS instead of generic accesses)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
     uint8_t* smem_o = smem_b + STAGES * Cfg::B_BYTES;
-    float* stat_x = reinterpret_cast<float*>(smem_o + 2 * Cfg::OUT_BYTES_PER_WG);   // [2 parity][128][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stat_x) + 2048);
+    float* vec_x = reinterpret_cast<float*>(smem_o + Cfg::OUT_BYTES);                 // [NWG][128]
+    float* stat_x = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(vec_x) + Cfg::VEC_BYTES);   // [2][NWG][128][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stat_x) + Cfg::STAT_BYTES);
     uint64_t* full_bar = bars;                  // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;        // [STAGES]  MMA -> TMA
     uint64_t* acc_full = bars + 2 * STAGES;     // [2]       MMA -> epilogue
     uint64_t* acc_empty = bars + 2 * STAGES + 2;// [2]       epilogue -> MMA
-    uint64_t* resid_full = bars + 2 * STAGES + 4;// [2 wg][2] residual tile landed (RESID only)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+    uint64_t* ring_full = bars + 2 * STAGES + 4;             // [RESID_RING] residual tile landed (RESID only)
+    uint64_t* ring_empty = ring_full + RESID_RING;           // [RESID_RING] its updated copy has been stored
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + RESID_RING);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -105,8 +131,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 1 && lane == 0) {
         // CG = 2: full_bar / acc_empty are used on the leader only and collect arrivals from both CTAs
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CG * 2 * GEMM_EPI_THREADS); }
-        for (int i = 0; i < 4; ++i) mbar_init(&resid_full[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], OUT_BF16 ? CG * 8 : CG * NWG * GEMM_EPI_THREADS); }
+        for (int i = 0; i < RESID_RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -131,13 +157,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int m0 = (tile / n_tiles) * TILE_M + cta_rank * GEMM_BM;
                 const int n0 = (tile % n_tiles) * BN + cta_rank * Cfg::B_ROWS;
+                TRACE(3, (tile - tile0) / tile_step, 0);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (kb == k_blocks - 1) TRACE(3, (tile - tile0) / tile_step, 1);
+#ifdef HB_EXP_NOLOAD
+                    if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&full_bar[stage], 0); else mbar_arrive(&full_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+#endif
                     if constexpr (CG == 2) {
                         // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the pair
+#ifdef HB_EXP_NOW
+                        tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * GEMM_BK, m0);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES));
+#elif defined(HB_EXP_NOA)
+                        tma_load_2d_2sm_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::B_BYTES));
+#else
                         tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * GEMM_BK, m0);
                         tma_load_2d_2sm_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+#endif
                         else mbar_arrive_remote(&full_bar[stage], 0);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
@@ -150,226 +191,341 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && cta_rank == 0) {
+        // The whole warp walks the pipeline (warp-uniform control flow and operands, so the descriptors live in
+        // uniform registers); one elected lane issues the tcgen05.mma / commit instructions.
+        if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
             uint32_t stage = 0, phase = 0;
             uint32_t it = 0;
             for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                if (lane == 0) TRACE(0, it, 0);
                 mbar_wait(&acc_empty[as], aphase ^ 1);
+                if (lane == 0) TRACE(0, it, 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_k128(smem_u32(smem_a + stage * Cfg::A_BYTES));
-                    const uint64_t db = umma_desc_k128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+                    const uint64_t da = umma_desc_k128(a_base + stage * Cfg::A_BYTES);
+                    const uint64_t db = umma_desc_k128(b_base + stage * Cfg::B_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        // advance 16 bf16 = 32 B inside the swizzle span: +2 in the (addr >> 4) field
-                        if constexpr (CG == 2) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            // advance 16 bf16 = 32 B inside the swizzle span: +2 in the (addr >> 4) field
+                            if constexpr (CG == 2) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            else umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if constexpr (CG == 2) {                   // arrive on the same barrier of BOTH CTAs
+                            umma_commit_2sm(&empty_bar[stage]);
+                            if (kb == k_blocks - 1) umma_commit_2sm(&acc_full[as]);
+                        } else {
+                            umma_commit(&empty_bar[stage]);        // smem slot free once these MMAs retire
+                            if (kb == k_blocks - 1) umma_commit(&acc_full[as]);
+                        }
                     }
-                    if constexpr (CG == 2) {                   // arrive on the same barrier of BOTH CTAs
-                        umma_commit_2sm(&empty_bar[stage]);
-                        if (kb == k_blocks - 1) umma_commit_2sm(&acc_full[as]);
-                    } else {
-                        umma_commit(&empty_bar[stage]);        // smem slot free once these MMAs retire
-                        if (kb == k_blocks - 1) umma_commit(&acc_full[as]);
-                    }
+                    __syncwarp();
+                    if (lane == 0 && kb == 0) TRACE(0, it, 2);
+                    if (lane == 0 && kb == k_blocks - 1) TRACE(0, it, 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ residual loader (RESID only)
+        // Streams the fp32 residual tiles of every (tile, chunk) of this CTA, in consumption order, into the ring:
+        // it runs up to RESID_RING chunks (one whole 192-wide tile) ahead of the epilogue warpgroups.
+        if constexpr (RESID) {
+            if (lane == 0) {
+                uint32_t q = 0;
+                for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                    const int m0 = (tile / n_tiles) * TILE_M + cta_rank * GEMM_BM;
+                    const int n0 = (tile % n_tiles) * BN;
+                    for (int c = 0; c < NCHUNK; ++c, ++q) {
+                        const uint32_t slot = q % RESID_RING, use = q / RESID_RING;
+                        mbar_wait(&ring_empty[slot], (use & 1) ^ 1);
+                        mbar_arrive_expect_tx(&ring_full[slot], STAGE_BYTES_OUT);
+                        tma_load_2d(smem_o + slot * STAGE_BYTES_OUT, &map_out, &ring_full[slot], n0 + c * 32, m0);
+                    }
+                }
+            }
+        }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (2 warpgroups)
-        // Each warpgroup covers all 128 accumulator rows (warp & 3 = TMEM lane quadrant) and takes every other
-        // 128-byte-wide column chunk of the tile, with its own staging buffers, named barrier and TMA thread.
+        // ------------------------------------------------------------------ epilogue, bf16 output: 16 independent warps
+        // The two TMEM accumulator buffers are served by disjoint sets of warps: warpgroups 0-1 drain the even tiles of
+        // this CTA, warpgroups 2-3 the odd ones, so that while one set is in its math phase the other waits for its MMAs,
+        // loads TMEM or stores - the four warps of an SM sub-partition are never all in the same phase.  Within a set,
+        // warp = (TMEM lane quadrant ew, column slot s): 32 accumulator rows x the 64-column chunks c = s' (mod 2),
+        // s' = s + k (mod 2) alternating per tile so that odd chunk counts balance.  Nothing synchronises across warps:
+        // each has its own 4 KB staging tile, column-vector slices and TMA stores.
+        if constexpr (OUT_BF16) {
+            const int wgi = (warp - 4) >> 2;
+            const int par = wgi >> 1;                                  // accumulator buffer served by this warp
+            const int s = wgi & 1;
+            const int ew = warp & 3;
+            const int sw = lane & 7;
+            uint8_t* stage_buf = smem_o + (warp - 4) * 4096;          // [32 rows][128 B], SWIZZLE_128B
+            const uint32_t row_addr = smem_u32(stage_buf) + lane * 128;
+            float* wvec = vec_x + (warp - 4) * 256;                   // [2 chunks][bias 64 | c 64]
+            const int step2 = 2 * tile_step;
+            const int step_m = step2 / n_tiles, step_n = step2 % n_tiles;
+            const int tile_first = tile0 + par * tile_step;
+            int m_idx = tile_first / n_tiles, n_idx = tile_first % n_tiles;
+            float pf_v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            float2 pf_sq = make_float2(0.f, 0.f);
+            auto pf_load = [&](int mi, int ni, uint32_t kk) {          // side inputs of a tile, fetched one tile ahead
+                const int sp = (s + kk) & 1;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = sp + 2 * cc;
+                    if (c < NCHUNK) {
+                        const int col = ni * BN + c * 64 + lane;
+                        pf_v[cc][0] = __ldg(bias + col);
+                        pf_v[cc][1] = __ldg(bias + col + 32);
+                        if constexpr (LNFOLD) {
+                            pf_v[cc][2] = __ldg(aux.colvec2 + col);
+                            pf_v[cc][3] = __ldg(aux.colvec2 + col + 32);
+                        }
+                    }
+                }
+                if constexpr (LNFOLD) {
+                    const int r = mi * TILE_M + cta_rank * GEMM_BM + ew * 32 + lane;
+                    pf_sq = (r < M) ? __ldg(reinterpret_cast<const float2*>(aux.row_stats) + r) : make_float2(0.f, 0.f);
+                }
+            };
+            if (tile_first < total_tiles) pf_load(m_idx, n_idx, 0);
+            uint32_t k = 0;
+            for (int tile = tile_first; tile < total_tiles; tile += step2, ++k) {
+                const int m0 = m_idx * TILE_M + cta_rank * GEMM_BM + ew * 32;
+                const int n0 = n_idx * BN;
+                const uint32_t as = par, aphase = k & 1;
+                const int sp = (s + k) & 1;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+                // the side inputs fetched one tile ago go to this warp's shared slices; then fetch the next tile's
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    wvec[cc * 128 + lane] = pf_v[cc][0]; wvec[cc * 128 + 32 + lane] = pf_v[cc][1];
+                    if constexpr (LNFOLD) { wvec[cc * 128 + 64 + lane] = pf_v[cc][2]; wvec[cc * 128 + 96 + lane] = pf_v[cc][3]; }
+                }
+                float rstd = 0.f, nrm = 0.f;
+                if constexpr (LNFOLD) {
+                    const float mu = pf_sq.x * aux.inv_dim;
+                    const float var = fmaxf(pf_sq.y * aux.inv_dim - mu * mu, 0.f);
+                    rstd = rsqrtf(var + aux.eps);
+                    nrm = -rstd * mu;
+                }
+                n_idx += step_n; m_idx += step_m;
+                if (n_idx >= n_tiles) { n_idx -= n_tiles; ++m_idx; }
+                if (tile + step2 < total_tiles) pf_load(m_idx, n_idx, k + 1);
+                [[maybe_unused]] const f32x2_t rstd2 = f2_pack(rstd, rstd), nrm2 = f2_pack(nrm, nrm);
+
+                if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 0);
+                mbar_wait(&acc_full[as], aphase);
+                if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 1);
+                tc_fence_after();
+                __syncwarp();                                        // the column-vector slices are visible to all lanes
+#ifdef HB_EXP_NOEPI
+                tc_fence_before();
+                if (lane == 0) { if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]); }
+                continue;
+#endif
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = sp + 2 * cc;
+                    if (c >= NCHUNK) break;
+                    if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 2 + 3 * cc);
+                    const float* wv = wvec + cc * 128;
+                    uint32_t pk[32];                 // 64 bf16 of this row
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + c * 64 + h * 32, v);
+                        tmem_ld_wait();
+                        if (h == 1 && c + 2 >= NCHUNK) {             // last TMEM read of the tile: hand the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0);
+                                else mbar_arrive(&acc_empty[as]);
+                            }
+                        }
+                        const float4* b4 = reinterpret_cast<const float4*>(wv + h * 32);
+                        const float4* c4 = reinterpret_cast<const float4*>(wv + 64 + h * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = b4[j];
+                            f32x2_t y0 = f2_pack(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]));
+                            f32x2_t y1 = f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            if constexpr (LNFOLD) {      // rstd * acc + (nrm * c + d)
+                                const float4 cv = c4[j];
+                                y0 = f2_fma(rstd2, y0, f2_fma(nrm2, f2_pack(cv.x, cv.y), f2_pack(b.x, b.y)));
+                                y1 = f2_fma(rstd2, y1, f2_fma(nrm2, f2_pack(cv.z, cv.w), f2_pack(b.z, b.w)));
+                            } else {
+                                y0 = f2_add(y0, f2_pack(b.x, b.y));
+                                y1 = f2_add(y1, f2_pack(b.z, b.w));
+                            }
+                            if constexpr (EPI == EPI_BIAS_GELU_FAST_BF16 || EPI == EPI_LNFOLD_GELU_BF16) {
+                                pk[h * 16 + 2 * j] = gelu_fast2_bf16(y0);
+                                pk[h * 16 + 2 * j + 1] = gelu_fast2_bf16(y1);
+                            } else if constexpr (EPI == EPI_LNFOLD_GELU2_BF16) {
+                                pk[h * 16 + 2 * j] = gelu_fast2x2_bf16(y0);
+                                pk[h * 16 + 2 * j + 1] = gelu_fast2x2_bf16(y1);
+                            } else {
+                                float f0, f1, f2, f3;
+                                f2_unpack(y0, f0, f1);
+                                f2_unpack(y1, f2, f3);
+                                if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                                    f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+                                }
+                                pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
+                                pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
+                            }
+                        }
+                    }
+                    if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 3 + 3 * cc);
+                    // the previous TMA store of this warp must have drained the staging tile (it has had the whole
+                    // math phase above to do so)
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        sts_u4(row_addr + ((q ^ sw) << 4), make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+#ifndef HB_EXP_NOSTORE
+                    if (lane == 0) {
+                        tma_store_2d(&map_out, stage_buf, n0 + c * 64, m0);
+                        tma_store_commit();
+                    }
+#endif
+                    if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 4 + 3 * cc);
+                }
+            }
+            if (lane == 0) tma_store_wait_all<0>();
+        } else {
+        // ------------------------------------------------------------------ epilogue, fp32 outputs (4 warpgroups)
+        // Each warpgroup covers all 128 accumulator rows (warp & 3 = TMEM lane quadrant, thread = row) and takes the
+        // 128-byte-wide column chunks c with c = wg + rot (mod 4); rot advances per tile so that chunk counts that are
+        // not a multiple of 4 balance over tiles.
         const int wg = (warp - 4) >> 2;
         const int ew = warp & 3;
+        const int t_wg = threadIdx.x & 127;                   // thread index within the warpgroup
         const int row_in_tile = ew * 32 + lane;
         const bool store_leader = ((warp & 3) == 0 && lane == 0);
-        uint8_t* wg_buf = smem_o + wg * Cfg::OUT_BYTES_PER_WG;
+        float* wg_vec = vec_x + wg * 128;
         const int sw = row_in_tile & 7;
-        constexpr int NCHUNK = BN / CHUNK_COLS;
         uint32_t it = 0;
-        uint32_t lc = 0;                                      // RESID: chunks processed by this warpgroup so far
         for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
             const int m0 = (tile / n_tiles) * TILE_M + cta_rank * GEMM_BM;
             const int n_idx = tile % n_tiles;
             const int n0 = n_idx * BN;
             const int row = m0 + row_in_tile;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int c_first = (wg + it * NCHUNK) & 1;       // alternate so odd chunk counts balance across tiles
-            float st_sum = 0.f, st_sq = 0.f;                  // row statistics of what this thread produced in the tile
-
-            // per-row LayerNorm factors for the folded epilogues
-            float rstd = 0.f, nrm = 0.f;
-            if constexpr (LNFOLD) {
-                if (row < M) {
-                    const float2 sq = __ldg(reinterpret_cast<const float2*>(aux.row_stats) + row);
-                    const float mu = sq.x * aux.inv_dim;
-                    const float var = fmaxf(sq.y * aux.inv_dim - mu * mu, 0.f);
-                    rstd = rsqrtf(var + aux.eps);
-                    nrm = -rstd * mu;
-                }
-            }
-            if constexpr (RESID) {
-                // fetch the residual tile of this warpgroup's first chunk while the MMAs are still running
-                if (store_leader && c_first < NCHUNK) {
-                    tma_store_wait_read<0>();
-                    const uint32_t b = lc & 1;
-                    mbar_arrive_expect_tx(&resid_full[wg * 2 + b], STAGE_BYTES_OUT);
-                    tma_load_2d(wg_buf + b * STAGE_BYTES_OUT, &map_out, &resid_full[wg * 2 + b], n0 + c_first * 32, m0);
-                }
-            }
-
-            mbar_wait(&acc_full[as], aphase);
-            tc_fence_after();
+            const int c_first = (wg + it * NCHUNK) & (NWG - 1);
+            [[maybe_unused]] float st_sum = 0.f, st_sq = 0.f;   // row statistics of what this thread produced in the tile
             const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 
-            if constexpr (OUT_TOKENS) {
-                // fp32 token rows written straight to global with a per-sequence row remap (+1 for the CLS slot)
-                // and a per-(token,col) additive table (positional embedding); optional bf16 copy + row statistics.
-                const int seq = row / tokens_per_seq;
-                const int tok = row - seq * tokens_per_seq;
-                const size_t out_row = static_cast<size_t>(seq) * (tokens_per_seq + 1) + 1 + tok;
+            {
+                mbar_wait(&acc_full[as], aphase);
+                tc_fence_after();
+#ifdef HB_EXP_NOEPI
+                tc_fence_before();
+                if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
+                continue;
+#endif
+                if constexpr (OUT_TOKENS) {
+                    // fp32 token rows written straight to global with a per-sequence row remap (+1 for the CLS slot)
+                    // and a per-(token,col) additive table (positional embedding); optional bf16 copy + row statistics.
+                    const int seq = row / tokens_per_seq;
+                    const int tok = row - seq * tokens_per_seq;
+                    const size_t out_row = static_cast<size_t>(seq) * (tokens_per_seq + 1) + 1 + tok;
 #pragma unroll 1
-                for (int c = c_first; c < NCHUNK; c += 2) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr_row + c * 32, v);
-                    tmem_ld_wait();
-                    if (row < M) {
-                        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
-                        const float4* t4 = reinterpret_cast<const float4*>(tok_table + static_cast<size_t>(1 + tok) * N + n0 + c * 32);
-                        float4* o4 = reinterpret_cast<float4*>(tok_out + out_row * N + n0 + c * 32);
-                        uint4* ob = aux.xb_out ? reinterpret_cast<uint4*>(aux.xb_out + out_row * N + n0 + c * 32) : nullptr;
+                    for (int c = c_first; c < NCHUNK; c += NWG) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr_row + c * 32, v);
+                        tmem_ld_wait();
+                        if (row < M) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+                            const float4* t4 = reinterpret_cast<const float4*>(tok_table + static_cast<size_t>(1 + tok) * N + n0 + c * 32);
+                            float4* o4 = reinterpret_cast<float4*>(tok_out + out_row * N + n0 + c * 32);
+                            uint4* ob = aux.xb_out ? reinterpret_cast<uint4*>(aux.xb_out + out_row * N + n0 + c * 32) : nullptr;
 #pragma unroll
-                        for (int j = 0; j < 8; j += 2) {
-                            float4 r[2];
+                            for (int j = 0; j < 8; j += 2) {
+                                float4 r[2];
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const float4 b = __ldg(b4 + j + u);
-                                const float4 t = __ldg(t4 + j + u);
-                                r[u].x = __uint_as_float(v[4 * (j + u) + 0]) + b.x;
-                                r[u].y = __uint_as_float(v[4 * (j + u) + 1]) + b.y;
-                                r[u].z = __uint_as_float(v[4 * (j + u) + 2]) + b.z;
-                                r[u].w = __uint_as_float(v[4 * (j + u) + 3]) + b.w;
-                                if constexpr (EPI == EPI_TOKENS_GELU_F32) {
-                                    r[u].x = gelu_erf(r[u].x); r[u].y = gelu_erf(r[u].y);
-                                    r[u].z = gelu_erf(r[u].z); r[u].w = gelu_erf(r[u].w);
-                                }
-                                r[u].x += t.x; r[u].y += t.y; r[u].z += t.z; r[u].w += t.w;
-                                o4[j + u] = r[u];
-                                st_sum += (r[u].x + r[u].y) + (r[u].z + r[u].w);
-                                st_sq = fmaf(r[u].x, r[u].x, fmaf(r[u].y, r[u].y, fmaf(r[u].z, r[u].z, fmaf(r[u].w, r[u].w, st_sq))));
-                            }
-                            if (ob) ob[j >> 1] = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[0].z, r[0].w),
-                                                            pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[1].z, r[1].w));
-                        }
-                    }
-                }
-            } else if constexpr (RESID) {
-                uint8_t* xb_buf = wg_buf + 2 * STAGE_BYTES_OUT;                  // [128 rows x 64 B], SWIZZLE_64B
-                uint8_t* xb_row = xb_buf + row_in_tile * 64;
-                const int sw64 = (row_in_tile >> 1) & 3;
-#pragma unroll 1
-                for (int c = c_first; c < NCHUNK; c += 2, ++lc) {
-                    const uint32_t b = lc & 1;
-                    uint8_t* rbuf = wg_buf + b * STAGE_BYTES_OUT;
-                    uint8_t* rrow = rbuf + row_in_tile * 128;
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr_row + c * 32, v);
-                    // every TMA store that read this warpgroup's buffers has drained; then prefetch the next chunk's
-                    // residual tile into the other buffer
-                    if (store_leader) {
-                        tma_store_wait_read<0>();
-                        if (c + 2 < NCHUNK) {
-                            const uint32_t nb = (lc + 1) & 1;
-                            mbar_arrive_expect_tx(&resid_full[wg * 2 + nb], STAGE_BYTES_OUT);
-                            tma_load_2d(wg_buf + nb * STAGE_BYTES_OUT, &map_out, &resid_full[wg * 2 + nb], n0 + (c + 2) * 32, m0);
-                        }
-                    }
-                    mbar_wait(&resid_full[wg * 2 + b], (lc >> 1) & 1);
-                    tmem_ld_wait();
-                    named_bar_sync(1 + wg, GEMM_EPI_THREADS);                    // bf16 staging tile is free for all
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 bb = __ldg(b4 + j);
-                        float4* p = reinterpret_cast<float4*>(rrow + ((j ^ sw) << 4));
-                        float4 r = *p;
-                        r.x += __uint_as_float(v[4 * j + 0]) + bb.x; r.y += __uint_as_float(v[4 * j + 1]) + bb.y;
-                        r.z += __uint_as_float(v[4 * j + 2]) + bb.z; r.w += __uint_as_float(v[4 * j + 3]) + bb.w;
-                        *p = r;
-                        st_sum += (r.x + r.y) + (r.z + r.w);
-                        st_sq = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, st_sq))));
-                        pk[2 * j] = pack_bf16x2(r.x, r.y);
-                        pk[2 * j + 1] = pack_bf16x2(r.z, r.w);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(xb_row + ((q ^ sw64) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + wg, GEMM_EPI_THREADS);
-                    if (store_leader) {
-                        tma_store_2d(&map_out, rbuf, n0 + c * 32, m0);
-                        tma_store_2d(&map_xb, xb_buf, n0 + c * 32, m0);
-                        tma_store_commit();
-                    }
-                }
-            } else {
-                uint8_t* stage_buf = wg_buf;
-                uint8_t* row_ptr = stage_buf + row_in_tile * 128;
-#pragma unroll 1
-                for (int c = c_first; c < NCHUNK; c += 2) {
-                    if constexpr (OUT_BF16) {
-                        uint32_t pk[32];                 // 64 bf16 of this row
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(taddr_row + c * 64 + h * 32, v);
-                            tmem_ld_wait();
-                            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 64 + h * 32);
-                            const float4* c4 = LNFOLD ? reinterpret_cast<const float4*>(aux.colvec2 + n0 + c * 64 + h * 32) : b4;
-                            [[maybe_unused]] const f32x2_t rstd2 = f2_pack(rstd, rstd), nrm2 = f2_pack(nrm, nrm);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 b = __ldg(b4 + j);
-                                f32x2_t y0 = f2_pack(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]));
-                                f32x2_t y1 = f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                                if constexpr (LNFOLD) {      // rstd * acc + (nrm * c + d)
-                                    const float4 cc = __ldg(c4 + j);
-                                    y0 = f2_fma(rstd2, y0, f2_fma(nrm2, f2_pack(cc.x, cc.y), f2_pack(b.x, b.y)));
-                                    y1 = f2_fma(rstd2, y1, f2_fma(nrm2, f2_pack(cc.z, cc.w), f2_pack(b.z, b.w)));
-                                } else {
-                                    y0 = f2_add(y0, f2_pack(b.x, b.y));
-                                    y1 = f2_add(y1, f2_pack(b.z, b.w));
-                                }
-                                if constexpr (EPI == EPI_BIAS_GELU_FAST_BF16 || EPI == EPI_LNFOLD_GELU_BF16) {
-                                    pk[h * 16 + 2 * j] = gelu_fast2_bf16(y0);
-                                    pk[h * 16 + 2 * j + 1] = gelu_fast2_bf16(y1);
-                                } else {
-                                    float f0, f1, f2, f3;
-                                    f2_unpack(y0, f0, f1);
-                                    f2_unpack(y1, f2, f3);
-                                    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-                                        f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+                                for (int u = 0; u < 2; ++u) {
+                                    const float4 b = __ldg(b4 + j + u);
+                                    const float4 t = __ldg(t4 + j + u);
+                                    r[u].x = __uint_as_float(v[4 * (j + u) + 0]) + b.x;
+                                    r[u].y = __uint_as_float(v[4 * (j + u) + 1]) + b.y;
+                                    r[u].z = __uint_as_float(v[4 * (j + u) + 2]) + b.z;
+                                    r[u].w = __uint_as_float(v[4 * (j + u) + 3]) + b.w;
+                                    if constexpr (EPI == EPI_TOKENS_GELU_F32) {
+                                        r[u].x = gelu_erf(r[u].x); r[u].y = gelu_erf(r[u].y);
+                                        r[u].z = gelu_erf(r[u].z); r[u].w = gelu_erf(r[u].w);
                                     }
-                                    pk[h * 16 + 2 * j] = pack_bf16x2(f0, f1);
-                                    pk[h * 16 + 2 * j + 1] = pack_bf16x2(f2, f3);
+                                    r[u].x += t.x; r[u].y += t.y; r[u].z += t.z; r[u].w += t.w;
+                                    o4[j + u] = r[u];
+                                    st_sum += (r[u].x + r[u].y) + (r[u].z + r[u].w);
+                                    st_sq = fmaf(r[u].x, r[u].x, fmaf(r[u].y, r[u].y, fmaf(r[u].z, r[u].z, fmaf(r[u].w, r[u].w, st_sq))));
                                 }
+                                if (ob) ob[j >> 1] = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[0].z, r[0].w),
+                                                                pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[1].z, r[1].w));
                             }
                         }
-                        // the TMA store that last read this warpgroup's staging buffer must have drained it
-                        if (store_leader) tma_store_wait_read<0>();
+                    }
+                } else if constexpr (RESID) {
+                    uint8_t* xb_buf = smem_o + RESID_RING * STAGE_BYTES_OUT + wg * 8192;   // [128 rows x 64 B], SWIZZLE_64B
+                    uint8_t* xb_row = xb_buf + row_in_tile * 64;
+                    const int sw64 = (row_in_tile >> 1) & 3;
+#pragma unroll 1
+                    for (int c = c_first; c < NCHUNK; c += NWG) {
+                        const uint32_t q = it * NCHUNK + c;                      // chunk sequence number of this CTA
+                        const uint32_t slot = q % RESID_RING, use = q / RESID_RING;
+                        uint8_t* rbuf = smem_o + slot * STAGE_BYTES_OUT;
+                        uint8_t* rrow = rbuf + row_in_tile * 128;
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr_row + c * 32, v);
+                        if (t_wg < 32) wg_vec[t_wg] = __ldg(bias + n0 + c * 32 + t_wg);
+                        mbar_wait(&ring_full[slot], use & 1);
+                        // bias slice visible; the leader has drained the stores that read the bf16 staging tile
                         named_bar_sync(1 + wg, GEMM_EPI_THREADS);
+                        tmem_ld_wait();
+                        const float4* b4 = reinterpret_cast<const float4*>(wg_vec);
+                        uint32_t pk[16];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<uint4*>(row_ptr + ((q ^ sw) << 4)) =
-                                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                    } else {
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = b4[j];
+                            float4* p = reinterpret_cast<float4*>(rrow + ((j ^ sw) << 4));
+                            float4 r = *p;
+                            r.x += __uint_as_float(v[4 * j + 0]) + bb.x; r.y += __uint_as_float(v[4 * j + 1]) + bb.y;
+                            r.z += __uint_as_float(v[4 * j + 2]) + bb.z; r.w += __uint_as_float(v[4 * j + 3]) + bb.w;
+                            *p = r;
+                            st_sum += (r.x + r.y) + (r.z + r.w);
+                            st_sq = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, st_sq))));
+                            pk[2 * j] = pack_bf16x2(r.x, r.y);
+                            pk[2 * j + 1] = pack_bf16x2(r.z, r.w);
+                        }
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq)
+                            *reinterpret_cast<uint4*>(xb_row + ((qq ^ sw64) << 4)) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + wg, GEMM_EPI_THREADS);
+                        if (store_leader) {
+                            tma_store_2d(&map_out, rbuf, n0 + c * 32, m0);
+                            tma_store_2d(&map_xb, xb_buf, n0 + c * 32, m0);
+                            tma_store_commit();
+                            tma_store_wait_read<0>();                            // both tiles read: hand the slot back
+                            mbar_arrive(&ring_empty[slot]);
+                        }
+                    }
+                } else {
+                    // ---- EPI_BIAS_RESADD_F32: fp32 chunks added into the output by TMA reduce
+                    uint8_t* stage_buf = smem_o + wg * STAGE_BYTES_OUT;
+                    uint8_t* row_ptr = stage_buf + row_in_tile * 128;
+#pragma unroll 1
+                    for (int c = c_first; c < NCHUNK; c += NWG) {
                         uint32_t v[32];
                         tmem_ld_32x32(taddr_row + c * 32, v);
                         tmem_ld_wait();
@@ -385,38 +541,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         named_bar_sync(1 + wg, GEMM_EPI_THREADS);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(row_ptr + ((j ^ sw) << 4)) = r[j];
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + wg, GEMM_EPI_THREADS);
-                    if (store_leader) {
-                        if constexpr (EPI == EPI_BIAS_RESADD_F32)
-                            tma_reduce_add_2d(&map_out, stage_buf, n0 + c * CHUNK_COLS, m0);
-                        else
-                            tma_store_2d(&map_out, stage_buf, n0 + c * CHUNK_COLS, m0);
-                        tma_store_commit();
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + wg, GEMM_EPI_THREADS);
+                        if (store_leader) {
+                            tma_reduce_add_2d(&map_out, stage_buf, n0 + c * 32, m0);
+                            tma_store_commit();
+                        }
                     }
                 }
+                // this thread has issued (and waited for) its last TMEM load of the tile: hand the buffer back
+                tc_fence_before();
+                if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0);
+                else mbar_arrive(&acc_empty[as]);
             }
-            // this thread has issued (and waited for) its last TMEM load of the tile: hand the buffer back
-            tc_fence_before();
-            if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0);
-            else mbar_arrive(&acc_empty[as]);
 
             if constexpr (RESID || OUT_TOKENS) {
-                // row statistics of the produced rows: warpgroup 1 hands its partial to warpgroup 0 through shared
+                // row statistics of the produced rows: warpgroups 1-3 hand their partials to warpgroup 0 through shared
                 // memory so that exactly one atomicAdd per (row, n-tile) reaches the global array (order-independent)
                 if (aux.stats_out != nullptr) {
-                    float* sx = stat_x + (it & 1) * 256 + row_in_tile * 2;
-                    if (wg == 1) { sx[0] = st_sum; sx[1] = st_sq; }
-                    named_bar_sync(3, 2 * GEMM_EPI_THREADS);
+                    float* sx = stat_x + (it & 1) * (NWG * 256) + row_in_tile * 2;
+                    if (wg != 0) { sx[wg * 256] = st_sum; sx[wg * 256 + 1] = st_sq; }
+                    named_bar_sync(BAR_EPI_ALL, NWG * GEMM_EPI_THREADS);
                     if (wg == 0 && row < M) {
                         size_t srow = row;
                         if constexpr (OUT_TOKENS) {
                             const int seq = row / tokens_per_seq;
                             srow = static_cast<size_t>(seq) * (tokens_per_seq + 1) + 1 + (row - seq * tokens_per_seq);
                         }
-                        atomicAdd(aux.stats_out + srow * 2, st_sum + sx[0]);
-                        atomicAdd(aux.stats_out + srow * 2 + 1, st_sq + sx[1]);
+#pragma unroll
+                        for (int g = 1; g < NWG; ++g) { st_sum += sx[g * 256]; st_sq += sx[g * 256 + 1]; }
+                        atomicAdd(aux.stats_out + srow * 2, st_sum);
+                        atomicAdd(aux.stats_out + srow * 2 + 1, st_sq);
                         if (RESID && n_idx == 0 && aux.stats_clear != nullptr)
                             *reinterpret_cast<float2*>(aux.stats_clear + static_cast<size_t>(row) * 2) = make_float2(0.f, 0.f);
                     }
@@ -424,6 +579,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
         if (store_leader) tma_store_wait_all<0>();
+        }
     }
 
     tc_fence_before();
@@ -485,7 +641,10 @@ static int launch_gemm_bn(const GemmArgs& g, cudaStream_t stream) {
         case EPI_BIAS_GELU_FAST_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_FAST_BF16>(g, stream);
         case EPI_LNFOLD_BF16: return launch_gemm_t<BN, EPI_LNFOLD_BF16>(g, stream);
         case EPI_LNFOLD_GELU_BF16: return launch_gemm_t<BN, EPI_LNFOLD_GELU_BF16>(g, stream);
-        case EPI_RESID_STATS_F32: return launch_gemm_t<BN, EPI_RESID_STATS_F32>(g, stream);
+        case EPI_LNFOLD_GELU2_BF16: return launch_gemm_t<BN, EPI_LNFOLD_GELU2_BF16>(g, stream);
+        case EPI_RESID_STATS_F32:
+            if constexpr (BN == 256) return set_error("hb_gemm: the residual epilogue runs 128/192-wide tiles only");
+            else return launch_gemm_t<BN, EPI_RESID_STATS_F32>(g, stream);
     }
     return set_error("hb_gemm: unknown epilogue %d", g.epi);
 }
@@ -497,6 +656,10 @@ static bool gemm_use_cta_pairs() {      // HB_GEMM_CG=1 forces the single-CTA ke
 }
 
 int gemm_pick_bn(int N) {
+    {   // experiment hook: HB_GEMM_BN forces the tile width when it divides N
+        const char* e = getenv("HB_GEMM_BN");
+        if (e) { const int v = atoi(e); if ((v == 128 || v == 192 || v == 256) && N % v == 0) return v; }
+    }
     if (N % 256 == 0 && N >= 1024) return 256;
     if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
@@ -507,7 +670,8 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
                  const float* tok_table, int tokens_per_seq, const GemmAux* aux, void* xb_out, size_t out_pitch_bytes) {
     if (M <= 0 || N <= 0 || K <= 0) return set_error("hb_gemm: bad shape M=%d N=%d K=%d", M, N, K);
     if (K % GEMM_BK != 0) return set_error("hb_gemm: K=%d must be a multiple of %d", K, GEMM_BK);
-    const int bn = gemm_pick_bn(N);
+    int bn = gemm_pick_bn(N);
+    if (bn == 256 && epi == EPI_RESID_STATS_F32) bn = 128;      // residual ring + staging leave room for 128/192 only
     if (bn == 0) return set_error("hb_gemm: N=%d must be a multiple of 128 or 192", N);
     if (bias == nullptr) return set_error("hb_gemm: bias is required");
     g.bn = bn; g.epi = epi; g.M = M; g.N = N; g.K = K; g.bias = bias;
@@ -519,12 +683,12 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     if (encode_tmap_2d(&g.map_w2, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn / 2, GEMM_BK)) return -1;
     g.cg2 = (M > GEMM_BM) && gemm_use_cta_pairs();
     g.map_xb = g.map_a;                                       // placeholder unless the epilogue uses it
-    const bool out_bf16 = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16 ||
-                           epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16);
+    const bool lnfold = (epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16 || epi == EPI_LNFOLD_GELU2_BF16);
+    const bool out_bf16 = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16 || lnfold);
     if (out_bf16) {
-        if ((epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16) && (!g.aux.colvec2 || !g.aux.row_stats))
+        if (lnfold && (!g.aux.colvec2 || !g.aux.row_stats))
             return set_error("hb_gemm: the LayerNorm-folded epilogue needs the column vector c and the row statistics");
-        if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, GEMM_BM, 64)) return -1;
+        if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, 32, 64)) return -1;   // one store per epilogue warp: 32 rows x 64 columns
     } else if (epi == EPI_BIAS_RESADD_F32 || epi == EPI_RESID_STATS_F32) {
         // out_pitch_bytes: the fp32 rows may be strided (the CLS rows of a [n_seq, seq_len, N] residual stream)
         const uint64_t pitch = out_pitch_bytes ? out_pitch_bytes : static_cast<uint64_t>(N) * 4;
@@ -543,6 +707,12 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     }
     return 0;
 }
+
+#ifdef HB_EXP_TRACE
+extern "C" int hb_exp_read_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 4 * 1024) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
     switch (g.bn) {

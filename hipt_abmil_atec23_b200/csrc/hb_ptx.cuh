@@ -134,6 +134,12 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// warpgroup register reallocation (every warp of the warpgroup must execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------
@@ -329,6 +335,39 @@ __device__ __forceinline__ uint32_t gelu_fast2_bf16(f32x2_t x) {
     const f32x2_t hx = f2_mul(x, f2_pack(0.5f, 0.5f));
     f2_unpack(f2_fma(hx, f2_pack(ta, tb), hx), a, b);
     return pack_bf16x2(a, b);
+}
+// TWICE the GELU of two values, x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))): the MLP hot path folds the factor 0.5 into the
+// weights of the Linear that consumes the result (exact: a power of two), saving one packed multiply per pair.
+__device__ __forceinline__ uint32_t gelu_fast2x2_bf16(f32x2_t x) {
+    f32x2_t x2 = f2_mul(x, x);
+    float a, b;
+    f2_unpack(x2, a, b);
+    x2 = f2_pack(fminf(a, 50.0f), fminf(b, 50.0f));
+    f32x2_t p = f2_fma(x2, f2_pack(-0.00035151678813682844f, -0.00035151678813682844f),
+                       f2_pack(0.03700564602178616f, 0.03700564602178616f));
+    p = f2_fma(p, x2, f2_pack(0.7975078842899392f, 0.7975078842899392f));
+    f2_unpack(f2_mul(p, x), a, b);
+    float ta, tb;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+    f2_unpack(f2_fma(x, f2_pack(ta, tb), x), a, b);
+    return pack_bf16x2(a, b);
+}
+
+// shared-memory accesses by 32-bit shared address (keeps LDS/STS when the generic pointer's state space is lost)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 }  // namespace hb

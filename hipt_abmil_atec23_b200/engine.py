@@ -94,7 +94,7 @@ class VitEngine:
             qw, qc, qd = fold(blk.norm1, blk.attn.qkv)
             fw, fc, fd = fold(blk.norm2, blk.mlp.fc1)
             w += [qw, qc, qd, bf16(blk.attn.proj.weight), f32(blk.attn.proj.bias),
-                  fw, fc, fd, bf16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)]
+                  fw, fc, fd, bf16(blk.mlp.fc2.weight * 0.5), f32(blk.mlp.fc2.bias)]      # fc1 epilogue emits 2 * GELU
         self.weights = w                              # keeps the device copies alive
         if self.kind == "vit4k":
             self.phi_w = bf16(m.phi[0].weight)

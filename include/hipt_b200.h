@@ -32,6 +32,7 @@ extern "C" {
 #define HB_EPI_LNFOLD_BF16 6         /* hb_gemm_lnfold_bf16 */
 #define HB_EPI_LNFOLD_GELU_BF16 7    /* hb_gemm_lnfold_bf16 with gelu */
 #define HB_EPI_RESID_STATS_F32 8     /* hb_gemm_resid_stats */
+#define HB_EPI_LNFOLD_GELU2_BF16 9   /* hb_gemm_lnfold_bf16 with gelu = 2: TWICE the GELU (0.5 folded into the next Linear) */
 
 int hb_abi_version(void);
 const char* hb_last_error(void);
@@ -72,7 +73,8 @@ int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int 
 /* LayerNorm followed by Linear (norm1 -> attn.qkv, norm2 -> mlp.fc1 [+ GELU]; vision_transformer.py:147,151) as ONE GEMM:
  * xb_bf16 [M,K] is the UN-normalised residual stream in bf16, w_gamma_bf16 [N,K] = bf16(W * gamma), c[j] = sum_k of
  * that rounded weight's row j, d[j] = sum_k beta_k W_jk + bias_j, row_stats [M,2] = (sum, sum of squares) of the fp32
- * rows.  out[r,j] = act(rstd_r * acc[r,j] - rstd_r * mu_r * c[j] + d[j]). */
+ * rows.  out[r,j] = act(rstd_r * acc[r,j] - rstd_r * mu_r * c[j] + d[j]); gelu: 0 none, 1 GELU, 2 twice the GELU (the MLP
+ * path: the consumer's weights carry the factor 0.5, which is exact in bf16). */
 int hb_gemm_lnfold_bf16(const void* xb_bf16, const void* w_gamma_bf16, const float* c, const float* d,
                         const float* row_stats, float eps, int gelu, void* out_bf16, int M, int N, int K, void* stream);
 
@@ -118,7 +120,8 @@ typedef struct hb_vit_config {
 
 /* weights[]: [0] cls_token f32[dim], [1] norm.weight, [2] norm.bias, then for block i at 3+10*i (LayerNorms folded, see
  * hb_gemm_lnfold_bf16): qkv w_gamma (bf16 [3dim,dim]), qkv c, qkv d, attn.proj.weight (bf16), attn.proj.bias,
- * fc1 w_gamma (bf16 [mlp,dim]), fc1 c, fc1 d, mlp.fc2.weight (bf16 [dim,mlp]), mlp.fc2.bias.  Non-weight entries fp32. */
+ * fc1 w_gamma (bf16 [mlp,dim]), fc1 c, fc1 d, 0.5 * mlp.fc2.weight (bf16 [dim,mlp]; the plan's fc1 epilogue emits twice the
+ * GELU), mlp.fc2.bias.  Non-weight entries fp32. */
 size_t hb_vit_workspace_bytes(const hb_vit_config* cfg);
 int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host, int n_weights, void* workspace,
                        size_t workspace_bytes, hb_vit_plan** plan_out);
