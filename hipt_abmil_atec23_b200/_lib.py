@@ -21,6 +21,7 @@ HB_EPI_LNFOLD_BF16 = 6
 HB_EPI_LNFOLD_GELU_BF16 = 7
 HB_EPI_RESID_STATS_F32 = 8
 HB_EPI_LNFOLD_GELU2_BF16 = 9
+HB_EPI_RESID_BF16 = 10
 
 
 class HbVitConfig(C.Structure):
@@ -38,12 +39,16 @@ SIGNATURES = {
     "hb_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "hb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_int, C.c_void_p]),
-    "hb_gemm_lnfold_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
-                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hb_gemm_lnfold_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                      C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hb_gemm_resid_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hb_gemm_resid_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hb_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p]),
+    "hb_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_void_p]),
     "hb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "hb_im2col_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p]),
@@ -161,15 +166,34 @@ def gemm_bf16(a, w, bias, epilogue, out=None, tok_table=None, tokens_per_seq=0):
 
 
 def gemm_lnfold_bf16(xb, w_gamma, c, d, row_stats, eps, gelu=0):
-    """LayerNorm + Linear (+GELU) as one GEMM on the un-normalised bf16 rows (see hb_gemm_lnfold_bf16); gelu: 0 / 1 / 2 (2 x GELU)."""
+    """LayerNorm + Linear (+GELU) as one GEMM on the un-normalised bf16 rows (see hb_gemm_lnfold_bf16); gelu: 0 / 1 / 2
+    (2 x GELU).  row_stats: [M, 2] or [n_part, rows >= M, 2] partial (sum, sum of squares) planes."""
     require_cuda(xb, "xb")
     device_check()
     M, K = xb.shape
     N = w_gamma.shape[0]
+    if row_stats.dim() == 2:
+        row_stats = row_stats.unsqueeze(0)
+    assert row_stats.is_contiguous() and row_stats.shape[1] >= M and row_stats.shape[2] == 2
     out = torch.empty((M, N), dtype=torch.bfloat16, device=xb.device)
-    check(load().hb_gemm_lnfold_bf16(ptr(xb), ptr(w_gamma), ptr(c), ptr(d), ptr(row_stats), eps, int(gelu), ptr(out),
-                                     M, N, K, stream_ptr()))
+    check(load().hb_gemm_lnfold_bf16(ptr(xb), ptr(w_gamma), ptr(c), ptr(d), ptr(row_stats), row_stats.shape[0],
+                                     row_stats.shape[1], eps, int(gelu), ptr(out), M, N, K, stream_ptr()))
     return out
+
+
+def gemm_resid_bf16(a, w, bias, res, out=None, res_pitch_bytes=0):
+    """out = bf16(res + a @ w.T + bias) (fp32 add, one rounding); res may be out itself (in place, the default) or a
+    strided source.  Returns (out, stats_part [N/64, M, 2])."""
+    require_cuda(a, "a")
+    device_check()
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = res
+    stats = torch.empty((N // 64, M, 2), dtype=torch.float32, device=a.device)
+    check(load().hb_gemm_resid_bf16(ptr(a), ptr(w), ptr(bias), ptr(res), res_pitch_bytes, ptr(out), ptr(stats), M, M, N, K,
+                                    stream_ptr()))
+    return out, stats
 
 
 def gemm_resid_stats(a, w, bias, x, xb, stats_out, stats_clear=None):
@@ -184,13 +208,15 @@ def gemm_resid_stats(a, w, bias, x, xb, stats_out, stats_clear=None):
 
 
 def layernorm(x, gamma, beta, eps, rows, dim, row_stride=None, want_bf16=True, want_f32=False):
+    """nn.LayerNorm over fp32 or bf16 rows (row_stride in elements)."""
     require_cuda(x, "x")
     device_check()
-    assert x.dtype == torch.float32
+    assert x.dtype in (torch.float32, torch.bfloat16)
     ob = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     of = torch.empty((rows, dim), dtype=torch.float32, device=x.device) if want_f32 else None
-    check(load().hb_layernorm(ptr(x), row_stride if row_stride is not None else dim, ptr(gamma), ptr(beta), eps,
-                              ptr(ob), ptr(of), rows, dim, stream_ptr()))
+    fn = load().hb_layernorm if x.dtype == torch.float32 else load().hb_layernorm_bf16
+    check(fn(ptr(x), row_stride if row_stride is not None else dim, ptr(gamma), ptr(beta), eps,
+             ptr(ob), ptr(of), rows, dim, stream_ptr()))
     return ob, of
 
 

@@ -107,24 +107,27 @@ ProfScope::~ProfScope() {
 using namespace hb;
 
 // ---------------------------------------------------------------------------------------------------- plan object
-// Block pipeline (Block.forward, vision_transformer.py:146-152) with both LayerNorms folded into the GEMMs around them:
-//   qkv  = LNFOLD(xb; Wqkv*gamma1)            A = bf16 residual stream, per-row (mu, rstd) from stats1
+// Block pipeline (Block.forward, vision_transformer.py:146-152).  The residual stream lives in HBM as bf16 only (xb): every
+// epilogue that updates it adds in fp32 (accumulator + bias + the bf16 residual), rounds once, and leaves per-row partial
+// (sum, sum of squares) of the UNROUNDED values, one plane per 64 columns, for the LayerNorm folded into the next GEMM:
+//   qkv  = LNFOLD(xb; Wqkv*gamma1)            per-row (mu, rstd) from the stats1 planes
 //   att  = softmax(q k^T) v
-//   x   += att Wproj^T + b      (RESID)       writes x fp32, xb bf16, stats2 = row sums of the new x; clears stats1
+//   xb   = bf16(xb + att Wproj^T + b)         (RESID_BF16)  writes the stats2 planes
 //   hid  = 2 gelu(LNFOLD(xb; Wfc1*gamma2))    per-row factors from stats2 (the 0.5 lives in the fc2 weights)
-//   x   += hid (Wfc2/2)^T + b   (RESID)       writes x, xb, stats1 (for the next block); clears stats2
+//   xb   = bf16(xb + hid (Wfc2/2)^T + b)      (RESID_BF16)  writes the stats1 planes
 struct hb_vit_plan {
     hb_vit_config cfg;
     int depth_limit;
     bool cls_only_last;
+    size_t rows;       // capacity in rows (max_rows rounded up to 256) = stride between statistics planes
+    int n_part;        // statistics planes per row = dim / 64
     // workspace carve-up
-    float* x;          // [max_rows, dim] fp32 residual stream
-    void* xb;          // [max_rows, dim] bf16 copy of the residual stream (A operand of the LN-folded GEMMs)
-    void* qkv;         // [max_rows, 3 dim] bf16
-    void* att;         // [max_rows, dim] bf16 attention output
-    void* hid;         // [max_rows, mlp] bf16 MLP hidden (also the im2col operand of the patch embed)
-    float* stats1;     // [max_rows, 2] (sum, sum of squares) of x rows before norm1
-    float* stats2;     // [max_rows, 2] same before norm2
+    void* xb;          // [rows, dim] bf16 residual stream (A operand of the LN-folded GEMMs)
+    void* qkv;         // [rows, 3 dim] bf16; its head doubles as the compact CLS-row stream of the last block
+    void* att;         // [rows, dim] bf16 attention output
+    void* hid;         // [rows, mlp] bf16 MLP hidden (also the im2col operand of the patch embed)
+    float* stats1;     // [n_part][rows][2] partial (sum, sum of squares) of the rows before norm1
+    float* stats2;     // same before norm2
     size_t hid_bytes;
     std::vector<const void*> w;
     std::vector<GemmArgs> g_qkv, g_proj, g_fc1, g_fc2;
@@ -132,21 +135,22 @@ struct hb_vit_plan {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct WsLayout { size_t x, xb, qkv, att, hid, hid_bytes, stats1, stats2, total; };
+struct WsLayout { size_t xb, qkv, att, hid, hid_bytes, stats1, stats2, total, rows; };
 
 static WsLayout ws_layout(const hb_vit_config* c) {
     const size_t rows = align_up(static_cast<size_t>(c->max_rows), 256);
+    const size_t n_part = static_cast<size_t>(c->dim) / 64;
     WsLayout L;
     size_t o = 0;
-    L.x = o;   o += align_up(rows * c->dim * 4, 1024);
+    L.rows = rows;
     L.xb = o;  o += align_up(rows * c->dim * 2, 1024);
     L.qkv = o; o += align_up(rows * c->dim * 3 * 2, 1024);
     L.att = o; o += align_up(rows * c->dim * 2, 1024);
     L.hid = o;
     L.hid_bytes = align_up(rows * c->mlp_dim * 2, 1024);
     o += L.hid_bytes;
-    L.stats1 = o; o += align_up(rows * 8, 1024);
-    L.stats2 = o; o += align_up(rows * 8, 1024);
+    L.stats1 = o; o += align_up(n_part * rows * 8, 1024);
+    L.stats2 = o; o += align_up(n_part * rows * 8, 1024);
     L.total = o;
     return L;
 }
@@ -172,7 +176,7 @@ int hb_device_check(int* sm_count, int* cc_major, int* cc_minor) {
 int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int epilogue, void* out, int M, int N,
                  int K, const float* tok_table, int tokens_per_seq, void* stream) {
     if (epilogue == HB_EPI_LNFOLD_BF16 || epilogue == HB_EPI_LNFOLD_GELU_BF16 || epilogue == HB_EPI_LNFOLD_GELU2_BF16 ||
-        epilogue == HB_EPI_RESID_STATS_F32)
+        epilogue == HB_EPI_RESID_STATS_F32 || epilogue == HB_EPI_RESID_BF16)
         return set_error("hb_gemm_bf16: use hb_gemm_lnfold_bf16 / hb_gemm_resid_stats for epilogue %d", epilogue);
     GemmArgs g;
     if (gemm_prepare(g, a_bf16, w_bf16, bias, epilogue, out, M, N, K, tok_table, tokens_per_seq)) return -1;
@@ -180,10 +184,13 @@ int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int 
 }
 
 int hb_gemm_lnfold_bf16(const void* xb_bf16, const void* w_gamma_bf16, const float* c, const float* d,
-                        const float* row_stats, float eps, int gelu, void* out_bf16, int M, int N, int K, void* stream) {
+                        const float* row_stats, int n_part, int stats_stride, float eps, int gelu, void* out_bf16, int M,
+                        int N, int K, void* stream) {
     GemmAux aux = {};
     aux.colvec2 = c;
     aux.row_stats = row_stats;
+    aux.n_part = n_part;
+    aux.stats_stride = stats_stride;
     aux.inv_dim = 1.0f / static_cast<float>(K);
     aux.eps = eps;
     GemmArgs g;
@@ -202,9 +209,28 @@ int hb_gemm_resid_stats(const void* a_bf16, const void* w_bf16, const float* bia
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
 
+int hb_gemm_resid_bf16(const void* a_bf16, const void* w_bf16, const float* bias, const void* res_bf16,
+                       size_t res_pitch_bytes, void* out_bf16, float* stats_part, int stats_stride, int M, int N, int K,
+                       void* stream) {
+    if (N % 64 != 0) return set_error("hb_gemm_resid_bf16: N=%d must be a multiple of 64", N);
+    GemmAux aux = {};
+    aux.stats_out = stats_part;
+    aux.stats_stride = stats_stride;
+    GemmArgs g;
+    if (gemm_prepare(g, a_bf16, w_bf16, bias, HB_EPI_RESID_BF16, out_bf16, M, N, K, nullptr, 0, &aux,
+                     const_cast<void*>(res_bf16), res_pitch_bytes)) return -1;
+    return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
 int hb_layernorm(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps, void* out_bf16,
                  float* out_f32, int rows, int dim, void* stream) {
-    return layernorm_launch(x, x_row_stride, gamma, beta, eps, out_bf16, out_f32, rows, dim,
+    return layernorm_launch(x, 0, x_row_stride, gamma, beta, eps, out_bf16, out_f32, rows, dim,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int hb_layernorm_bf16(const void* x_bf16, size_t x_row_stride, const float* gamma, const float* beta, float eps,
+                      void* out_bf16, float* out_f32, int rows, int dim, void* stream) {
+    return layernorm_launch(x_bf16, 1, x_row_stride, gamma, beta, eps, out_bf16, out_f32, rows, dim,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -267,7 +293,8 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
         p->cls_only_last = !(e && e[0] == '1');
     }
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    p->x = reinterpret_cast<float*>(ws + L.x);
+    p->rows = L.rows;
+    p->n_part = cfg->dim / 64;
     p->xb = ws + L.xb;
     p->qkv = ws + L.qkv;
     p->att = ws + L.att;
@@ -277,19 +304,22 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
     p->stats2 = reinterpret_cast<float*>(ws + L.stats2);
     p->w.assign(weights_host, weights_host + n_weights);
     const int D = cfg->dim, H = cfg->mlp_dim, R = cfg->max_rows;
+    const int stride = static_cast<int>(L.rows);
     p->g_qkv.resize(cfg->depth); p->g_proj.resize(cfg->depth); p->g_fc1.resize(cfg->depth); p->g_fc2.resize(cfg->depth);
     for (int i = 0; i < cfg->depth; ++i) {
         const void* const* w = &p->w[3 + 10 * i];
         GemmAux a1 = {}, a2 = {}, r1 = {}, r2 = {};
         a1.colvec2 = static_cast<const float*>(w[1]); a1.row_stats = p->stats1; a1.inv_dim = 1.0f / D; a1.eps = cfg->ln_eps;
         a2.colvec2 = static_cast<const float*>(w[6]); a2.row_stats = p->stats2; a2.inv_dim = 1.0f / D; a2.eps = cfg->ln_eps;
-        r1.stats_out = p->stats2; r1.stats_clear = p->stats1;
-        r2.stats_out = p->stats1; r2.stats_clear = p->stats2;
+        a1.n_part = a2.n_part = p->n_part;
+        a1.stats_stride = a2.stats_stride = r1.stats_stride = r2.stats_stride = stride;
+        r1.stats_out = p->stats2;
+        r2.stats_out = p->stats1;
         int rc = 0;
         rc |= gemm_prepare(p->g_qkv[i], p->xb, w[0], static_cast<const float*>(w[2]), HB_EPI_LNFOLD_BF16, p->qkv, R, 3 * D, D, nullptr, 0, &a1);
-        rc |= gemm_prepare(p->g_proj[i], p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_STATS_F32, p->x, R, D, D, nullptr, 0, &r1, p->xb);
+        rc |= gemm_prepare(p->g_proj[i], p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_BF16, p->xb, R, D, D, nullptr, 0, &r1, p->xb);
         rc |= gemm_prepare(p->g_fc1[i], p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU2_BF16, p->hid, R, H, D, nullptr, 0, &a2);
-        rc |= gemm_prepare(p->g_fc2[i], p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_STATS_F32, p->x, R, D, H, nullptr, 0, &r2, p->xb);
+        rc |= gemm_prepare(p->g_fc2[i], p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_BF16, p->xb, R, D, H, nullptr, 0, &r2, p->xb);
         if (rc) { delete p; return -1; }
     }
     *plan_out = p;
@@ -306,29 +336,31 @@ int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit) {
 
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes) {
     if (!plan || !ptr || !bytes) return set_error("null argument");
-    const size_t rows = align_up(static_cast<size_t>(plan->cfg.max_rows), 256);
+    const size_t rows = plan->rows;
     switch (which) {
-        case 0: *ptr = plan->x; *bytes = rows * plan->cfg.dim * 4; return 0;
         case 1: *ptr = plan->xb; *bytes = rows * plan->cfg.dim * 2; return 0;
         case 2: *ptr = plan->qkv; *bytes = rows * plan->cfg.dim * 6; return 0;
         case 3: *ptr = plan->att; *bytes = rows * plan->cfg.dim * 2; return 0;
         case 4: *ptr = plan->hid; *bytes = plan->hid_bytes; return 0;
     }
-    return set_error("hb_vit_plan_buffer: unknown buffer %d", which);
+    return set_error("hb_vit_plan_buffer: unknown buffer %d (1 residual stream bf16, 2 qkv, 3 attention out, 4 hidden)", which);
 }
 
 }  // extern "C"
 
-// x / xb / stats1 already hold the token rows; runs the transformer blocks and the final LayerNorm on the CLS rows.
+// xb / stats1 already hold the token rows; runs the transformer blocks and the final LayerNorm on the CLS rows.
 static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, void* cls_bf16, cudaStream_t st) {
     const hb_vit_config& c = p->cfg;
     const int M = n_seq * seq_len;
     const int D = c.dim, hd = D / c.heads;
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
     const int kb = (D == 192) ? HB_PROF_4K_OFFSET : 0;     // profiler kind base: ViT-256 vs ViT-4K
+    const int stride = static_cast<int>(p->rows);
     // forward() returns x[:, 0] only, so after the K / V of the LAST block exist nothing but the CLS rows matters:
     // its attention, proj, fc1 and fc2 run on n_seq rows instead of n_seq * seq_len.
     const bool cls_tail = p->cls_only_last && p->depth_limit == c.depth;
+    const void* final_src = p->xb;
+    size_t final_stride = static_cast<size_t>(seq_len) * D;
     for (int i = 0; i < p->depth_limit; ++i) {
         GemmArgs g = p->g_qkv[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_QKV_GEMM, st); if (gemm_launch(g, st)) return -1; }
@@ -336,17 +368,24 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
             const void* const* w = &p->w[3 + 10 * i];
             { ProfScope ps(kb + HB_PROF_ATTENTION, st);
               if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st, 1)) return -1; }
-            const size_t pitch = static_cast<size_t>(seq_len) * D * 4;
+            // compact CLS stream xc [n_seq, D] in the head of the (now dead) qkv buffer; its residual source is the
+            // strided CLS rows of xb
+            void* xc = p->qkv;
+            const size_t pitch = static_cast<size_t>(seq_len) * D * 2;
             GemmAux r1 = {}, a2 = {}, r2 = {};
-            r1.stats_out = p->stats2;                       // compact: row r = sequence r (stats2 is zero here)
+            r1.stats_out = p->stats2; r1.stats_stride = stride;
             a2.colvec2 = static_cast<const float*>(w[6]); a2.row_stats = p->stats2; a2.inv_dim = 1.0f / D; a2.eps = c.ln_eps;
+            a2.n_part = p->n_part; a2.stats_stride = stride;
+            r2.stats_out = p->stats1; r2.stats_stride = stride;
             GemmArgs gp, g1, g2;
-            if (gemm_prepare(gp, p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_STATS_F32, p->x, n_seq, D, D, nullptr, 0, &r1, p->xb, pitch)) return -1;
-            if (gemm_prepare(g1, p->xb, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU2_BF16, p->hid, n_seq, c.mlp_dim, D, nullptr, 0, &a2)) return -1;
-            if (gemm_prepare(g2, p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_STATS_F32, p->x, n_seq, D, c.mlp_dim, nullptr, 0, &r2, p->xb, pitch)) return -1;
+            if (gemm_prepare(gp, p->att, w[3], static_cast<const float*>(w[4]), HB_EPI_RESID_BF16, xc, n_seq, D, D, nullptr, 0, &r1, p->xb, pitch)) return -1;
+            if (gemm_prepare(g1, xc, w[5], static_cast<const float*>(w[7]), HB_EPI_LNFOLD_GELU2_BF16, p->hid, n_seq, c.mlp_dim, D, nullptr, 0, &a2)) return -1;
+            if (gemm_prepare(g2, p->hid, w[8], static_cast<const float*>(w[9]), HB_EPI_RESID_BF16, xc, n_seq, D, c.mlp_dim, nullptr, 0, &r2, xc)) return -1;
             { ProfScope ps(kb + HB_PROF_PROJ_GEMM, st); if (gemm_launch(gp, st)) return -1; }
             { ProfScope ps(kb + HB_PROF_FC1_GEMM, st); if (gemm_launch(g1, st)) return -1; }
             { ProfScope ps(kb + HB_PROF_FC2_GEMM, st); if (gemm_launch(g2, st)) return -1; }
+            final_src = xc;
+            final_stride = D;
             break;
         }
         { ProfScope ps(kb + HB_PROF_ATTENTION, st);
@@ -360,14 +399,14 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
     }
     // final LayerNorm only where it is consumed: x[:, 0] (vision_transformer.py:252-253)
     ProfScope ps(kb + HB_PROF_FINAL_LN, st);
-    return layernorm_launch(p->x, static_cast<size_t>(seq_len) * D, static_cast<const float*>(p->w[1]),
+    return layernorm_launch(final_src, 1, final_stride, static_cast<const float*>(p->w[1]),
                             static_cast<const float*>(p->w[2]), c.ln_eps, cls_bf16, cls_f32, n_seq, D, st);
 }
 
-// zero both statistics arrays for the rows of this call (they are accumulated with atomics)
-static int clear_stats(hb_vit_plan* p, int rows, cudaStream_t st) {
-    HB_CUDA_OK(cudaMemsetAsync(p->stats1, 0, static_cast<size_t>(rows) * 8, st));
-    HB_CUDA_OK(cudaMemsetAsync(p->stats2, 0, static_cast<size_t>(rows) * 8, st));
+// zero the norm1 statistics planes for the rows of this call: the token epilogue accumulates into plane 0 with atomics
+// and every later producer overwrites all planes (stats2 is always fully written by proj before fc1 reads it)
+static int clear_stats(hb_vit_plan* p, cudaStream_t st) {
+    HB_CUDA_OK(cudaMemsetAsync(p->stats1, 0, static_cast<size_t>(p->n_part) * p->rows * 8, st));
     return 0;
 }
 
@@ -385,16 +424,16 @@ int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, si
         return set_error("hb_vit256_forward: im2col operand does not fit the workspace");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = plan->cfg.dim;
-    if (clear_stats(plan, n_patches * seq_len, st)) return -1;
+    if (clear_stats(plan, st)) return -1;
     { ProfScope ps(HB_PROF_IM2COL, st);
       if (im2col_launch(image, image_is_f32, patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, plan->hid, st)) return -1; }
     GemmAux aux = {};
     aux.stats_out = plan->stats1;
     GemmArgs g;
-    if (gemm_prepare(g, plan->hid, embed_w_bf16, embed_b, HB_EPI_TOKENS_F32, plan->x, n_patches * T, D, 768, pos_table, T, &aux, plan->xb)) return -1;
+    if (gemm_prepare(g, plan->hid, embed_w_bf16, embed_b, HB_EPI_TOKENS_F32, nullptr, n_patches * T, D, 768, pos_table, T, &aux, plan->xb)) return -1;
     { ProfScope ps(HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
     { ProfScope ps(HB_PROF_CLS_ROWS, st);
-      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, plan->xb, plan->stats1, n_patches, seq_len, D, st)) return -1; }
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, nullptr, plan->xb, plan->stats1, n_patches, seq_len, D, st)) return -1; }
     return run_blocks(plan, n_patches, seq_len, cls_f32, cls_bf16, st);
 }
 
@@ -407,14 +446,14 @@ int hb_vit4k_forward(hb_vit_plan* plan, const void* cls256_bf16, int n_regions, 
         return set_error("hb_vit4k_forward: %d regions exceed the plan capacity of %d rows", n_regions, plan->cfg.max_rows);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = plan->cfg.dim;
-    if (clear_stats(plan, n_regions * seq_len, st)) return -1;
+    if (clear_stats(plan, st)) return -1;
     GemmAux aux = {};
     aux.stats_out = plan->stats1;
     GemmArgs g;
-    if (gemm_prepare(g, cls256_bf16, phi_w_bf16, phi_b, HB_EPI_TOKENS_GELU_F32, plan->x, n_regions * tokens_per_region, D, in_dim, pos_table, tokens_per_region, &aux, plan->xb)) return -1;
+    if (gemm_prepare(g, cls256_bf16, phi_w_bf16, phi_b, HB_EPI_TOKENS_GELU_F32, nullptr, n_regions * tokens_per_region, D, in_dim, pos_table, tokens_per_region, &aux, plan->xb)) return -1;
     { ProfScope ps(HB_PROF_4K_OFFSET + HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
     { ProfScope ps(HB_PROF_4K_OFFSET + HB_PROF_CLS_ROWS, st);
-      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, plan->x, plan->xb, plan->stats1, n_regions, seq_len, D, st)) return -1; }
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, nullptr, plan->xb, plan->stats1, n_regions, seq_len, D, st)) return -1; }
     return run_blocks(plan, n_regions, seq_len, out_f32, nullptr, st);
 }
 

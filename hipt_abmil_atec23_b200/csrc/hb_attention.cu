@@ -339,13 +339,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
         }
     } else if (warp == 1 || warp == 2) {
         // ------------------------------------------------------------------------------------------ MMA issuers
-        if (lane == 0) {
+        // The whole warp walks the pipeline (warp-uniform control flow and operands keep the descriptors in uniform
+        // registers); one elected lane issues the tcgen05.mma / commit instructions.
+        {
             const int x = warp - 1;                                                // pipeline
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
             const uint32_t t_acc = tmem_base + x * 256;
             const uint64_t dq = umma_desc_k128(smem_u32(sQ + x * ATC_TILE_BYTES));
             const uint64_t dk = umma_desc_k128(smem_u32(sK));
+            const uint32_t p_base = smem_u32(sP + (x * 2) * ATC_TILE_BYTES);
             uint32_t use0 = 0, use1 = 0;                                           // uses of P slot 0 / 1 so far
             for (int it = 0; it < my_items; ++it) {
                 const int st = it & 1;
@@ -353,28 +356,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map128, const __grid_con
                 mbar_wait(&q_full[x], it & 1);
                 if (it > 0) mbar_wait(&o_free[x], (it - 1) & 1);
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(t_acc, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
-                umma_commit(&s_full[x]);
-                umma_commit(&q_empty[x]);
-                umma_commit(k_empty);
+                    for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(t_acc, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+                    umma_commit(&s_full[x]);
+                    umma_commit(&q_empty[x]);
+                    umma_commit(k_empty);
+                }
+                __syncwarp();
                 mbar_wait(&v_full[st], (it >> 1) & 1);
                 const uint32_t v_base = smem_u32(sV + st * ATC_KV_BYTES);
+#pragma unroll
                 for (int a = 0; a < 5; ++a) {
                     const int slot = a & 1;
                     const uint32_t use = slot ? use1++ : use0++;
                     mbar_wait(&p_full[x * 2 + slot], use & 1);
                     tc_fence_after();
-                    const uint64_t dp = umma_desc_k128(smem_u32(sP + (x * 2 + slot) * ATC_TILE_BYTES));
-                    const int ksteps = (a < 4) ? 4 : 1;
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint64_t dv = umma_desc_k128(v_base + (a * 64 + kk * 16) * 128);
-                        umma_bf16_ss(t_acc, dp + 2 * kk, dv, idesc_pv, (a | kk) != 0);
+                    const uint64_t dp = umma_desc_k128(p_base + slot * ATC_TILE_BYTES);
+                    constexpr int dummy = 0; (void)dummy;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (a == 4 && kk > 0) break;                           // tail atom: key 256 only (K = 16)
+                            const uint64_t dv = umma_desc_k128(v_base + (a * 64 + kk * 16) * 128);
+                            umma_bf16_ss(t_acc, dp + 2 * kk, dv, idesc_pv, (a | kk) != 0);
+                        }
+                        umma_commit(&p_empty[x * 2 + slot]);
+                        if (a == 4) { umma_commit(&o_full[x]); umma_commit(&v_empty[st]); }
                     }
-                    umma_commit(&p_empty[x * 2 + slot]);
+                    __syncwarp();
                 }
-                umma_commit(&o_full[x]);
-                umma_commit(&v_empty[st]);
             }
         }
     } else if (warp == 3) {

@@ -53,11 +53,12 @@ constexpr uint32_t BAR_EPI_ALL = 5;  // named barrier over every epilogue thread
 // Epilogue kinds (mirrored in include/hipt_b200.h as HB_EPI_*)
 enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2, EPI_TOKENS_F32 = 3, EPI_TOKENS_GELU_F32 = 4,
               EPI_BIAS_GELU_FAST_BF16 = 5, EPI_LNFOLD_BF16 = 6, EPI_LNFOLD_GELU_BF16 = 7, EPI_RESID_STATS_F32 = 8,
-              EPI_LNFOLD_GELU2_BF16 = 9 };
+              EPI_LNFOLD_GELU2_BF16 = 9, EPI_RESID_BF16 = 10 };
 
 template <int BN, int CG, int EPI>
 struct GemmCfg {
     static constexpr bool RESID = (EPI == EPI_RESID_STATS_F32);
+    static constexpr bool RESB = (EPI == EPI_RESID_BF16);
     static constexpr bool TOKENS = (EPI == EPI_TOKENS_F32 || EPI == EPI_TOKENS_GELU_F32);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_ROWS = BN / CG;                    // W rows staged by this CTA
@@ -86,8 +87,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  const GemmAux aux, int M, int N, int K, int tokens_per_seq) {
     using Cfg = GemmCfg<BN, CG, EPI>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool RESB = Cfg::RESB;                    // bf16 residual stream: x = bf16(x + acc + bias), row statistics
     constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_FAST_BF16 ||
-                               EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16 || EPI == EPI_LNFOLD_GELU2_BF16);
+                               EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16 || EPI == EPI_LNFOLD_GELU2_BF16 || RESB);
     constexpr bool LNFOLD = (EPI == EPI_LNFOLD_BF16 || EPI == EPI_LNFOLD_GELU_BF16 || EPI == EPI_LNFOLD_GELU2_BF16);
     constexpr bool OUT_TOKENS = Cfg::TOKENS;
     constexpr bool RESID = Cfg::RESID;
@@ -112,7 +114,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* acc_empty = bars + 2 * STAGES + 2;// [2]       epilogue -> MMA
     uint64_t* ring_full = bars + 2 * STAGES + 4;             // [RESID_RING] residual tile landed (RESID only)
     uint64_t* ring_empty = ring_full + RESID_RING;           // [RESID_RING] its updated copy has been stored
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + RESID_RING);
+    uint64_t* res_full = ring_empty + RESID_RING;            // [16] per epilogue warp: bf16 residual chunk landed (RESB)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,13 +129,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
         if (!OUT_TOKENS) tma_prefetch_desc(&map_out);
-        if (RESID) tma_prefetch_desc(&map_xb);
+        if (RESID || RESB) tma_prefetch_desc(&map_xb);
     }
     if (warp == 1 && lane == 0) {
         // CG = 2: full_bar / acc_empty are used on the leader only and collect arrivals from both CTAs
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], OUT_BF16 ? CG * 8 : CG * NWG * GEMM_EPI_THREADS); }
         for (int i = 0; i < RESID_RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+        for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -290,11 +294,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
                 if constexpr (LNFOLD) {
+                    // (sum, sum of squares) of the row: aux.n_part partial sums left by the producing epilogues
                     const int r = mi * TILE_M + cta_rank * GEMM_BM + ew * 32 + lane;
-                    pf_sq = (r < M) ? __ldg(reinterpret_cast<const float2*>(aux.row_stats) + r) : make_float2(0.f, 0.f);
+                    pf_sq = make_float2(0.f, 0.f);
+                    if (r < M) {
+                        const float2* sp2 = reinterpret_cast<const float2*>(aux.row_stats) + r;
+#pragma unroll
+                        for (int pp = 0; pp < 6; ++pp) {
+                            if (pp < aux.n_part) {
+                                const float2 t = __ldg(sp2 + static_cast<size_t>(pp) * aux.stats_stride);
+                                pf_sq.x += t.x; pf_sq.y += t.y;
+                            }
+                        }
+                    }
                 }
             };
             if (tile_first < total_tiles) pf_load(m_idx, n_idx, 0);
+            [[maybe_unused]] uint32_t res_use = 0;                     // RESB: residual chunks received so far
             uint32_t k = 0;
             for (int tile = tile_first; tile < total_tiles; tile += step2, ++k) {
                 const int m0 = m_idx * TILE_M + cta_rank * GEMM_BM + ew * 32;
@@ -319,6 +335,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (n_idx >= n_tiles) { n_idx -= n_tiles; ++m_idx; }
                 if (tile + step2 < total_tiles) pf_load(m_idx, n_idx, k + 1);
                 [[maybe_unused]] const f32x2_t rstd2 = f2_pack(rstd, rstd), nrm2 = f2_pack(nrm, nrm);
+                if constexpr (RESB) {
+                    // residual chunk of the tile's first column chunk, fetched while the MMAs are still running (the
+                    // staging tile doubles as its landing buffer: the previous store must have drained it)
+                    if (lane == 0) {
+                        tma_store_wait_read<0>();
+                        mbar_arrive_expect_tx(&res_full[warp - 4], 4096);
+                        tma_load_2d(stage_buf, &map_xb, &res_full[warp - 4], n0 + sp * 64, m0);
+                    }
+                }
 
                 if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 0);
                 mbar_wait(&acc_full[as], aphase);
@@ -336,6 +361,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (c >= NCHUNK) break;
                     if (lane == 0 && (warp == 4 || warp == 12)) TRACE(1 + (warp == 12), k, 2 + 3 * cc);
                     const float* wv = wvec + cc * 128;
+                    if constexpr (RESB) {
+                        // ---- x_new = bf16(x_old + acc + bias) in place in the staging tile, partial row statistics
+                        if (cc == 1 && lane == 0) {                  // second chunk: its residual can only land now
+                            tma_store_wait_read<0>();
+                            mbar_arrive_expect_tx(&res_full[warp - 4], 4096);
+                            tma_load_2d(stage_buf, &map_xb, &res_full[warp - 4], n0 + c * 64, m0);
+                        }
+                        float st_sum = 0.f, st_sq = 0.f;
+                        mbar_wait(&res_full[warp - 4], res_use & 1);
+                        ++res_use;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(taddr + c * 64 + h * 32, v);
+                            tmem_ld_wait();
+                            if (h == 1 && c + 2 >= NCHUNK) {         // last TMEM read of the tile: hand the accumulator back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    if (CG == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0);
+                                    else mbar_arrive(&acc_empty[as]);
+                                }
+                            }
+                            const float4* b4 = reinterpret_cast<const float4*>(wv + h * 32);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {            // 8 columns = one 16-byte piece of the row
+                                const uint32_t addr = row_addr + (((h * 4 + q) ^ sw) << 4);
+                                uint4 rr;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(addr));
+                                const float4 ba = b4[2 * q], bb = b4[2 * q + 1];
+                                float o[8];
+                                o[0] = __uint_as_float(rr.x << 16) + __uint_as_float(v[8 * q + 0]) + ba.x;
+                                o[1] = __uint_as_float(rr.x & 0xffff0000u) + __uint_as_float(v[8 * q + 1]) + ba.y;
+                                o[2] = __uint_as_float(rr.y << 16) + __uint_as_float(v[8 * q + 2]) + ba.z;
+                                o[3] = __uint_as_float(rr.y & 0xffff0000u) + __uint_as_float(v[8 * q + 3]) + ba.w;
+                                o[4] = __uint_as_float(rr.z << 16) + __uint_as_float(v[8 * q + 4]) + bb.x;
+                                o[5] = __uint_as_float(rr.z & 0xffff0000u) + __uint_as_float(v[8 * q + 5]) + bb.y;
+                                o[6] = __uint_as_float(rr.w << 16) + __uint_as_float(v[8 * q + 6]) + bb.z;
+                                o[7] = __uint_as_float(rr.w & 0xffff0000u) + __uint_as_float(v[8 * q + 7]) + bb.w;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) { st_sum += o[e]; st_sq = fmaf(o[e], o[e], st_sq); }
+                                sts_u4(addr, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+                            }
+                        }
+                        {
+                            const int row = m0 + lane;
+                            const int slot = (n0 >> 6) + c;
+                            if (row < M)
+                                *reinterpret_cast<float2*>(aux.stats_out + (static_cast<size_t>(slot) * aux.stats_stride + row) * 2) =
+                                    make_float2(st_sum, st_sq);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_out, stage_buf, n0 + c * 64, m0);
+                            tma_store_commit();
+                        }
+                        continue;
+                    }
                     uint32_t pk[32];                 // 64 bf16 of this row
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -466,7 +552,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                         r[u].z = gelu_erf(r[u].z); r[u].w = gelu_erf(r[u].w);
                                     }
                                     r[u].x += t.x; r[u].y += t.y; r[u].z += t.z; r[u].w += t.w;
-                                    o4[j + u] = r[u];
+                                    if (tok_out) o4[j + u] = r[u];
                                     st_sum += (r[u].x + r[u].y) + (r[u].z + r[u].w);
                                     st_sq = fmaf(r[u].x, r[u].x, fmaf(r[u].y, r[u].y, fmaf(r[u].z, r[u].z, fmaf(r[u].w, r[u].w, st_sq))));
                                 }
@@ -642,6 +728,7 @@ static int launch_gemm_bn(const GemmArgs& g, cudaStream_t stream) {
         case EPI_LNFOLD_BF16: return launch_gemm_t<BN, EPI_LNFOLD_BF16>(g, stream);
         case EPI_LNFOLD_GELU_BF16: return launch_gemm_t<BN, EPI_LNFOLD_GELU_BF16>(g, stream);
         case EPI_LNFOLD_GELU2_BF16: return launch_gemm_t<BN, EPI_LNFOLD_GELU2_BF16>(g, stream);
+        case EPI_RESID_BF16: return launch_gemm_t<BN, EPI_RESID_BF16>(g, stream);
         case EPI_RESID_STATS_F32:
             if constexpr (BN == 256) return set_error("hb_gemm: the residual epilogue runs 128/192-wide tiles only");
             else return launch_gemm_t<BN, EPI_RESID_STATS_F32>(g, stream);
@@ -672,6 +759,7 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     if (K % GEMM_BK != 0) return set_error("hb_gemm: K=%d must be a multiple of %d", K, GEMM_BK);
     int bn = gemm_pick_bn(N);
     if (bn == 256 && epi == EPI_RESID_STATS_F32) bn = 128;      // residual ring + staging leave room for 128/192 only
+    if (bn == 256 && epi == EPI_RESID_BF16) bn = 128;           // 64-column statistics planes: keep the chunking simple
     if (bn == 0) return set_error("hb_gemm: N=%d must be a multiple of 128 or 192", N);
     if (bias == nullptr) return set_error("hb_gemm: bias is required");
     g.bn = bn; g.epi = epi; g.M = M; g.N = N; g.K = K; g.bias = bias;
@@ -684,10 +772,19 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     g.cg2 = (M > GEMM_BM) && gemm_use_cta_pairs();
     g.map_xb = g.map_a;                                       // placeholder unless the epilogue uses it
     const bool lnfold = (epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16 || epi == EPI_LNFOLD_GELU2_BF16);
-    const bool out_bf16 = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16 || lnfold);
+    const bool out_bf16 = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16 || lnfold ||
+                           epi == EPI_RESID_BF16);
     if (out_bf16) {
         if (lnfold && (!g.aux.colvec2 || !g.aux.row_stats))
             return set_error("hb_gemm: the LayerNorm-folded epilogue needs the column vector c and the row statistics");
+        if (lnfold && (g.aux.n_part < 1 || g.aux.n_part > 6 || g.aux.stats_stride < M))
+            return set_error("hb_gemm: the LayerNorm-folded epilogue needs 1..6 partial-sum planes of at least M rows");
+        if (epi == EPI_RESID_BF16) {
+            if (!xb_out || !g.aux.stats_out || g.aux.stats_stride < M)
+                return set_error("hb_gemm: the bf16 residual epilogue needs the residual source and the statistics planes");
+            const uint64_t rp = out_pitch_bytes ? out_pitch_bytes : static_cast<uint64_t>(N) * 2;
+            if (encode_tmap_2d(&g.map_xb, TMAP_BF16, xb_out, M, N, rp, 32, 64)) return -1;
+        }
         if (encode_tmap_2d(&g.map_out, TMAP_BF16, out, M, N, static_cast<uint64_t>(N) * 2, 32, 64)) return -1;   // one store per epilogue warp: 32 rows x 64 columns
     } else if (epi == EPI_BIAS_RESADD_F32 || epi == EPI_RESID_STATS_F32) {
         // out_pitch_bytes: the fp32 rows may be strided (the CLS rows of a [n_seq, seq_len, N] residual stream)

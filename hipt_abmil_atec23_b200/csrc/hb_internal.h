@@ -33,11 +33,13 @@ int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t ro
 
 struct GemmAux {                                 // epilogue side inputs / outputs, passed to the kernel by value
     const float* colvec2;                        // LNFOLD: c[N] = sum_k gamma_k W_jk (bias slot carries d[N])
-    const float* row_stats;                      // LNFOLD: [M][2] (sum, sum of squares) of the fp32 rows behind A
+    const float* row_stats;                      // LNFOLD: [n_part][stats_stride][2] partial (sum, sum of squares) of the rows behind A
     float* stats_out;                            // RESID / TOKENS: (sum, sum of squares) of the produced rows, accumulated
     float* stats_clear;                          // RESID: the other LayerNorm's statistics array, zeroed on the way
     __nv_bfloat16* xb_out;                       // TOKENS: bf16 copy of the produced rows (RESID stores it by TMA)
     float inv_dim, eps;                          // LNFOLD: 1 / normalised width, LayerNorm epsilon
+    int n_part;                                  // LNFOLD: partial sums per row (1..6); RESID_BF16 writes one per 64 columns
+    int stats_stride;                            // rows between two partial-sum planes
 };
 
 struct GemmArgs {
@@ -53,10 +55,12 @@ int gemm_pick_bn(int N);
 int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, int epi, void* out, int M, int N, int K,
                  const float* tok_table, int tokens_per_seq, const GemmAux* aux = nullptr, void* xb_out = nullptr,
                  size_t out_pitch_bytes = 0);
+// RESID_BF16: `out` is the destination [M, N] bf16 (dense), xb_out the residual source (row pitch out_pitch_bytes, 0 = dense;
+// may alias `out`), aux->stats_out the [N/64][stats_stride][2] partial row statistics.
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
 
 // elementwise / row kernels
-int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps,
+int layernorm_launch(const void* x, int x_is_bf16, size_t x_row_stride, const float* gamma, const float* beta, float eps,
                      void* out_bf16, float* out_f32, int rows, int dim, cudaStream_t stream);
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
                      cudaStream_t stream, int cls_only = 0);

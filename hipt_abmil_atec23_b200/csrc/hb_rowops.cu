@@ -12,8 +12,8 @@
 namespace hb {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-template <int DIM>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t x_row_stride,
+template <int DIM, bool IN_BF16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_any, size_t x_row_stride,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ out_bf16,
                                                         float* __restrict__ out_f32, int rows) {
@@ -36,9 +36,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const int row = r0 + sub;
         const bool valid = row < rows;
         float4 v[3];
-        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(valid ? row : 0) * x_row_stride);
+        if constexpr (IN_BF16) {
+            const uint2* xr = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(x_any) +
+                                                             static_cast<size_t>(valid ? row : 0) * x_row_stride);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) v[i] = xr[i * LANES + l];
+            for (int i = 0; i < 3; ++i) {
+                const uint2 w = xr[i * LANES + l];
+                v[i] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u),
+                                   __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+            }
+        } else {
+            const float4* xr = reinterpret_cast<const float4*>(static_cast<const float*>(x_any) +
+                                                               static_cast<size_t>(valid ? row : 0) * x_row_stride);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[i] = xr[i * LANES + l];
+        }
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -75,7 +87,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
-int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps,
+int layernorm_launch(const void* x, int x_is_bf16, size_t x_row_stride, const float* gamma, const float* beta, float eps,
                      void* out_bf16, float* out_f32, int rows, int dim, cudaStream_t stream) {
     if (rows <= 0) return 0;
     if (x_row_stride % 4 != 0) return set_error("hb_layernorm: row stride %zu must be a multiple of 4", x_row_stride);
@@ -83,12 +95,11 @@ int layernorm_launch(const float* x, size_t x_row_stride, const float* gamma, co
     int blocks = (rows + rows_per_block - 1) / rows_per_block;
     const int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    if (dim == 384)
-        layernorm_kernel<384><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps,
-                                                          static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows);
-    else if (dim == 192)
-        layernorm_kernel<192><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps,
-                                                          static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows);
+    __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+    if (dim == 384 && x_is_bf16) layernorm_kernel<384, true><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, ob, out_f32, rows);
+    else if (dim == 384) layernorm_kernel<384, false><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, ob, out_f32, rows);
+    else if (dim == 192 && x_is_bf16) layernorm_kernel<192, true><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, ob, out_f32, rows);
+    else if (dim == 192) layernorm_kernel<192, false><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, ob, out_f32, rows);
     else
         return set_error("hb_layernorm: dim %d not supported (384 or 192)", dim);
     count_launch();
@@ -192,7 +203,7 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls_token, const float
     float s = 0.f, q = 0.f;
     for (int d = lane; d < dim; d += 32) {
         const float v = cls_token[d] + pos_table[d];
-        x[row * dim + d] = v;
+        if (x) x[row * dim + d] = v;
         if (xb) xb[row * dim + d] = __float2bfloat16(v);
         s += v;
         q = fmaf(v, v, q);

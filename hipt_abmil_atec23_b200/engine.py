@@ -207,7 +207,7 @@ class VitEngine:
         _lib.check(self.lib.hb_vit_plan_set_depth_limit(self.plan, n))
 
     def buffer(self, which, rows, cols, dtype):
-        """View of a workspace buffer (0 x fp32, 1 bf16 copy of x, 2 qkv, 3 attention out, 4 hidden) as [rows, cols]."""
+        """View of a workspace buffer (1 bf16 residual stream, 2 qkv, 3 attention out, 4 hidden) as [rows, cols]."""
         p, nb = C.c_void_p(), C.c_size_t()
         _lib.check(self.lib.hb_vit_plan_buffer(self.plan, which, C.byref(p), C.byref(nb)))
         off = p.value - self._ws_raw.data_ptr()

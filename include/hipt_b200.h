@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 /* GEMM epilogues */
 #define HB_EPI_BIAS_BF16 0        /* out_bf16[M,N]  = A W^T + bias                                  */
@@ -33,6 +33,7 @@ extern "C" {
 #define HB_EPI_LNFOLD_GELU_BF16 7    /* hb_gemm_lnfold_bf16 with gelu */
 #define HB_EPI_RESID_STATS_F32 8     /* hb_gemm_resid_stats */
 #define HB_EPI_LNFOLD_GELU2_BF16 9   /* hb_gemm_lnfold_bf16 with gelu = 2: TWICE the GELU (0.5 folded into the next Linear) */
+#define HB_EPI_RESID_BF16 10         /* hb_gemm_resid_bf16 */
 
 int hb_abi_version(void);
 const char* hb_last_error(void);
@@ -72,15 +73,26 @@ int hb_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, int 
 
 /* LayerNorm followed by Linear (norm1 -> attn.qkv, norm2 -> mlp.fc1 [+ GELU]; vision_transformer.py:147,151) as ONE GEMM:
  * xb_bf16 [M,K] is the UN-normalised residual stream in bf16, w_gamma_bf16 [N,K] = bf16(W * gamma), c[j] = sum_k of
- * that rounded weight's row j, d[j] = sum_k beta_k W_jk + bias_j, row_stats [M,2] = (sum, sum of squares) of the fp32
- * rows.  out[r,j] = act(rstd_r * acc[r,j] - rstd_r * mu_r * c[j] + d[j]); gelu: 0 none, 1 GELU, 2 twice the GELU (the MLP
- * path: the consumer's weights carry the factor 0.5, which is exact in bf16). */
+ * that rounded weight's row j, d[j] = sum_k beta_k W_jk + bias_j.  row_stats holds n_part (1..6) planes
+ * [n_part][stats_stride][2] of partial (sum, sum of squares) of the rows (stats_stride >= M rows per plane); the planes
+ * are summed per row.  out[r,j] = act(rstd_r * acc[r,j] - rstd_r * mu_r * c[j] + d[j]); gelu: 0 none, 1 GELU, 2 twice the
+ * GELU (the MLP path: the consumer's weights carry the factor 0.5, which is exact in bf16). */
 int hb_gemm_lnfold_bf16(const void* xb_bf16, const void* w_gamma_bf16, const float* c, const float* d,
-                        const float* row_stats, float eps, int gelu, void* out_bf16, int M, int N, int K, void* stream);
+                        const float* row_stats, int n_part, int stats_stride, float eps, int gelu, void* out_bf16, int M,
+                        int N, int K, void* stream);
 
-/* Residual update x = x + drop_path(Linear(a)) (vision_transformer.py:149,151) with the bookkeeping the next folded
- * LayerNorm needs: x_f32 [M,N] updated in place, xb_bf16 [M,N] = bf16(x), stats_out [M,2] += (sum, sum of squares)
- * of the new rows (must be zero on entry), stats_clear [M,2] (may be NULL) zeroed. */
+/* Residual update x = x + drop_path(Linear(a)) (vision_transformer.py:149,151) on the bf16 residual stream:
+ * out_bf16[M,N] = bf16(float(res_bf16) + a W^T + bias), added in fp32 and rounded once.  res_bf16 rows are
+ * res_pitch_bytes apart (0 = dense N*2; the CLS rows of a [n_seq, seq_len, N] stream are a strided source) and may
+ * alias out_bf16 (in-place update).  stats_part [N/64][stats_stride][2]: per row and per 64-column group the (sum, sum
+ * of squares) of the UNROUNDED values, every plane fully overwritten (no atomics, no zeroing needed). */
+int hb_gemm_resid_bf16(const void* a_bf16, const void* w_bf16, const float* bias, const void* res_bf16,
+                       size_t res_pitch_bytes, void* out_bf16, float* stats_part, int stats_stride, int M, int N, int K,
+                       void* stream);
+
+/* The same residual update on an fp32 stream with a bf16 copy (the first design of the block pipeline; kept as a
+ * higher-precision building block): x_f32 [M,N] updated in place, xb_bf16 [M,N] = bf16(x), stats_out [M,2] += (sum, sum
+ * of squares) of the new rows (must be zero on entry), stats_clear [M,2] (may be NULL) zeroed. */
 int hb_gemm_resid_stats(const void* a_bf16, const void* w_bf16, const float* bias, float* x_f32, void* xb_bf16,
                         float* stats_out, float* stats_clear, int M, int N, int K, void* stream);
 
@@ -88,6 +100,9 @@ int hb_gemm_resid_stats(const void* a_bf16, const void* w_bf16, const float* bia
  * writes out_bf16 and/or out_f32 (either may be NULL), densely packed [rows, dim].  dim in {384, 192}. */
 int hb_layernorm(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps, void* out_bf16,
                  float* out_f32, int rows, int dim, void* stream);
+/* the same over bf16 rows (the final norm reads the CLS rows of the bf16 residual stream) */
+int hb_layernorm_bf16(const void* x_bf16, size_t x_row_stride, const float* gamma, const float* beta, float eps,
+                      void* out_bf16, float* out_f32, int rows, int dim, void* stream);
 
 /* softmax(q k^T * scale) v per (sequence, head): vision_transformer.py:119-128.
  * qkv_bf16 [n_seq*seq_len, 3*heads*head_dim] (q|k|v, head-major); out_bf16 [n_seq*seq_len, heads*head_dim]. */
@@ -127,7 +142,7 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
                        size_t workspace_bytes, hb_vit_plan** plan_out);
 void hb_vit_plan_destroy(hb_vit_plan* plan);
 /* debug / test hooks: run only the first `depth_limit` blocks (<=0: all); fetch a workspace buffer
- * (0 = x fp32 residual stream, 1 = bf16 copy of x, 2 = qkv bf16, 3 = attention out bf16, 4 = MLP hidden bf16) */
+ * (1 = bf16 residual stream, 2 = qkv bf16, 3 = attention out bf16, 4 = MLP hidden bf16) */
 int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit);
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes);
 

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_error_string():
     from hipt_abmil_atec23_b200 import _lib
     lib = _lib.load()
-    assert lib.hb_abi_version() == 1
+    assert lib.hb_abi_version() == 2
     assert isinstance(lib.hb_last_error(), bytes)
     assert lib.hb_clam_workspace_bytes(20000, 256, 5, 16) == 5 * 256 * 157 * 18 * 4
 
@@ -38,5 +38,6 @@ def test_config_struct_layout_matches_header():
     lib = __import__("hipt_abmil_atec23_b200._lib", fromlist=["load"]).load()
     cfg = HbVitConfig(384, 6, 12, 1536, 256 * 257, 1e-6)
     rows = 65792                                       # = 257 * 256: already a multiple of the 256-row pair tile
-    expect = rows * 384 * 4 + rows * 384 * 2 + rows * 384 * 6 + rows * 384 * 2 + rows * 1536 * 2 + 2 * rows * 8
+    # bf16 residual stream + qkv + attention out + MLP hidden + two sets of 6 statistics planes
+    expect = rows * 384 * 2 + rows * 384 * 6 + rows * 384 * 2 + rows * 1536 * 2 + 2 * 6 * rows * 8
     assert lib.hb_vit_workspace_bytes(ctypes.byref(cfg)) == expect

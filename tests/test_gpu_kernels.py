@@ -113,6 +113,62 @@ def test_gemm_residual_with_row_stats(M, N, K):
     assert torch.equal(stats2, stats) and torch.equal(x2, x)
 
 
+@pytest.mark.parametrize("M,N,K", [(257, 384, 384), (1000, 384, 1536), (65792, 384, 384), (65792, 384, 1536), (257, 192, 768),
+                                   (4112, 192, 192)])
+def test_gemm_residual_bf16_stream(M, N, K):
+    """x = bf16(x + a W^T + b) in place on the bf16 residual stream, with the per-64-column partial row statistics of
+    the unrounded values (bit-exact run to run: plain stores, no atomics)."""
+    L = _lib()
+    a = _rand((M, K), 60).cuda().bfloat16()
+    w = _rand((N, K), 61, 0.05).cuda().bfloat16()
+    b = _rand((N,), 62, 0.1).cuda()
+    x0 = _rand((M, N), 63).cuda().bfloat16()
+    x = x0.clone()
+    _, stats = L.gemm_resid_bf16(a, w, b, x)
+    ref = x0.float() + a.float() @ w.float().t() + b
+    err = (x.float() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-3).all()), err.max().item()
+    part = ref.view(M, N // 64, 64)
+    assert torch.allclose(stats[:, :, 0].t(), part.sum(2), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(stats[:, :, 1].t(), (part * part).sum(2), rtol=1e-4, atol=2e-2)
+    x2 = x0.clone()
+    _, stats2 = L.gemm_resid_bf16(a, w, b, x2)
+    assert torch.equal(x2, x) and torch.equal(stats2, stats)
+
+
+def test_gemm_residual_bf16_strided_source():
+    """The CLS rows of a [n_seq, 257, 384] stream as the residual source, compact destination (last-block tail)."""
+    L = _lib()
+    n_seq, S, N, K = 256, 257, 384, 384
+    a = _rand((n_seq, K), 70).cuda().bfloat16()
+    w = _rand((N, K), 71, 0.05).cuda().bfloat16()
+    b = _rand((N,), 72, 0.1).cuda()
+    stream = _rand((n_seq * S, N), 73).cuda().bfloat16()
+    out = torch.zeros((n_seq, N), dtype=torch.bfloat16, device="cuda")
+    before = stream.clone()
+    L.gemm_resid_bf16(a, w, b, stream, out=out, res_pitch_bytes=S * N * 2)
+    ref = stream[::S].float() + a.float() @ w.float().t() + b
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() + 1e-3
+    assert torch.equal(stream, before)
+
+
+def test_gemm_layernorm_folded_partial_planes():
+    """LN-folded GEMM reading the row statistics as 6 partial planes with a plane stride larger than M."""
+    L = _lib()
+    M, N, K = 1000, 1152, 384
+    x = (_rand((M, K), 80, 1.5) + 0.3 * _rand((1, K), 81)).cuda()
+    gamma = (1.0 + 0.2 * _rand((K,), 82)).cuda(); beta = (0.1 * _rand((K,), 83)).cuda()
+    W = _rand((N, K), 84, 0.05).cuda(); b = _rand((N,), 85, 0.1).cuda()
+    wg = (W * gamma[None, :]).bfloat16(); c = wg.float().sum(1); d = W @ beta + b
+    planes = torch.zeros((6, 1024, 2), device="cuda")
+    part = x.view(M, 6, 64)
+    planes[:, :M, 0] = part.sum(2).t(); planes[:, :M, 1] = (part * part).sum(2).t()
+    out = L.gemm_lnfold_bf16(x.bfloat16(), wg, c, d, planes, 1e-6)
+    ref = F.linear(F.layer_norm(x, (K,), gamma, beta, 1e-6), W, b)
+    assert F.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() > 0.9999
+    assert (out.float() - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("n_seq,T,N,K,gelu", [(3, 256, 384, 768, False), (2, 256, 192, 384, True), (3, 35, 192, 384, True)])
 def test_gemm_tokens(n_seq, T, N, K, gelu):
     L = _lib()
@@ -144,6 +200,17 @@ def test_layernorm(rows, dim):
     ref = F.layer_norm(x, (dim,), g, b, 1e-6)
     assert (of - ref).abs().max().item() < 2e-5
     assert (ob.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_layernorm_bf16_rows_strided():
+    """Final norm as the plan runs it: bf16 CLS rows of a [n, S, dim] stream."""
+    L = _lib()
+    n, S, dim = 256, 257, 384
+    x = _rand((n * S, dim), 90, 2.0).cuda().bfloat16()
+    g = (1.0 + 0.1 * _rand((dim,), 91)).cuda(); b = (0.1 * _rand((dim,), 92)).cuda()
+    _, of = L.layernorm(x, g, b, 1e-6, n, dim, row_stride=S * dim, want_bf16=False, want_f32=True)
+    ref = F.layer_norm(x[::S].float(), (dim,), g, b, 1e-6)
+    assert (of - ref).abs().max().item() < 1e-4
 
 
 def test_layernorm_strided_cls_rows():

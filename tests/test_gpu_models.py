@@ -51,7 +51,10 @@ def test_vit256_per_block_against_reference(gold, hipt):
             torch.cuda.synchronize()
             # the last block updates only the CLS rows (forward() returns x[:, 0]): compare 1 token at full depth
             nt = 1 if depth == 12 else 3
-            tok = eng.buffer(0, 2 * 257, 384, torch.float32).view(2, 257, 384)[:, :nt].cpu()
+            if depth == 12:      # the CLS-only tail keeps its compact [n_seq, 384] stream in the head of the qkv buffer
+                tok = eng.buffer(2, 2, 384, torch.bfloat16).view(2, 1, 384).float().cpu()
+            else:
+                tok = eng.buffer(1, 2 * 257, 384, torch.bfloat16).view(2, 257, 384)[:, :nt].float().cpu()
             ref = g["tokens_first3_per_block"][depth][:, :nt]
             err = (tok - ref).abs().max().item()
             print(f"depth {depth}: max abs {err:.4e}, cos {_cos(tok, ref):.6f}")
@@ -77,7 +80,7 @@ def test_tokens_before_blocks_match_oracle(hipt):
     try:
         eng.forward_patches(x.to(DEV))
         torch.cuda.synchronize()
-        tok = eng.buffer(0, 3 * 257, 384, torch.float32).view(3, 257, 384).cpu()
+        tok = eng.buffer(1, 3 * 257, 384, torch.bfloat16).view(3, 257, 384).float().cpu()
     finally:
         eng.set_depth_limit(0)
     ref1 = O.block(sd, "blocks.0.", ref, 6)
