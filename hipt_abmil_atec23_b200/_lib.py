@@ -45,6 +45,8 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hb_gemm_resid_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hb_mlp_fused_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hb_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p]),
     "hb_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
@@ -122,7 +124,8 @@ def device_check():
 
 PROF_KINDS = 32
 PROF_NAMES = {0: "im2col", 1: "embed_gemm", 2: "cls_rows", 3: "layernorm", 4: "qkv_gemm", 5: "attention",
-              6: "proj_gemm", 7: "fc1_gemm", 8: "fc2_gemm", 9: "final_ln", 10: "clam_scores", 11: "clam_combine"}
+              6: "proj_gemm", 7: "fc1_gemm", 8: "fc2_gemm", 9: "final_ln", 10: "clam_scores", 11: "clam_combine",
+              12: "mlp_fused"}
 
 
 def prof_enable(on=True):
@@ -194,6 +197,20 @@ def gemm_resid_bf16(a, w, bias, res, out=None, res_pitch_bytes=0):
     check(load().hb_gemm_resid_bf16(ptr(a), ptr(w), ptr(bias), ptr(res), res_pitch_bytes, ptr(out), ptr(stats), M, M, N, K,
                                     stream_ptr()))
     return out, stats
+
+
+def mlp_fused_bf16(xb, w1_gamma, c1, d1, w2_half, b2, stats_in):
+    """xb (bf16 [M, 384], updated in place) = bf16(xb + (2 gelu(LN-folded fc1)) @ w2_half.T + b2); returns the
+    [6, M, 2] partial row statistics of the new rows.  stats_in: [6, rows >= M, 2]."""
+    require_cuda(xb, "xb")
+    device_check()
+    M, D = xb.shape
+    H = w1_gamma.shape[0]
+    assert stats_in.is_contiguous() and stats_in.shape[0] == 6 and stats_in.shape[1] >= M
+    stats_out = torch.empty((6, stats_in.shape[1], 2), dtype=torch.float32, device=xb.device)
+    check(load().hb_mlp_fused_bf16(ptr(xb), ptr(w1_gamma), ptr(c1), ptr(d1), ptr(w2_half), ptr(b2), ptr(stats_in),
+                                   ptr(stats_out), stats_in.shape[1], 1e-6, M, D, H, stream_ptr()))
+    return stats_out
 
 
 def gemm_resid_stats(a, w, bias, x, xb, stats_out, stats_clear=None):

@@ -119,6 +119,7 @@ struct hb_vit_plan {
     hb_vit_config cfg;
     int depth_limit;
     bool cls_only_last;
+    bool fuse_mlp;     // dim 384 / hidden 1536: fc1 + GELU + fc2 + residual as one kernel (hb_mlp.cu)
     size_t rows;       // capacity in rows (max_rows rounded up to 256) = stride between statistics planes
     int n_part;        // statistics planes per row = dim / 64
     // workspace carve-up
@@ -222,6 +223,16 @@ int hb_gemm_resid_bf16(const void* a_bf16, const void* w_bf16, const float* bias
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
 
+int hb_mlp_fused_bf16(void* xb_bf16, const void* w1_gamma_bf16, const float* c1, const float* d1, const void* w2_half_bf16,
+                      const float* b2, const float* stats_in, float* stats_out, int stats_stride, float eps, int M,
+                      int dim, int hidden, void* stream) {
+    if (dim != 384 || hidden != 1536) return set_error("hb_mlp_fused_bf16: only dim 384 / hidden 1536 (ViT-S) is fused");
+    if (!xb_bf16 || !w1_gamma_bf16 || !c1 || !d1 || !w2_half_bf16 || !b2 || !stats_in || !stats_out)
+        return set_error("hb_mlp_fused_bf16: null argument");
+    return mlp_fused_launch(xb_bf16, w1_gamma_bf16, c1, d1, w2_half_bf16, b2, stats_in, stats_out, stats_stride, eps, M,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int hb_layernorm(const float* x, size_t x_row_stride, const float* gamma, const float* beta, float eps, void* out_bf16,
                  float* out_f32, int rows, int dim, void* stream) {
     return layernorm_launch(x, 0, x_row_stride, gamma, beta, eps, out_bf16, out_f32, rows, dim,
@@ -291,6 +302,10 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
     {
         const char* e = getenv("HB_VIT_FULL_LAST_BLOCK");   // debug: compute every token in the last block too
         p->cls_only_last = !(e && e[0] == '1');
+    }
+    {
+        const char* e = getenv("HB_MLP_UNFUSED");           // debug / comparison: run fc1 and fc2 as two GEMMs
+        p->fuse_mlp = cfg->dim == 384 && cfg->mlp_dim == 1536 && !(e && e[0] == '1');
     }
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     p->rows = L.rows;
@@ -392,6 +407,13 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
           if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st)) return -1; }
         g = p->g_proj[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_PROJ_GEMM, st); if (gemm_launch(g, st)) return -1; }
+        if (p->fuse_mlp) {
+            const void* const* w = &p->w[3 + 10 * i];
+            ProfScope ps(kb + HB_PROF_MLP_FUSED, st);
+            if (mlp_fused_launch(p->xb, w[5], static_cast<const float*>(w[6]), static_cast<const float*>(w[7]), w[8],
+                                 static_cast<const float*>(w[9]), p->stats2, p->stats1, stride, c.ln_eps, M, st)) return -1;
+            continue;
+        }
         g = p->g_fc1[i]; g.M = M;
         { ProfScope ps(kb + HB_PROF_FC1_GEMM, st); if (gemm_launch(g, st)) return -1; }
         g = p->g_fc2[i]; g.M = M;

@@ -58,6 +58,10 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
 // RESID_BF16: `out` is the destination [M, N] bf16 (dense), xb_out the residual source (row pitch out_pitch_bytes, 0 = dense;
 // may alias `out`), aux->stats_out the [N/64][stats_stride][2] partial row statistics.
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);
+// fused fc1 -> GELU -> fc2 -> residual for dim 384 / hidden 1536 (hb_mlp.cu); xb is updated in place
+int mlp_fused_launch(const void* xb_bf16, const void* w1g_bf16, const float* c1, const float* d1, const void* w2h_bf16,
+                     const float* b2, const float* stats_in, float* stats_out, int stats_stride, float eps, int M,
+                     cudaStream_t stream);
 
 // elementwise / row kernels
 int layernorm_launch(const void* x, int x_is_bf16, size_t x_row_stride, const float* gamma, const float* beta, float eps,

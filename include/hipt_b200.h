@@ -55,6 +55,7 @@ int hb_device_check(int* sm_count, int* cc_major, int* cc_minor);
 #define HB_PROF_FINAL_LN 9
 #define HB_PROF_CLAM_SCORES 10
 #define HB_PROF_CLAM_COMBINE 11
+#define HB_PROF_MLP_FUSED 12
 #define HB_PROF_4K_OFFSET 16
 #define HB_PROF_KINDS 32
 long long hb_launch_count(void);
@@ -95,6 +96,15 @@ int hb_gemm_resid_bf16(const void* a_bf16, const void* w_bf16, const float* bias
  * of squares) of the new rows (must be zero on entry), stats_clear [M,2] (may be NULL) zeroed. */
 int hb_gemm_resid_stats(const void* a_bf16, const void* w_bf16, const float* bias, float* x_f32, void* xb_bf16,
                         float* stats_out, float* stats_clear, int M, int N, int K, void* stream);
+
+/* The MLP half of a ViT-S block as ONE kernel: x = x + fc2(GELU(fc1(norm2(x)))) (vision_transformer.py:151 with Mlp.forward
+ * :98-104), dim 384, hidden 1536, on the bf16 residual stream in place; the hidden activation never leaves the SM.
+ * w1_gamma_bf16 [1536,384], c1, d1: fc1 with norm2 folded in as for hb_gemm_lnfold_bf16; w2_half_bf16 [384,1536] =
+ * 0.5 * fc2.weight (the GELU epilogue emits twice the GELU); stats_in / stats_out: [6][stats_stride][2] partial row
+ * statistics planes (read for norm2, written for the next norm1). */
+int hb_mlp_fused_bf16(void* xb_bf16, const void* w1_gamma_bf16, const float* c1, const float* d1, const void* w2_half_bf16,
+                      const float* b2, const float* stats_in, float* stats_out, int stats_stride, float eps, int M,
+                      int dim, int hidden, void* stream);
 
 /* nn.LayerNorm(dim, eps): vision_transformer.py:138,142,195.  x fp32 rows at x_row_stride (elements);
  * writes out_bf16 and/or out_f32 (either may be NULL), densely packed [rows, dim].  dim in {384, 192}. */

@@ -169,6 +169,37 @@ def test_gemm_layernorm_folded_partial_planes():
     assert (out.float() - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M", [256, 1000, 65792])
+def test_mlp_fused(M):
+    """fc1 (norm2 folded) -> GELU -> fc2 -> residual as one kernel against fp32 torch on the same bf16 stream."""
+    L = _lib()
+    D, H = 384, 1536
+    x = (_rand((M, D), 100, 1.5) + 0.3 * _rand((1, D), 101)).cuda()
+    xb0 = x.bfloat16()
+    gamma = (1.0 + 0.2 * _rand((D,), 102)).cuda(); beta = (0.1 * _rand((D,), 103)).cuda()
+    W1 = _rand((H, D), 104, 0.05).cuda(); b1 = _rand((H,), 105, 0.1).cuda()
+    W2 = _rand((D, H), 106, 0.03).cuda(); b2 = _rand((D,), 107, 0.1).cuda()
+    w1g = (W1 * gamma[None, :]).bfloat16(); c1 = w1g.float().sum(1); d1 = W1 @ beta + b1
+    w2h = (0.5 * W2).bfloat16()
+    part = x.view(M, 6, 64)
+    stats_in = torch.stack([part.sum(2).t(), (part * part).sum(2).t()], dim=2).contiguous()      # [6, M, 2]
+    xb = xb0.clone()
+    stats_out = L.mlp_fused_bf16(xb, w1g, c1, d1, w2h, b2, stats_in)
+    torch.cuda.synchronize()
+    hid = F.gelu(F.linear(F.layer_norm(x, (D,), gamma, beta, 1e-6), W1, b1))
+    ref = xb0.float() + F.linear(hid, W2, b2)
+    err = (xb.float() - ref).abs()
+    assert F.cosine_similarity(xb.float().flatten(), ref.flatten(), dim=0).item() > 0.9999
+    assert err.max().item() <= 4e-2 * max(1.0, ref.abs().max().item()), err.max().item()
+    # statistics of the produced rows (compare with the kernel's own rounded output, loosely: they are of the unrounded values)
+    po = xb.float().view(M, 6, 64)
+    assert torch.allclose(stats_out[:, :M, 0].t(), po.sum(2), rtol=2e-2, atol=0.5)
+    assert torch.allclose(stats_out[:, :M, 1].t(), (po * po).sum(2), rtol=2e-2, atol=0.5)
+    xb2 = xb0.clone()
+    stats2 = L.mlp_fused_bf16(xb2, w1g, c1, d1, w2h, b2, stats_in)
+    assert torch.equal(xb2, xb) and torch.equal(stats2[:, :M], stats_out[:, :M])
+
+
 @pytest.mark.parametrize("n_seq,T,N,K,gelu", [(3, 256, 384, 768, False), (2, 256, 192, 384, True), (3, 35, 192, 384, True)])
 def test_gemm_tokens(n_seq, T, N, K, gelu):
     L = _lib()

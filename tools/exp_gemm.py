@@ -32,3 +32,8 @@ for name, N, K, kind in (("qkv", 1152, 384, "ln"), ("fc1", 1536, 384, "lng"), ("
         a = att if K == 384 else hid
         f = lambda: L.gemm_resid_bf16(a, w, b, xb)
     timeit(name, f, 2.0 * M * N * K)
+if not only or "mlp" in only.split(","):
+    w1 = r((1536, 384), 0.05).bfloat16(); c1 = r((1536,), 0.1); d1 = r((1536,), 0.1)
+    w2 = r((384, 1536), 0.02).bfloat16(); b2 = r((384,), 0.1)
+    planes = torch.zeros((6, M, 2), device="cuda"); planes[0] = stats
+    timeit("mlp_fused", lambda: L.mlp_fused_bf16(xb, w1, c1, d1, w2, b2, planes), 4.0 * M * 1536 * 384)
