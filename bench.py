@@ -41,9 +41,17 @@ CLS = {             # the last block after its qkv GEMM: CLS rows only (forward(
     "proj_gemm": 2 * 256 * 384 * 384, "fc1_gemm": 2 * 256 * 1536 * 384, "fc2_gemm": 2 * 256 * 384 * 1536,
     "attention": 2 * 2 * 1 * 257 * 64 * 6 * 256,
 }
-# executed FLOPs per region and kernel: 12 launches, of which the last is CLS-only for everything but qkv
-KERNEL_FLOPS_PER_REGION = {k: (12 * v if k in ("qkv_gemm",) else v if k == "embed_gemm" else 11 * v + CLS[k])
-                           for k, v in FULL.items()}
+# executed FLOPs per region and kernel: 12 blocks, of which the last is CLS-only for everything but qkv; blocks 1-11 run
+# fc1 + GELU + fc2 + residual as ONE kernel (mlp_fused), the CLS-only tail of block 12 as two small GEMMs
+KERNEL_FLOPS_PER_REGION = {
+    "qkv_gemm": 12 * FULL["qkv_gemm"],
+    "embed_gemm": FULL["embed_gemm"],
+    "attention": 11 * FULL["attention"] + CLS["attention"],
+    "proj_gemm": 11 * FULL["proj_gemm"] + CLS["proj_gemm"],
+    "mlp_fused": 11 * (FULL["fc1_gemm"] + FULL["fc2_gemm"]),
+    "fc1_gemm": CLS["fc1_gemm"],
+    "fc2_gemm": CLS["fc2_gemm"],
+}
 VIT4K_FLOPS_PER_REGION = 1_706_365_440
 EXECUTED_FLOPS_PER_REGION = sum(KERNEL_FLOPS_PER_REGION.values()) + VIT4K_FLOPS_PER_REGION
 KERNEL_BYTES_PER_LAUNCH = {            # HBM-bound row kernels: bytes that must move per launch

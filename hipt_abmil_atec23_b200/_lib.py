@@ -60,8 +60,9 @@ SIGNATURES = {
     "hb_vit_plan_destroy": (None, [C.c_void_p]),
     "hb_vit_plan_set_depth_limit": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_vit_plan_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
-    "hb_vit256_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_vit256_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                    C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "hb_vit4k_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_clam_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -247,21 +248,29 @@ def attention(qkv, n_seq, seq_len, heads, head_dim, scale):
 
 
 def image_layout(image):
-    """(patch_stride, chan_stride, row_pitch, grid_cols, n_patches) of a region [3,H,W] or a patch batch [B,3,256,256]."""
+    """(patch_stride, chan_stride, row_pitch, grid_cols, n_patches, patches_per_image, image_stride_bytes) of a region
+    [3,H,W], a batch of regions [R,3,H,W] (H, W multiples of 256) or a patch batch [B,3,256,256]."""
     assert image.dtype in (torch.uint8, torch.float32) and image.stride(-1) == 1
     if image.dim() == 3:
         assert image.shape[0] == 3 and image.shape[1] % 256 == 0 and image.shape[2] % 256 == 0
         gc = image.shape[2] // 256
-        return 0, image.stride(0), image.stride(1), gc, (image.shape[1] // 256) * gc
-    assert image.dim() == 4 and tuple(image.shape[1:]) == (3, 256, 256)
-    return image.stride(0), image.stride(1), image.stride(2), 0, image.shape[0]
+        ppi = (image.shape[1] // 256) * gc
+        return 0, image.stride(0), image.stride(1), gc, ppi, ppi, 0
+    assert image.dim() == 4 and image.shape[1] == 3
+    if tuple(image.shape[2:]) == (256, 256):
+        return image.stride(0), image.stride(1), image.stride(2), 0, image.shape[0], 1, 0
+    assert image.shape[2] % 256 == 0 and image.shape[3] % 256 == 0
+    gc = image.shape[3] // 256
+    ppi = (image.shape[2] // 256) * gc
+    return 0, image.stride(1), image.stride(2), gc, ppi * image.shape[0], ppi, image.stride(0) * image.element_size()
 
 
 def im2col_patches(image, patch_begin, n_patches):
     """image: region [3, H, W] or patch batch [B, 3, 256, 256]; uint8 or fp32; unit stride along the last dim."""
     require_cuda(image, "image")
     device_check()
-    ps, cs, rp, gc, _ = image_layout(image)
+    ps, cs, rp, gc, _, _, _ = image_layout(image)
+    assert image.dim() == 3 or gc == 0, "im2col_patches takes one region or a patch batch"
     a = torch.empty((n_patches * 256, 768), dtype=torch.bfloat16, device=image.device)
     check(load().hb_im2col_patches(ptr(image), int(image.dtype == torch.float32), ps, cs, rp, gc, patch_begin,
                                    n_patches, ptr(a), stream_ptr()))

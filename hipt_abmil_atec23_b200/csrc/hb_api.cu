@@ -435,7 +435,8 @@ static int clear_stats(hb_vit_plan* p, cudaStream_t st) {
 extern "C" {
 
 int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t patch_stride,
-                      size_t chan_stride, size_t row_pitch, int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
+                      size_t chan_stride, size_t row_pitch, int grid_cols, int patches_per_image, size_t image_stride_bytes,
+                      int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
                       const float* pos_table, float* cls_f32, void* cls_bf16, void* stream) {
     if (!plan || !image || !embed_w_bf16 || !embed_b || !pos_table) return set_error("hb_vit256_forward: null argument");
     const int seq_len = 257, T = 256;
@@ -447,8 +448,22 @@ int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, si
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = plan->cfg.dim;
     if (clear_stats(plan, st)) return -1;
+    if (grid_cols > 0 && patches_per_image <= 0) return set_error("hb_vit256_forward: patches_per_image must be positive");
     { ProfScope ps(HB_PROF_IM2COL, st);
-      if (im2col_launch(image, image_is_f32, patch_stride, chan_stride, row_pitch, grid_cols, patch_begin, n_patches, plan->hid, st)) return -1; }
+      if (grid_cols == 0) {
+          if (im2col_launch(image, image_is_f32, patch_stride, chan_stride, row_pitch, 0, patch_begin, n_patches, plan->hid, st)) return -1;
+      } else {
+          // one launch per region image touched by [patch_begin, patch_begin + n_patches)
+          for (int done = 0; done < n_patches;) {
+              const int p = patch_begin + done;
+              const int img = p / patches_per_image, local = p - img * patches_per_image;
+              const int cnt = (patches_per_image - local < n_patches - done) ? patches_per_image - local : n_patches - done;
+              const uint8_t* src = static_cast<const uint8_t*>(image) + static_cast<size_t>(img) * image_stride_bytes;
+              uint8_t* dst = static_cast<uint8_t*>(plan->hid) + static_cast<size_t>(done) * T * 768 * 2;
+              if (im2col_launch(src, image_is_f32, patch_stride, chan_stride, row_pitch, grid_cols, local, cnt, dst, st)) return -1;
+              done += cnt;
+          }
+      } }
     GemmAux aux = {};
     aux.stats_out = plan->stats1;
     GemmArgs g;

@@ -18,7 +18,7 @@ _lock = threading.Lock()
 import os
 
 # default capacities (token sequences per launch)
-VIT256_MAX_PATCHES = int(os.environ.get("HB_VIT256_MAX_PATCHES", "256"))   # 256 = one 4096x4096 region per launch
+VIT256_MAX_PATCHES = int(os.environ.get("HB_VIT256_MAX_PATCHES", "512"))   # 512 = two 4096x4096 regions per launch (514 CTA-pair tiles over 74 SM pairs)
 VIT4K_MAX_REGIONS = 64
 
 
@@ -157,11 +157,11 @@ class VitEngine:
 
     # ------------------------------------------------------------------------------------------------ forwards
     def forward_patches(self, image, patch_begin=0, n_patches=None, mean=None, std=None, want_f32=True, out_bf16=None):
-        """ViT-256 over patches of `image` (region [3,H,W] or batch [B,3,256,256]; fp32 normalised, or uint8 with
-        mean/std).  Returns (cls_f32 [n, dim] or None, cls_bf16 [n, dim])."""
+        """ViT-256 over patches of `image` (region [3,H,W], region batch [R,3,H,W] or patch batch [B,3,256,256]; fp32
+        normalised, or uint8 with mean/std).  Returns (cls_f32 [n, dim] or None, cls_bf16 [n, dim])."""
         assert self.kind == "vit256"
         _lib.require_cuda(image, "image")
-        ps, cs, rp, gc, total = _lib.image_layout(image)
+        ps, cs, rp, gc, total, ppi, istride = _lib.image_layout(image)
         n = total - patch_begin if n_patches is None else n_patches
         is_f32 = image.dtype == torch.float32
         if not is_f32 and mean is None:
@@ -176,7 +176,7 @@ class VitEngine:
             while done < n:                         # minibatches of the plan capacity (hipt_4k.py:68-70)
                 cur = min(self.max_seqs, n - done)
                 _lib.check(self.lib.hb_vit256_forward(
-                    self.plan, _lib.ptr(image), int(is_f32), ps, cs, rp, gc, patch_begin + done, cur, _lib.ptr(ew),
+                    self.plan, _lib.ptr(image), int(is_f32), ps, cs, rp, gc, ppi, istride, patch_begin + done, cur, _lib.ptr(ew),
                     _lib.ptr(eb), _lib.ptr(pos), _lib.ptr(cls_f32[done:] if cls_f32 is not None else None),
                     _lib.ptr(cls_bf16[done:]), _lib.stream_ptr()))
                 done += cur

@@ -109,8 +109,8 @@ class HIPT_4K(nn.Module):
         dev = regions_u8.device
         eng = self.model256._engine(dev)
         cls_bf16 = torch.empty((R * T, eng.dim), dtype=torch.bfloat16, device=dev)
-        for r in range(R):
-            eng.forward_patches(regions_u8[r], mean=mean, std=std, want_f32=False, out_bf16=cls_bf16[r * T:(r + 1) * T])
+        # the whole batch in one call: the engine walks it in launches of its capacity (two 4096x4096 regions each)
+        eng.forward_patches(regions_u8, mean=mean, std=std, want_f32=False, out_bf16=cls_bf16)
         if torch.device(self.device4k) != cls_bf16.device:
             cls_bf16 = cls_bf16.to(self.device4k, non_blocking=True)
         out = self.model4k._engine(cls_bf16.device).forward_grid(cls_bf16, R, w_256, h_256)

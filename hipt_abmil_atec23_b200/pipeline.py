@@ -2,8 +2,9 @@
 
 This is the call a user of the accelerated path makes for one slide (the reference spreads it over three scripts and
 the file system: extract_features_fp.py:159-171 -> .h5/.pt -> eval.py / create_heatmaps.py:34-57).  `run_device` takes
-regions already resident in HBM; `run_host` takes pinned host memory and overlaps the host->device copy of region r+1
-with the ViT-256 pass of region r on a second stream (two staging buffers).
+regions already resident in HBM; `run_host` takes pinned host memory and overlaps the host->device copy of the next group of regions
+(one ViT-256 launch = two 4096 x 4096 regions) with the ViT-256 pass of the current one on a second stream (two staging
+buffers).
 """
 import torch
 
@@ -44,26 +45,29 @@ class SlidePipeline:
         dev = self.device
         T = (W // 256) * (H // 256)
         with torch.cuda.device(dev):
-            if self._stage is None or self._stage.shape[1:] != regions_u8_pinned.shape[1:]:
-                self._stage = torch.empty((2,) + tuple(regions_u8_pinned.shape[1:]), dtype=torch.uint8, device=dev)
+            eng = self.hipt.model256._engine(dev)
+            k = max(1, eng.max_seqs // T)                       # regions per ViT-256 launch (two 4096x4096 regions)
+            shape = (2, k) + tuple(regions_u8_pinned.shape[1:])
+            if self._stage is None or tuple(self._stage.shape) != shape:
+                self._stage = torch.empty(shape, dtype=torch.uint8, device=dev)
                 self._copy_stream = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream(dev)
-            eng = self.hipt.model256._engine(dev)
             cls_bf16 = torch.empty((R * T, eng.dim), dtype=torch.bfloat16, device=dev)
             copied = [torch.cuda.Event() for _ in range(2)]
             consumed = [torch.cuda.Event() for _ in range(2)]
-            for r in range(R):
-                b = r & 1
+            for g, r0 in enumerate(range(0, R, k)):
+                b = g & 1
+                n = min(k, R - r0)
                 with torch.cuda.stream(self._copy_stream):
-                    if r >= 2:
+                    if g >= 2:
                         self._copy_stream.wait_event(consumed[b])
                     else:
                         self._copy_stream.wait_stream(main)
-                    self._stage[b].copy_(regions_u8_pinned[r], non_blocking=True)
+                    self._stage[b, :n].copy_(regions_u8_pinned[r0:r0 + n], non_blocking=True)
                     copied[b].record(self._copy_stream)
                 main.wait_event(copied[b])
-                eng.forward_patches(self._stage[b], mean=self.mean, std=self.std, want_f32=False,
-                                    out_bf16=cls_bf16[r * T:(r + 1) * T])
+                eng.forward_patches(self._stage[b, :n], mean=self.mean, std=self.std, want_f32=False,
+                                    out_bf16=cls_bf16[r0 * T:(r0 + n) * T])
                 consumed[b].record(main)
             feats = self.hipt.model4k._engine(dev).forward_grid(cls_bf16, R, W // 256, H // 256)
             out = self._pool(feats)

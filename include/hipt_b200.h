@@ -156,12 +156,17 @@ void hb_vit_plan_destroy(hb_vit_plan* plan);
 int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit);
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes);
 
-/* ViT-256 over n_patches 256x256 patches of one region image (HIPT_4K.forward steps 2-3, hipt_4k.py:64-70).
+/* ViT-256 over n_patches 256x256 patches of one or more region images (HIPT_4K.forward steps 2-3, hipt_4k.py:64-70).
+ * grid_cols > 0: the input is n_images-many region images, image_stride BYTES apart, each a grid of
+ * patches_per_image = grid_rows * grid_cols tiles; global patch p is tile (p % patches_per_image) of image
+ * (p / patches_per_image).  grid_cols == 0: patch p is a separate 256x256 image at image + p * patch_stride elements.
+ * Batching two 4096x4096 regions (512 patches, 131,584 token rows = 514 CTA-pair tiles) per call fills the 148 SMs evenly.
  * embed_w_bf16 [dim, 768] / embed_b f32 [dim]: patch_embed.proj with any input normalisation folded in by the caller;
  * pos_table f32 [257, dim]: cls+pos rows after interpolate_pos_encoding (vision_transformer.py:213-233).
  * Outputs the final-LayerNorm CLS rows: cls_f32 [n_patches, dim] and/or cls_bf16 (either may be NULL). */
 int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, size_t patch_stride,
-                      size_t chan_stride, size_t row_pitch, int grid_cols, int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
+                      size_t chan_stride, size_t row_pitch, int grid_cols, int patches_per_image, size_t image_stride_bytes,
+                      int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
                       const float* pos_table, float* cls_f32, void* cls_bf16, void* stream);
 
 /* ViT-4K over n_regions grids of tokens_per_region ViT-256 CLS tokens (hipt_4k.py:72-75; the reshape/transpose at :73
