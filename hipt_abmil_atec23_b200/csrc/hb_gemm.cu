@@ -55,7 +55,7 @@ enum : int { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_BIAS_RESADD_F32 = 2,
               EPI_BIAS_GELU_FAST_BF16 = 5, EPI_LNFOLD_BF16 = 6, EPI_LNFOLD_GELU_BF16 = 7, EPI_RESID_STATS_F32 = 8,
               EPI_LNFOLD_GELU2_BF16 = 9, EPI_RESID_BF16 = 10 };
 
-template <int BN, int CG, int EPI>
+template <int BN, int CG, int EPI, int AST = 0>
 struct GemmCfg {
     static constexpr bool RESID = (EPI == EPI_RESID_STATS_F32);
     static constexpr bool RESB = (EPI == EPI_RESID_BF16);
@@ -70,22 +70,26 @@ struct GemmCfg {
                                            : (TOKENS ? 0 : GEMM_EPI_WGS * STAGE_BYTES_OUT);
     static constexpr int VEC_BYTES = (RESID || TOKENS || EPI == EPI_BIAS_RESADD_F32) ? GEMM_EPI_WGS * 128 * 4 : 16 * 256 * 4;                                        // bias / c slices per warp(group)
     static constexpr int STAT_BYTES = (RESID || TOKENS) ? 2 * GEMM_EPI_WGS * 128 * 8 : 0; // row-stat exchange
-    static constexpr int TAIL_BYTES = VEC_BYTES + STAT_BYTES + 512 /* barriers */;
-    static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - OUT_BYTES - TAIL_BYTES;
-    static constexpr int STAGES_FIT = RING_BUDGET / (A_BYTES + B_BYTES);
+    static constexpr int TAIL_BYTES = VEC_BYTES + STAT_BYTES + 640 /* barriers */;
+    // AST (A-stationary, K = 384): the whole [128 x 384] A tile stays resident for a group of n-tiles, only W is streamed
+    static constexpr int A_RES = AST ? 6 * A_BYTES : 0;
+    static constexpr int STAGE_BYTES = AST ? B_BYTES : (A_BYTES + B_BYTES);
+    static constexpr int RING_BUDGET = SMEM_LIMIT - 1024 - OUT_BYTES - TAIL_BYTES - A_RES;
+    static constexpr int STAGES_FIT = RING_BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + TAIL_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + A_RES + STAGES * STAGE_BYTES + OUT_BYTES + TAIL_BYTES;
     static_assert(STAGES >= 2, "operand ring too shallow");
 };
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int AST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_xb,
                  const float* __restrict__ bias, const float* __restrict__ tok_table, float* __restrict__ tok_out,
-                 const GemmAux aux, int M, int N, int K, int tokens_per_seq) {
-    using Cfg = GemmCfg<BN, CG, EPI>;
+                 const GemmAux aux, int M, int N, int K, int tokens_per_seq, int n_group) {
+    using Cfg = GemmCfg<BN, CG, EPI, AST>;
+    static_assert(!AST || CG == 2, "the A-stationary variant runs as CTA pairs");
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool RESB = Cfg::RESB;                    // bf16 residual stream: x = bf16(x + acc + bias), row statistics
     constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_FAST_BF16 ||
@@ -102,8 +106,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint8_t* smem_a = smem;                                   // AST: resident [6 k-blocks][128 x 128 B]; else the A ring
+    uint8_t* smem_b = smem + (AST ? Cfg::A_RES : STAGES * Cfg::A_BYTES);
     uint8_t* smem_o = smem_b + STAGES * Cfg::B_BYTES;
     float* vec_x = reinterpret_cast<float*>(smem_o + Cfg::OUT_BYTES);                 // [NWG][128]
     float* stat_x = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(vec_x) + Cfg::VEC_BYTES);   // [2][NWG][128][2]
@@ -115,7 +119,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* ring_full = bars + 2 * STAGES + 4;             // [RESID_RING] residual tile landed (RESID only)
     uint64_t* ring_empty = ring_full + RESID_RING;           // [RESID_RING] its updated copy has been stored
     uint64_t* res_full = ring_empty + RESID_RING;            // [16] per epilogue warp: bf16 residual chunk landed (RESB)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
+    uint64_t* a_full = res_full + 16;                        // [6] AST: resident A k-block landed (leader collects both CTAs)
+    uint64_t* a_empty = a_full + 6;                          // [6] AST: the last n-tile of the group is done with it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -137,6 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], OUT_BF16 ? CG * 8 : CG * NWG * GEMM_EPI_THREADS); }
         for (int i = 0; i < RESID_RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
         for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
+        for (int i = 0; i < 6; ++i) { mbar_init(&a_full[i], CG); mbar_init(&a_empty[i], 1); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -152,10 +159,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int m_tiles = (M + TILE_M - 1) / TILE_M;
     const int total_tiles = m_tiles * n_tiles;
     const int k_blocks = K / GEMM_BK;
+    // Tile sequence of this CTA (pair): local tile `it` = (unit ui = it / NG, t = it % NG); unit = tile0 + ui * tile_step
+    // covers the n-tiles [g * NG, g * NG + NG) of one m-tile.  NG = 1 (groups = n_tiles) is the plain tile-strided order.
+    const int NG = AST ? n_group : 1;
+    const int groups = n_tiles / NG;
+    const int total_units = m_tiles * groups;
+    auto tile_at = [&](uint32_t it_, int& m_idx_, int& n_idx_) -> bool {
+        const uint32_t ui = it_ / NG, t = it_ - ui * NG;
+        const int unit = tile0 + static_cast<int>(ui) * tile_step;
+        if (unit >= total_units) return false;
+        m_idx_ = unit / groups;
+        n_idx_ = (unit - m_idx_ * groups) * NG + static_cast<int>(t);
+        return true;
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (AST && lane == 0) {
+            // A-stationary: this thread streams W only; the A tiles are loaded by warp 2
+            const uint64_t pol_w = policy_evict_last();
+            uint32_t stage = 0, phase = 0;
+            int m_idx, n_idx;
+            for (uint32_t it = 0; tile_at(it, m_idx, n_idx); ++it) {
+                const int n0 = n_idx * BN + cta_rank * Cfg::B_ROWS;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    tma_load_2d_2sm_hint(smem_b + stage * Cfg::B_BYTES, &map_w, &full_bar[stage], kb * GEMM_BK, n0, pol_w);
+                    if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
+                    else mbar_arrive_remote(&full_bar[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (lane == 0) {
             const uint64_t pol_w = policy_evict_last();
             uint32_t stage = 0, phase = 0;
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
@@ -197,7 +232,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ------------------------------------------------------------------ MMA issuer
         // The whole warp walks the pipeline (warp-uniform control flow and operands, so the descriptors live in
         // uniform registers); one elected lane issues the tcgen05.mma / commit instructions.
-        if (cta_rank == 0) {
+        if (AST && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+            uint32_t stage = 0, phase = 0;
+            int m_idx, n_idx;
+            for (uint32_t it = 0; tile_at(it, m_idx, n_idx); ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                const uint32_t ui = it / NG, t = it - ui * NG;
+                mbar_wait(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < 6; ++kb) {
+                    if (t == 0) mbar_wait(&a_full[kb], ui & 1);          // first n-tile of the group: A k-block landed
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k128(a_base + kb * Cfg::A_BYTES);
+                    const uint64_t db = umma_desc_k128(b_base + stage * Cfg::B_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k)
+                            umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (t == static_cast<uint32_t>(NG) - 1) umma_commit_2sm(&a_empty[kb]);   // group done with this A k-block
+                        if (kb == 5) umma_commit_2sm(&acc_full[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
             const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
             uint32_t stage = 0, phase = 0;
@@ -233,6 +297,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (lane == 0 && kb == 0) TRACE(0, it, 2);
                     if (lane == 0 && kb == k_blocks - 1) TRACE(0, it, 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ A-tile loader (A-stationary variant only)
+        // One [128 x 384] A tile per unit, k-block by k-block as the previous group's last n-tile releases them, so the
+        // reload overlaps that tile's remaining MMAs.
+        if constexpr (AST) {
+            if (lane == 0) {
+                for (uint32_t ui = 0;; ++ui) {
+                    const int unit = tile0 + static_cast<int>(ui) * tile_step;
+                    if (unit >= total_units) break;
+                    const int m0 = (unit / groups) * TILE_M + cta_rank * GEMM_BM;
+                    for (int kb = 0; kb < 6; ++kb) {
+                        mbar_wait(&a_empty[kb], (ui & 1) ^ 1);
+                        tma_load_2d_2sm(smem_a + kb * Cfg::A_BYTES, &map_a, &a_full[kb], kb * GEMM_BK, m0);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * Cfg::A_BYTES);
+                        else mbar_arrive_remote(&a_full[kb], 0);
+                    }
                 }
             }
         }
@@ -272,10 +355,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint8_t* stage_buf = smem_o + (warp - 4) * 4096;          // [32 rows][128 B], SWIZZLE_128B
             const uint32_t row_addr = smem_u32(stage_buf) + lane * 128;
             float* wvec = vec_x + (warp - 4) * 256;                   // [2 chunks][bias 64 | c 64]
-            const int step2 = 2 * tile_step;
-            const int step_m = step2 / n_tiles, step_n = step2 % n_tiles;
-            const int tile_first = tile0 + par * tile_step;
-            int m_idx = tile_first / n_tiles, n_idx = tile_first % n_tiles;
+            int m_idx = 0, n_idx = 0;
+            bool have_tile = tile_at(par, m_idx, n_idx);                 // this warp's tiles: it = par, par + 2, ...
             float pf_v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             float2 pf_sq = make_float2(0.f, 0.f);
             auto pf_load = [&](int mi, int ni, uint32_t kk) {          // side inputs of a tile, fetched one tile ahead
@@ -309,10 +390,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             };
-            if (tile_first < total_tiles) pf_load(m_idx, n_idx, 0);
+            if (have_tile) pf_load(m_idx, n_idx, 0);
             [[maybe_unused]] uint32_t res_use = 0;                     // RESB: residual chunks received so far
-            uint32_t k = 0;
-            for (int tile = tile_first; tile < total_tiles; tile += step2, ++k) {
+            for (uint32_t k = 0; have_tile; ++k) {
                 const int m0 = m_idx * TILE_M + cta_rank * GEMM_BM + ew * 32;
                 const int n0 = n_idx * BN;
                 const uint32_t as = par, aphase = k & 1;
@@ -331,9 +411,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     rstd = rsqrtf(var + aux.eps);
                     nrm = -rstd * mu;
                 }
-                n_idx += step_n; m_idx += step_m;
-                if (n_idx >= n_tiles) { n_idx -= n_tiles; ++m_idx; }
-                if (tile + step2 < total_tiles) pf_load(m_idx, n_idx, k + 1);
+                have_tile = tile_at(par + 2 * (k + 1), m_idx, n_idx);   // next tile of this warp (m_idx / n_idx now refer to it)
+                if (have_tile) pf_load(m_idx, n_idx, k + 1);
                 [[maybe_unused]] const f32x2_t rstd2 = f2_pack(rstd, rstd), nrm2 = f2_pack(nrm, nrm);
                 if constexpr (RESB) {
                     // residual chunk of the tile's first column chunk, fetched while the MMAs are still running (the
@@ -681,18 +760,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int AST>
 static int launch_gemm_cg(const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, CG, EPI>;
-    auto kern = gemm_bf16_kernel<BN, EPI, CG>;
+    using Cfg = GemmCfg<BN, CG, EPI, AST>;
+    auto kern = gemm_bf16_kernel<BN, EPI, CG, AST>;
     static bool attr_done = false;     // per instantiation
     if (!attr_done) {
         HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_done = true;
     }
     const int m_tiles = (g.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
-    const int total = m_tiles * (g.N / BN);
+    const int n_tiles = g.N / BN;
     const int slots = num_sms() / CG;
+    // A-stationary grouping: all n-tiles of an m-tile share one A load when there are enough m-tiles to fill the SM pairs
+    // evenly; otherwise half of them (twice the units, half the reuse)
+    int n_group = 1;
+    if (AST) {
+        n_group = n_tiles;
+        const int waves_full = (m_tiles + slots - 1) / slots;
+        if (n_tiles % 2 == 0 && (m_tiles < slots || static_cast<double>(m_tiles) / slots < 0.9 * waves_full)) n_group = n_tiles / 2;
+    }
+    const int total = AST ? m_tiles * (n_tiles / n_group) : m_tiles * n_tiles;
     const int grid = (total < slots ? total : slots) * CG;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -705,15 +793,18 @@ static int launch_gemm_cg(const GemmArgs& g, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = (CG == 2) ? 1 : 0;
     HB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.map_a, CG == 2 ? g.map_w2 : g.map_w, g.map_out, g.map_xb, g.bias,
-                                  g.tok_table, g.tok_out, g.aux, g.M, g.N, g.K, g.tokens_per_seq));
+                                  g.tok_table, g.tok_out, g.aux, g.M, g.N, g.K, g.tokens_per_seq, n_group));
     count_launch();
     return 0;
 }
 
 template <int BN, int EPI>
 static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
-    if (g.cg2) return launch_gemm_cg<BN, EPI, 2>(g, stream);
-    return launch_gemm_cg<BN, EPI, 1>(g, stream);
+    if constexpr ((EPI == EPI_LNFOLD_BF16 || EPI == EPI_RESID_BF16) && BN != 256) {
+        if (g.cg2 && g.astat) return launch_gemm_cg<BN, EPI, 2, 1>(g, stream);
+    }
+    if (g.cg2) return launch_gemm_cg<BN, EPI, 2, 0>(g, stream);
+    return launch_gemm_cg<BN, EPI, 1, 0>(g, stream);
 }
 
 template <int BN>
@@ -770,6 +861,11 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     if (encode_tmap_2d(&g.map_w, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn, GEMM_BK)) return -1;
     if (encode_tmap_2d(&g.map_w2, TMAP_BF16, W, N, K, static_cast<uint64_t>(K) * 2, bn / 2, GEMM_BK)) return -1;
     g.cg2 = (M > GEMM_BM) && gemm_use_cta_pairs();
+    {   // A-stationary variant for the K = 384 GEMMs of the block pipeline (HB_GEMM_ASTAT=0 disables it)
+        static int use_astat = -1;
+        if (use_astat < 0) { const char* e = getenv("HB_GEMM_ASTAT"); use_astat = (e && e[0] == '0') ? 0 : 1; }
+        g.astat = (use_astat && g.cg2 && K == 384 && bn != 256 && (epi == EPI_LNFOLD_BF16 || epi == EPI_RESID_BF16)) ? 1 : 0;
+    }
     g.map_xb = g.map_a;                                       // placeholder unless the epilogue uses it
     const bool lnfold = (epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16 || epi == EPI_LNFOLD_GELU2_BF16);
     const bool out_bf16 = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16 || lnfold ||

@@ -46,6 +46,7 @@ struct GemmArgs {
     CUtensorMap map_a, map_w, map_w2, map_out, map_xb;   // map_w2: W with a half-height box for the CTA-pair kernel
     GemmAux aux;
     int cg2;                                     // 1: launch as clusters of 2 CTAs (tcgen05 cta_group::2)
+    int astat;                                   // 1: A-stationary variant (K = 384): the A tile is loaded once per group of n-tiles
     const float* bias;
     const float* tok_table;
     float* tok_out;
