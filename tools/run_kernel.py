@@ -6,13 +6,14 @@ from hipt_abmil_atec23_b200 import _lib as L
 
 which = sys.argv[1] if len(sys.argv) > 1 else "attention"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-M = 256 * 257
+NSEQ = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+M = NSEQ * 257
 g = torch.Generator().manual_seed(0)
 def r(shape, s=1.0): return (torch.randn(shape, generator=g) * s).cuda()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if which == "attention":
     qkv = r((M, 1152)).bfloat16()
-    f = lambda: L.attention(qkv, 256, 257, 6, 64, 0.125)
+    f = lambda: L.attention(qkv, NSEQ, 257, 6, 64, 0.125)
 elif which.startswith("gemm_"):
     N, K, epi = {"gemm_qkv": (1152, 384, 0), "gemm_fc1": (1536, 384, 5), "gemm_fc2": (384, 1536, 2), "gemm_proj": (384, 384, 2)}[which]
     a = r((M, K)).bfloat16(); w = r((N, K), 0.05).bfloat16(); b = r((N,), 0.1)
