@@ -8,7 +8,13 @@
 //   logits = classifiers(M); Y_prob = softmax; Y_hat = top1  :181-183
 // Dropout layers are identities at inference (model.eval()).
 //
-// Kernel 1 (scores): one CTA per 128-instance chunk of one bag, one instance per thread.  The feature tile is staged
+// Kernel 1, HIPT sizes (192-d features, L1 <= 128: clam_scores192_kernel): one CTA per 64-instance chunk of one bag.
+// The [64 x 192] fp32 feature tile is read from HBM ONCE (coalesced 128-bit loads) into shared memory and reused by
+// every weight set ("fold"); the first Linear runs as a register-tiled SGEMM on packed f32x2 FMAs (thread tile = 2
+// instances x 4 or 8 output columns, W1 staged k-major 64 rows at a time); the gate reads h1 rows as float4 and the
+// gate weights as shared-memory broadcasts, two threads per instance; chunk-local softmax partials (max, sum exp,
+// sum exp * h1) use warp-shuffle reductions.  Algorithmic HBM bytes: 772 per instance.
+// Kernel 1, any other size (clam_scores_kernel): one CTA per 128-instance chunk, one instance per thread.  The feature tile is staged
 // through shared memory with coalesced 128-bit loads (row stride padded to 65 words: conflict-free per-thread rows),
 // the first Linear is computed 16 output columns at a time against a k-major weight tile read as broadcast float4,
 // h1 stays in shared memory for the gate and for the chunk-local softmax partial (max, sum exp, sum exp*h1).
@@ -23,8 +29,17 @@
 
 namespace hb {
 
-constexpr int CLAM_CHUNK = 128;     // instances per CTA (32 when L1 > 256 so that h1 still fits in shared memory)
-__host__ __device__ inline int clam_chunk_for(int L1) { return L1 <= 256 ? CLAM_CHUNK : 32; }
+constexpr int CLAM_CHUNK = 128;     // generic kernel: instances per CTA (32 when L1 > 256 so that h1 still fits in shared memory)
+constexpr int CL_CH = 64;           // 192-d kernel: instances per CTA
+constexpr int CL_THREADS = 128;     // 256 when L1 >= 64 (one CTA per SM then: more warps to hide latency)
+constexpr int CL_XS = 196;          // feature row stride in floats: 16 B aligned and conflict-free for 8-lane float4 wavefronts
+__host__ __device__ inline int clam_kc_for(int L1) { return L1 <= 32 ? 192 : 64; }   // rows of W1^T staged per step
+__host__ __device__ inline bool clam_is192(int L0, int L1, int D) {
+    return L0 == 192 && L1 <= 128 && (L1 % 8) == 0 && (D % 4) == 0;
+}
+__host__ __device__ inline int clam_chunk_for(int L0, int L1, int D) {
+    return clam_is192(L0, L1, D) ? CL_CH : (L1 <= 256 ? CLAM_CHUNK : 32);
+}
 constexpr int CLAM_KC = 64;         // feature columns staged per step
 constexpr int CLAM_OB = 16;         // first-layer output columns per pass
 constexpr int CLAM_MAX_MODELS = 8;
@@ -55,11 +70,53 @@ __device__ __forceinline__ float block_reduce_sum_128(float v, float* red) {
     return v;
 }
 
+// Work table: ragged bags -> flat list of (bag, chunk) items so that the score kernels launch exactly the CTAs that have
+// work (a 2-D grid of n_bags x max_chunks is mostly empty CTAs when bag sizes span 50..20,000).  prefix[b] = number of
+// chunks before bag b; work[w] = bag << 12-free pair stored as two ints.  One CTA, block-wide scan over the bags.
+__global__ void __launch_bounds__(1024) clam_work_table_kernel(const int32_t* __restrict__ bag_offsets, int n_bags, int CH,
+                                                               int32_t* __restrict__ prefix, int32_t* __restrict__ work,
+                                                               int work_cap) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_bags; b0 += 1024) {
+        const int b = b0 + tid;
+        const int len = (b < n_bags) ? bag_offsets[b + 1] - bag_offsets[b] : 0;
+        const int cnt = (len + CH - 1) / CH;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + inc - cnt;
+        if (b < n_bags) {
+            prefix[b] = excl;
+            for (int c = 0; c < cnt; ++c)
+                if (excl + c < work_cap) { work[2 * (excl + c)] = b; work[2 * (excl + c) + 1] = c; }
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) prefix[n_bags] = carry_s;
+}
+
 __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __restrict__ feats,
                                                                   const int32_t* __restrict__ bag_offsets,
                                                                   const __grid_constant__ ClamModels models,
                                                                   int n_models, int n_bags, int total_instances, int L0,
-                                                                  int L1, int D, int max_chunks,
+                                                                  int L1, int D, const int32_t* __restrict__ prefix,
+                                                                  const int32_t* __restrict__ work, int work_cap,
                                                                   float* __restrict__ a_raw, float* __restrict__ partials) {
     extern __shared__ __align__(16) float smem_clam[];
     const int CH = blockDim.x;                               // instances per CTA (128 or 32)
@@ -70,11 +127,13 @@ __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __
     float* sH = red + 4;                                     // [CH][L1+1]
     const int ldh = L1 + 1;
 
-    const int bag = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int wi = blockIdx.x;
+    if (wi >= prefix[n_bags]) return;
+    const int bag = work[2 * wi], chunk = work[2 * wi + 1];
     const int start = bag_offsets[bag];
     const int len = bag_offsets[bag + 1] - start;
     const int i0 = chunk * CH;
-    if (i0 >= len) return;
     const int n_valid = min(CH, len - i0);
     const bool valid = tid < n_valid;
     const float* xbase = feats + static_cast<size_t>(start + i0) * L0;
@@ -153,7 +212,7 @@ __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __
         const float e = valid ? expf(A - mx) : 0.f;
         sE[tid] = e;
         const float sum = block_reduce_sum_128(e, red);     // contains the __syncthreads that publishes sE
-        float* out = partials + (static_cast<size_t>(mi * n_bags + bag) * max_chunks + chunk) * (L1 + 2);
+        float* out = partials + (static_cast<size_t>(mi) * work_cap + wi) * (L1 + 2);
         if (tid == 0) { out[0] = mx; out[1] = sum; }
         for (int j = tid; j < L1; j += CH) {
             float acc = 0.f;
@@ -164,35 +223,249 @@ __global__ void __launch_bounds__(CLAM_CHUNK) clam_scores_kernel(const float* __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 192-d kernel
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lds_2f2(uint32_t addr, f32x2_t& a, f32x2_t& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+// h1 tile.  FMAs are packed along K: acc (lo, hi) += (x[k], x[k+1]) * (w[k], w[k+1]), so both operands are natural
+// 64-bit pairs of a float4 load (x row of the instance, W1 row of the output column in nn.Linear's own [L1][192]
+// layout) and no value is ever duplicated into a pair; h1 = relu(lo + hi + bias).  Thread tile = 2 instances (lane,
+// lane + 32) x TN columns; warp w owns column groups w, w + nw, ...; W1 reads are warp-uniform broadcasts.
+template <int TN>
+__device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const float* b1, int L1,
+                                             const float* sX, float* sW, float* sH, int ldh) {
+    constexpr int GPW = (TN == 8) ? 2 : 1;                   // column groups per warp: L1 <= 16 (TN 4, 4 warps), L1 = 32 (TN 8,
+                                                             // 4 warps), L1 = 64 / 128 (TN 8, 8 warps)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = blockDim.x, nw = nthreads >> 5;
+    const int n_groups = L1 / TN;
+    const int KC = clam_kc_for(L1), ldw = KC + 4;
+    f32x2_t acc[GPW][2][TN];
+#pragma unroll
+    for (int g = 0; g < GPW; ++g)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < TN; ++c) acc[g][i][c] = f2_pack(0.f, 0.f);
+    const uint32_t x0_addr = smem_u32(sX + lane * CL_XS), x1_addr = smem_u32(sX + (lane + 32) * CL_XS);
+    for (int kc = 0; kc < 192; kc += KC) {
+        // stage W1[:, kc:kc+KC] as sW[col][k] (row stride KC + 4): straight 16-byte copies
+        {
+            const int per_row = KC / 4;
+            const uint32_t dst0 = smem_u32(sW);
+            for (int idx = tid; idx < L1 * per_row; idx += nthreads) {
+                const int col = idx / per_row, c4 = idx - col * per_row;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + (col * ldw + c4 * 4) * 4),
+                             "l"(W1 + static_cast<size_t>(col) * 192 + kc + c4 * 4) : "memory");
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < GPW; ++g) {
+            const int grp = warp + nw * g;
+            if (grp < n_groups) {
+                const uint32_t w_addr = smem_u32(sW + grp * TN * ldw);
+#pragma unroll 2
+                for (int k4 = 0; k4 < KC / 4; ++k4) {
+                    f32x2_t xa0, xa1, xb0, xb1;
+                    lds_2f2(x0_addr + (kc + 4 * k4) * 4, xa0, xa1);
+                    lds_2f2(x1_addr + (kc + 4 * k4) * 4, xb0, xb1);
+#pragma unroll
+                    for (int c = 0; c < TN; ++c) {
+                        f32x2_t w0, w1;
+                        lds_2f2(w_addr + (c * ldw + 4 * k4) * 4, w0, w1);
+                        acc[g][0][c] = f2_fma(xa0, w0, acc[g][0][c]);
+                        acc[g][1][c] = f2_fma(xb0, w0, acc[g][1][c]);
+                        acc[g][0][c] = f2_fma(xa1, w1, acc[g][0][c]);
+                        acc[g][1][c] = f2_fma(xb1, w1, acc[g][1][c]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int g = 0; g < GPW; ++g) {
+        const int grp = warp + nw * g;
+        if (grp < n_groups) {
+#pragma unroll
+            for (int c = 0; c < TN; ++c) {
+                const int col = grp * TN + c;
+                const float bias = b1[col];                  // shared memory (staged with the fold's other small vectors)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float v0, v1;
+                    f2_unpack(acc[g][i][c], v0, v1);
+                    sH[(lane + 32 * i) * ldh + col] = fmaxf(v0 + v1 + bias, 0.f);
+                }
+            }
+        }
+    }
+}
+
+template <int TN>
+__global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __restrict__ feats,
+                                                                     const int32_t* __restrict__ bag_offsets,
+                                                                     const __grid_constant__ ClamModels models,
+                                                                     int n_models, int n_bags, int total_instances, int L1,
+                                                                     int D, const int32_t* __restrict__ prefix,
+                                                                     const int32_t* __restrict__ work, int work_cap,
+                                                                     float* __restrict__ a_raw, float* __restrict__ partials) {
+    extern __shared__ __align__(16) float smem_clam[];
+    const int ldh = L1 + 4;
+    float* sX = smem_clam;                                   // [64][196]
+    float* sW = sX + CL_CH * CL_XS;                          // [L1][KC + 4]  W1 slice
+    float* sH = sW + (clam_kc_for(L1) + 4) * L1;             // [64][L1 + 4]
+    float* sG = sH + CL_CH * ldh;                            // [2][D][L1]    Wa, Wb
+    float* sA = sG + 2 * D * L1;                             // [4][64]       per-part score partials
+    float* sE = sA + 4 * CL_CH;                              // [64]
+    float* red = sE + CL_CH;                                 // [8]
+    float* sV = red + 8;                                     // b1 [L1] | ba [D] | bb [D] | Wc [D] | bc [1]
+    const int nthreads = blockDim.x;
+
+    const int tid = threadIdx.x;
+    const int wi = blockIdx.x;
+    if (wi >= prefix[n_bags]) return;
+    const int bag = work[2 * wi], chunk = work[2 * wi + 1];
+    const int start = bag_offsets[bag];
+    const int len = bag_offsets[bag + 1] - start;
+    const int i0 = chunk * CL_CH;
+    const int n_valid = min(CL_CH, len - i0);
+
+    // ---- the feature tile: HBM -> shared memory, once
+    {                                                        // cp.async: every 16-byte piece in flight at once, no registers
+        const float4* src = reinterpret_cast<const float4*>(feats + static_cast<size_t>(start + i0) * 192);
+        const uint32_t dst0 = smem_u32(sX);
+        for (int idx = tid; idx < CL_CH * 48; idx += nthreads) {
+            const int r = idx / 48, c4 = idx - r * 48;
+            const uint32_t dst = dst0 + (r * CL_XS + c4 * 4) * 4;
+            const int nbytes = (r < n_valid) ? 16 : 0;       // rows past the bag end are zero-filled
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + (r < n_valid ? idx : 0)), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int parts = nthreads >> 6;                         // gate: `parts` threads per instance, each D / parts units
+    const int inst = tid & 63, half = tid >> 6;
+    const bool valid = half == 0 && inst < n_valid;
+    for (int mi = 0; mi < n_models; ++mi) {
+        const ClamModel& w = models.m[mi];
+        // gate weights and every small vector of this fold: issued before the first Linear so that their latency hides
+        // under it (the staging of W1 inside clam_fc1_192 waits on the same cp.async group)
+        for (int idx = tid; idx < D * L1 / 4; idx += nthreads) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG + idx * 4)), "l"(w.p[2] + idx * 4) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG + D * L1 + idx * 4)), "l"(w.p[4] + idx * 4) : "memory");
+        }
+        for (int idx = tid; idx < L1 + 3 * D + 1; idx += nthreads) {
+            const float* src = idx < L1 ? w.p[1] + idx : idx < L1 + D ? w.p[3] + (idx - L1) : idx < L1 + 2 * D ? w.p[5] + (idx - L1 - D)
+                             : idx < L1 + 3 * D ? w.p[6] + (idx - L1 - 2 * D) : w.p[7];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sV + idx)), "l"(src) : "memory");
+        }
+        clam_fc1_192<TN>(w.p[0], sV, L1, sX, sW, sH, ldh);
+        __syncthreads();
+
+        // ---- gated attention score
+        {
+            const float* ba = sV + L1; const float* bb = ba + D; const float* Wc = bb + D;
+            const uint32_t h_addr = smem_u32(sH + inst * ldh);
+            const int dn = D / parts, d0 = half * dn;
+            float A = 0.f;
+            for (int d = d0; d < d0 + dn; ++d) {
+                float a0 = ba[d], a1 = 0.f, b0 = bb[d], b1v = 0.f;
+                const uint32_t wa_addr = smem_u32(sG + d * L1), wb_addr = smem_u32(sG + (D + d) * L1);
+#pragma unroll 4
+                for (int j = 0; j < L1; j += 4) {
+                    const float4 h4 = lds_f4(h_addr + j * 4);
+                    const float4 wa = lds_f4(wa_addr + j * 4), wb = lds_f4(wb_addr + j * 4);
+                    a0 = fmaf(wa.x, h4.x, a0); a1 = fmaf(wa.y, h4.y, a1); a0 = fmaf(wa.z, h4.z, a0); a1 = fmaf(wa.w, h4.w, a1);
+                    b0 = fmaf(wb.x, h4.x, b0); b1v = fmaf(wb.y, h4.y, b1v); b0 = fmaf(wb.z, h4.z, b0); b1v = fmaf(wb.w, h4.w, b1v);
+                }
+                A = fmaf(Wc[d], tanhf(a0 + a1) * (1.0f / (1.0f + expf(-(b0 + b1v)))), A);
+            }
+            sA[half * CL_CH + inst] = A;
+        }
+        __syncthreads();
+        float A = sV[L1 + 3 * D];
+        for (int q = 0; q < parts; ++q) A += sA[q * CL_CH + inst];
+        if (valid) a_raw[static_cast<size_t>(mi) * total_instances + start + i0 + inst] = A;
+
+        // ---- chunk-local softmax partial
+        const float mx = block_reduce_max_128(valid ? A : -INFINITY, red);
+        const float e = valid ? expf(A - mx) : 0.f;
+        if (half == 0) sE[inst] = e;
+        const float sum = block_reduce_sum_128(e, red);     // contains the __syncthreads that publishes sE
+        float* out = partials + (static_cast<size_t>(mi) * work_cap + wi) * (L1 + 2);
+        if (tid == 0) { out[0] = mx; out[1] = sum; }
+        {                                                    // sum_i e_i h1[i][:]: instance groups in parallel, then a small reduce
+            const int G = nthreads / L1;                     // >= 1 (L1 <= 128 <= nthreads)
+            const int ig = tid / L1, j = tid - ig * L1;
+            float acc = 0.f;
+            if (ig < G)
+                for (int i = ig; i < n_valid; i += G) acc = fmaf(sE[i], sH[i * ldh + j], acc);
+            sA[tid] = acc;                                   // sA ([4][64] >= nthreads floats) is free again here
+            __syncthreads();
+            if (tid < L1) {
+                float v = 0.f;
+                for (int g = 0; g < G; ++g) v += sA[g * L1 + tid];
+                out[2 + tid] = v;
+            }
+        }
+        __syncthreads();       // sH / sE / sG / sA are rewritten by the next model
+    }
+}
+
 __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __restrict__ bag_offsets,
                                                            const __grid_constant__ ClamModels models, int n_bags, int L1,
-                                                           int C, int max_chunks, const float* __restrict__ partials,
+                                                           int C, int work_cap, int CH, const int32_t* __restrict__ prefix,
+                                                           const float* __restrict__ partials,
                                                            float* __restrict__ m_out, float* __restrict__ logits,
                                                            float* __restrict__ y_prob, long long* __restrict__ y_hat) {
-    extern __shared__ float sM[];                             // [L1] + [C]
+    extern __shared__ float sM[];                             // [L1] + [C] + [128] scratch + [8]
     float* sL = sM + L1;
+    float* sP = sL + C;                                       // [128] per-group partial sums of M
+    float* red = sP + 128;
     const int bag = blockIdx.x, mi = blockIdx.y, tid = threadIdx.x;
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
-    const int CH = clam_chunk_for(L1);
     const int n_chunks = (len + CH - 1) / CH;
-    const float* base = partials + static_cast<size_t>(mi * n_bags + bag) * max_chunks * (L1 + 2);
-    float gmax = -INFINITY;
-    for (int c = 0; c < n_chunks; ++c) gmax = fmaxf(gmax, base[static_cast<size_t>(c) * (L1 + 2)]);
-    float total = 0.f;
-    for (int c = 0; c < n_chunks; ++c) {
-        const float* pc = base + static_cast<size_t>(c) * (L1 + 2);
-        total += pc[1] * expf(pc[0] - gmax);
-    }
+    const size_t rec = L1 + 2;
+    const float* base = partials + (static_cast<size_t>(mi) * work_cap + prefix[bag]) * rec;
+    // chunks are spread over the threads (a 20,000-instance bag has 313 of them: a serial walk is latency-bound)
+    float gm = -INFINITY;
+    for (int c = tid; c < n_chunks; c += 128) gm = fmaxf(gm, base[c * rec]);
+    const float gmax = block_reduce_max_128(gm, red);
+    float tl = 0.f;
+    for (int c = tid; c < n_chunks; c += 128) tl += base[c * rec + 1] * expf(base[c * rec] - gmax);
+    const float total = block_reduce_sum_128(tl, red);
     const float inv = (n_chunks > 0) ? 1.0f / total : 0.f;
-    for (int j = tid; j < L1; j += blockDim.x) {
+    if (L1 <= 128) {
+        const int G = 128 / L1;                               // chunk groups walking the chunk list in parallel
+        const int cg = tid / L1, j = tid - cg * L1;
         float acc = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-            const float* pc = base + static_cast<size_t>(c) * (L1 + 2);
-            acc = fmaf(pc[2 + j], expf(pc[0] - gmax), acc);
+        if (cg < G)
+            for (int c = cg; c < n_chunks; c += G) acc = fmaf(base[c * rec + 2 + j], expf(base[c * rec] - gmax), acc);
+        sP[tid] = acc;
+        __syncthreads();
+        if (tid < L1) {
+            float v = 0.f;
+            for (int g = 0; g < G; ++g) v += sP[g * L1 + tid];
+            v *= inv;
+            sM[tid] = v;
+            if (m_out) m_out[static_cast<size_t>(mi * n_bags + bag) * L1 + tid] = v;
         }
-        acc *= inv;
-        sM[j] = acc;
-        if (m_out) m_out[static_cast<size_t>(mi * n_bags + bag) * L1 + j] = acc;
+    } else {
+        for (int j = tid; j < L1; j += blockDim.x) {
+            float acc = 0.f;
+            for (int c = 0; c < n_chunks; ++c) acc = fmaf(base[c * rec + 2 + j], expf(base[c * rec] - gmax), acc);
+            acc *= inv;
+            sM[j] = acc;
+            if (m_out) m_out[static_cast<size_t>(mi * n_bags + bag) * L1 + j] = acc;
+        }
     }
     __syncthreads();
     const float* Wcls = models.m[mi].p[8];
@@ -215,10 +488,20 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
     }
 }
 
+// workspace = [prefix: n_bags + 1 ints][work: 2 * cap ints][partials: n_models * cap * (L1 + 2) floats], cap = bound on
+// the number of (bag, chunk) items.  The size query knows only max_bag_len: it uses the smallest chunk of any variant.
+static size_t clam_ws_layout(size_t cap, int n_bags, int n_models, int L1, size_t* off_work, size_t* off_part) {
+    size_t o = (static_cast<size_t>(n_bags) + 1) * sizeof(int32_t);
+    o = (o + 15) & ~static_cast<size_t>(15);
+    if (off_work) *off_work = o;
+    o += 2 * cap * sizeof(int32_t);
+    o = (o + 15) & ~static_cast<size_t>(15);
+    if (off_part) *off_part = o;
+    return o + static_cast<size_t>(n_models) * cap * (L1 + 2) * sizeof(float);
+}
 size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1) {
-    const size_t ch = clam_chunk_for(L1);
-    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + ch - 1) / ch;
-    return static_cast<size_t>(n_models) * n_bags * (max_chunks ? max_chunks : 1) * (L1 + 2) * sizeof(float);
+    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + 31) / 32;
+    return clam_ws_layout(static_cast<size_t>(n_bags) * (max_chunks ? max_chunks : 1), n_bags, n_models, L1, nullptr, nullptr);
 }
 
 int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
@@ -232,8 +515,20 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     if (!bag_offsets || !weights_host || !a_raw || !workspace) return set_error("hb_clam: null argument");
     if (total_instances > 0 && !feats) return set_error("hb_clam: null features");
     if ((reinterpret_cast<uintptr_t>(feats) & 15) != 0) return set_error("hb_clam: features must be 16 B aligned");
-    const size_t need = clam_workspace_bytes(max_bag_len, n_bags, n_models, L1);
+    const int CH = clam_chunk_for(L0, L1, D);
+    const int max_chunks = (max_bag_len + CH - 1) / CH;
+    // (bag, chunk) items: every bag has at most one partial chunk
+    size_t cap = static_cast<size_t>(total_instances) / CH + n_bags;
+    const size_t cap2 = static_cast<size_t>(n_bags) * (max_chunks ? max_chunks : 1);
+    if (cap2 < cap) cap = cap2;
+    if (cap < 1) cap = 1;
+    size_t off_work, off_part;
+    const size_t need = clam_ws_layout(cap, n_bags, n_models, L1, &off_work, &off_part);
     if (workspace_bytes < need) return set_error("hb_clam: workspace %zu < %zu bytes", workspace_bytes, need);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return set_error("hb_clam: workspace must be 16 B aligned");
+    int32_t* prefix = static_cast<int32_t*>(workspace);
+    int32_t* work = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + off_work);
+    const int work_cap = static_cast<int>(cap);
     ClamModels models;
     memset(&models, 0, sizeof(models));
     for (int m = 0; m < n_models; ++m)
@@ -241,26 +536,37 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
             models.m[m].p[k] = static_cast<const float*>(weights_host[m * 10 + k]);
             if (!models.m[m].p[k]) return set_error("hb_clam: weight pointer %d of model %d is null", k, m);
         }
-    const int CH = clam_chunk_for(L1);
-    const int max_chunks = (max_bag_len + CH - 1) / CH;
-    float* partials = static_cast<float*>(workspace);
-    if (max_chunks > 0) {
+    float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + off_part);
+    clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, CH, prefix, work, work_cap);
+    count_launch();
+    HB_CUDA_OK(cudaGetLastError());
+    if (max_chunks > 0 && clam_is192(L0, L1, D)) {
+        const size_t smem = (static_cast<size_t>(CL_CH) * CL_XS + (clam_kc_for(L1) + 4) * L1 + static_cast<size_t>(CL_CH) * (L1 + 4) +
+                             2 * static_cast<size_t>(D) * L1 + 5 * CL_CH + 8 + L1 + 3 * D + 4) * sizeof(float);
+        const int threads = L1 >= 64 ? 256 : CL_THREADS;
+        auto kern = (L1 <= 16) ? clam_scores192_kernel<4> : clam_scores192_kernel<8>;
+        HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        ProfScope ps(10, stream);
+        kern<<<work_cap, threads, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags, total_instances, L1, D,
+                                                  prefix, work, work_cap, a_raw, partials);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+    } else if (max_chunks > 0) {
         const size_t smem = (static_cast<size_t>(CH) * (CLAM_KC + 1) + CLAM_KC * CLAM_OB + CH + 4 +
                              static_cast<size_t>(CH) * (L1 + 1)) * sizeof(float);
         if (smem > 220 * 1024) return set_error("hb_clam: L1=%d too large for the fused kernel", L1);
         HB_CUDA_OK(cudaFuncSetAttribute(clam_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        dim3 grid(max_chunks, n_bags);
         ProfScope ps(10, stream);
-        clam_scores_kernel<<<grid, CH, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags,
-                                                                total_instances, L0, L1, D, max_chunks, a_raw, partials);
+        clam_scores_kernel<<<work_cap, CH, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags, total_instances,
+                                                           L0, L1, D, prefix, work, work_cap, a_raw, partials);
         count_launch();
     HB_CUDA_OK(cudaGetLastError());
     }
     dim3 grid2(n_bags, n_models);
     ProfScope ps2(11, stream);
-    clam_combine_kernel<<<grid2, 128, (L1 + C) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
-                                                                           max_chunks > 0 ? max_chunks : 1, partials,
-                                                                           m_out, logits, y_prob, y_hat);
+    clam_combine_kernel<<<grid2, 128, (L1 + C + 128 + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
+                                                                                    work_cap, CH, prefix, partials, m_out,
+                                                                                    logits, y_prob, y_hat);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;

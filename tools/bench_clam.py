@@ -1,0 +1,51 @@
+"""Config 4 of BASELINE.json: CLAM_SB gated-ABMIL on ragged bags of 50-20,000 instances x 192-d, reported as achieved
+HBM GB/s (algorithmic bytes: 772 B / instance forward = 192 fp32 features read once + one fp32 score written; SURVEY
+§8d).  One launch covers all bags (and all folds).  python tools/bench_clam.py [--size hipt_smaller] [--folds 1]"""
+import argparse, json, math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from hipt_abmil_atec23_b200 import clam_engine, _lib
+from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+
+
+def bag_lengths(n_bags=256, lo=50, hi=20000, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(n_bags, generator=g)
+    return torch.exp(math.log(lo) + u * (math.log(hi) - math.log(lo))).long().clamp(lo, hi)
+
+
+def run(size, folds, reps=20):
+    dev = torch.device("cuda:0")
+    lens = bag_lengths()
+    offs = torch.zeros(lens.numel() + 1, dtype=torch.int32)
+    offs[1:] = torch.cumsum(lens, 0)
+    total = int(offs[-1])
+    feats = torch.randn((total, 192), generator=torch.Generator().manual_seed(5)).to(dev)
+    models = []
+    for f in range(folds):
+        torch.manual_seed(10 + f)
+        models.append(CLAM_SB(size_arg=size, dropout=0.0, n_classes=2).eval().to(dev))
+    offs_d = offs.to(dev)
+    mx = int(lens.max())
+    f = lambda: clam_engine.forward_bags(models, feats, offs_d, max_bag_len=mx, want=("logits", "y_prob", "y_hat"))
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): f()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bytes_alg = total * (192 * 4 + 4 * folds)
+    return {"size": size, "folds": folds, "bags": int(lens.numel()), "instances": total, "ms": ms,
+            "bags_per_s": lens.numel() / ms * 1e3, "instances_per_s": total / ms * 1e3,
+            "algorithmic_GBps": bytes_alg / ms / 1e6, "feature_MB": total * 768 / 1e6}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", default=None)
+    ap.add_argument("--folds", type=int, default=None)
+    a = ap.parse_args()
+    for size in ([a.size] if a.size else ["hipt_smaller", "hipt_big"]):
+        for folds in ([a.folds] if a.folds else [1, 5]):
+            print(json.dumps(run(size, folds)))
