@@ -28,7 +28,11 @@ def test_abi_version_and_error_string():
     lib = _lib.load()
     assert lib.hb_abi_version() == 2
     assert isinstance(lib.hb_last_error(), bytes)
-    assert lib.hb_clam_workspace_bytes(20000, 256, 5, 16) == 5 * 256 * 157 * 18 * 4
+    # [prefix: n_bags + 1 ints][work: 2 ints per (bag, chunk) item][partials: n_models x items x (L1 + 2) floats], items bounded
+    # with the smallest chunk (32 instances); each part 16-byte aligned
+    items = 256 * ((20000 + 31) // 32)
+    al = lambda v: (v + 15) & ~15
+    assert lib.hb_clam_workspace_bytes(20000, 256, 5, 16) == al(al(257 * 4) + 2 * items * 4) + 5 * items * 18 * 4
 
 
 def test_config_struct_layout_matches_header():
