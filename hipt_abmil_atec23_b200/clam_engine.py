@@ -85,3 +85,126 @@ def forward_single(model, h, attention_only=False):
     if attention_only:
         return r["a_raw"]
     return r["logits"][0], r["y_prob"][0], r["y_hat"][0].view(1, 1), r["a_raw"], r["m"][0]
+
+
+# ------------------------------------------------------------------------------------------------------ training step
+def supports_fused_backward(model):
+    """The fused backward covers the HIPT sizes: 192-d features, L1 <= 128 (hb_clam_sb_backward)."""
+    fc = model.attention_net[0]
+    g = _gate_module(model)
+    D = g.attention_c.in_features
+    return (fc.in_features == 192 and fc.out_features <= 128 and fc.out_features % 8 == 0 and D % 4 == 0
+            and g.attention_c.out_features == 1)
+
+
+def _param_list(model):
+    g = _gate_module(model)
+    return [model.attention_net[0].weight, model.attention_net[0].bias,
+            g.attention_a[0].weight, g.attention_a[0].bias, g.attention_b[0].weight, g.attention_b[0].bias,
+            g.attention_c.weight, g.attention_c.bias, model.classifiers.weight, model.classifiers.bias]
+
+
+class ClamSBFunction(torch.autograd.Function):
+    """CLAM_SB.forward for one bag as a differentiable op: forward = hb_clam_sb_forward, backward = hb_clam_sb_backward
+    (recomputation: only A_raw and M are kept).  Differentiable outputs: logits [1,C], Y_prob [1,C], A_raw [1,N], M [1,L1];
+    gradients flow to the 10 weight tensors (not to the bag: features are frozen HIPT_4K embeddings)."""
+
+    @staticmethod
+    def forward(ctx, h, *params):
+        lib = _lib.load()
+        dev = h.device
+        if h.dtype != torch.float32 or not h.is_contiguous():
+            h = h.float().contiguous()
+        N, L0 = h.shape
+        w = [p.detach().contiguous() for p in params]
+        L1, D, Cc = w[0].shape[0], w[2].shape[0], w[8].shape[0]
+        offs = torch.tensor([0, N], dtype=torch.int32).to(dev)
+        with torch.cuda.device(dev):
+            arr = (C.c_void_p * 10)(*[t.data_ptr() for t in w])
+            a_raw = torch.empty((1, N), dtype=torch.float32, device=dev)
+            m_out = torch.empty((1, L1), dtype=torch.float32, device=dev)
+            logits = torch.empty((1, Cc), dtype=torch.float32, device=dev)
+            y_prob = torch.empty((1, Cc), dtype=torch.float32, device=dev)
+            ws_bytes = lib.hb_clam_workspace_bytes(N, 1, 1, L1)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            _lib.check(lib.hb_clam_sb_forward(_lib.ptr(h), _lib.ptr(offs), 1, N, N, arr, 1, L0, L1, D, Cc, _lib.ptr(a_raw),
+                                              _lib.ptr(m_out), _lib.ptr(logits), _lib.ptr(y_prob), None, _lib.ptr(ws),
+                                              ws.numel(), _lib.stream_ptr()))
+        ctx.save_for_backward(h, a_raw, m_out, y_prob, *w)
+        ctx.dims = (N, L0, L1, D, Cc)
+        return logits, y_prob, a_raw, m_out
+
+    @staticmethod
+    def backward(ctx, g_logits, g_yprob, g_araw, g_m):
+        lib = _lib.load()
+        h, a_raw, m_out, y_prob, *w = ctx.saved_tensors
+        N, L0, L1, D, Cc = ctx.dims
+        dev = h.device
+        dl = torch.zeros((1, Cc), dtype=torch.float32, device=dev) if g_logits is None else g_logits.float()
+        if g_yprob is not None:                                    # softmax backward on the [1, C] logits
+            dl = dl + y_prob * (g_yprob - (g_yprob * y_prob).sum(dim=1, keepdim=True))
+        dl = dl.contiguous()
+        gm = None if g_m is None else g_m.float().contiguous()
+        ga = None if g_araw is None else g_araw.float().contiguous()
+        with torch.cuda.device(dev):
+            grads = [torch.empty_like(t) for t in w]
+            warr = (C.c_void_p * 10)(*[t.data_ptr() for t in w])
+            garr = (C.c_void_p * 10)(*[t.data_ptr() for t in grads])
+            ws = torch.empty(4 + L1, dtype=torch.float32, device=dev)
+            _lib.check(lib.hb_clam_sb_backward(_lib.ptr(h), N, warr, _lib.ptr(a_raw), _lib.ptr(m_out), _lib.ptr(dl),
+                                               _lib.ptr(gm), _lib.ptr(ga), garr, L0, L1, D, Cc, _lib.ptr(ws),
+                                               ws.numel() * 4, _lib.stream_ptr()))
+        return (None, *grads)
+
+
+def forward_single_autograd(model, h):
+    """(logits, Y_prob, Y_hat, A_raw, M) with autograd through the fused kernels (training: main.py -> train_loop)."""
+    logits, y_prob, a_raw, m = ClamSBFunction.apply(h, *_param_list(model))
+    y_hat = torch.topk(logits, 1, dim=1)[1]
+    return logits, y_prob, y_hat, a_raw, m
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr, betas, eps, weight_decay) semantics with every fp32 CUDA tensor of a group updated by
+    ONE hb_adam_step launch (the reference's get_optim builds optim.Adam(lr=args.lr, weight_decay=args.reg),
+    utils/utils.py:100-107; a CLAM_SB step is 14 tiny tensors -> 14+ launches there)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("FusedAdam updates contiguous fp32 CUDA parameters only (there is no CPU path)")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+            step = self.state[ps[0]]["step"] + 1
+            for i in range(0, len(ps), 16):
+                chunk = ps[i:i + 16]
+                n = len(chunk)
+                grads = [p.grad.contiguous() for p in chunk]
+                parr = (C.c_void_p * n)(*[p.data_ptr() for p in chunk])
+                garr = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+                marr = (C.c_void_p * n)(*[self.state[p]["exp_avg"].data_ptr() for p in chunk])
+                varr = (C.c_void_p * n)(*[self.state[p]["exp_avg_sq"].data_ptr() for p in chunk])
+                narr = (C.c_int * n)(*[p.numel() for p in chunk])
+                with torch.cuda.device(chunk[0].device):
+                    _lib.check(lib.hb_adam_step(parr, garr, marr, varr, narr, n, float(group["lr"]), float(group["betas"][0]),
+                                                float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
+                                                step, _lib.stream_ptr()))
+            for p in ps:
+                self.state[p]["step"] = step
+        return loss

@@ -33,7 +33,12 @@ constexpr int CLAM_CHUNK = 128;     // generic kernel: instances per CTA (32 whe
 constexpr int CL_CH = 64;           // 192-d kernel: instances per CTA
 constexpr int CL_THREADS = 128;     // 256 when L1 >= 64 (one CTA per SM then: more warps to hide latency)
 constexpr int CL_XS = 196;          // feature row stride in floats: 16 B aligned and conflict-free for 8-lane float4 wavefronts
-__host__ __device__ inline int clam_kc_for(int L1) { return L1 <= 32 ? 192 : 64; }   // rows of W1^T staged per step
+__host__ __device__ inline int clam_kc_for(int L1) { return L1 <= 32 ? 192 : 64; }   // columns of W1 staged per step
+// floats of the W1 staging buffer [L1][KC + 4]; the backward reuses it for dz [64][L1 + 4]
+__host__ __device__ inline int clam_sw_floats(int L1) {
+    const int a = (clam_kc_for(L1) + 4) * L1, b = CL_CH * (L1 + 4);
+    return a > b ? a : b;
+}
 __host__ __device__ inline bool clam_is192(int L0, int L1, int D) {
     return L0 == 192 && L1 <= 128 && (L1 % 8) == 0 && (D % 4) == 0;
 }
@@ -237,7 +242,7 @@ __device__ __forceinline__ void lds_2f2(uint32_t addr, f32x2_t& a, f32x2_t& b) {
 // lane + 32) x TN columns; warp w owns column groups w, w + nw, ...; W1 reads are warp-uniform broadcasts.
 template <int TN>
 __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const float* b1, int L1,
-                                             const float* sX, float* sW, float* sH, int ldh) {
+                                             const float* sX, float* sW, float* sH, int ldh, bool two_halves = true) {
     constexpr int GPW = (TN == 8) ? 2 : 1;                   // column groups per warp: L1 <= 16 (TN 4, 4 warps), L1 = 32 (TN 8,
                                                              // 4 warps), L1 = 64 / 128 (TN 8, 8 warps)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -251,7 +256,8 @@ __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int c = 0; c < TN; ++c) acc[g][i][c] = f2_pack(0.f, 0.f);
-    const uint32_t x0_addr = smem_u32(sX + lane * CL_XS), x1_addr = smem_u32(sX + (lane + 32) * CL_XS);
+    // 32-instance tiles (backward of the large heads): the second instance of the thread tile repeats the first
+    const uint32_t x0_addr = smem_u32(sX + lane * CL_XS), x1_addr = two_halves ? smem_u32(sX + (lane + 32) * CL_XS) : x0_addr;
     for (int kc = 0; kc < 192; kc += KC) {
         // stage W1[:, kc:kc+KC] as sW[col][k] (row stride KC + 4): straight 16-byte copies
         {
@@ -299,6 +305,7 @@ __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const
                 const float bias = b1[col];                  // shared memory (staged with the fold's other small vectors)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
+                    if (i == 1 && !two_halves) break;
                     float v0, v1;
                     f2_unpack(acc[g][i][c], v0, v1);
                     sH[(lane + 32 * i) * ldh + col] = fmaxf(v0 + v1 + bias, 0.f);
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
     const int ldh = L1 + 4;
     float* sX = smem_clam;                                   // [64][196]
     float* sW = sX + CL_CH * CL_XS;                          // [L1][KC + 4]  W1 slice
-    float* sH = sW + (clam_kc_for(L1) + 4) * L1;             // [64][L1 + 4]
+    float* sH = sW + clam_sw_floats(L1);                     // [64][L1 + 4]
     float* sG = sH + CL_CH * ldh;                            // [2][D][L1]    Wa, Wb
     float* sA = sG + 2 * D * L1;                             // [4][64]       per-part score partials
     float* sE = sA + 4 * CL_CH;                              // [64]
@@ -541,7 +548,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     if (max_chunks > 0 && clam_is192(L0, L1, D)) {
-        const size_t smem = (static_cast<size_t>(CL_CH) * CL_XS + (clam_kc_for(L1) + 4) * L1 + static_cast<size_t>(CL_CH) * (L1 + 4) +
+        const size_t smem = (static_cast<size_t>(CL_CH) * CL_XS + clam_sw_floats(L1) + static_cast<size_t>(CL_CH) * (L1 + 4) +
                              2 * static_cast<size_t>(D) * L1 + 5 * CL_CH + 8 + L1 + 3 * D + 4) * sizeof(float);
         const int threads = L1 >= 64 ? 256 : CL_THREADS;
         auto kern = (L1 <= 16) ? clam_scores192_kernel<4> : clam_scores192_kernel<8>;
@@ -572,6 +579,296 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     return 0;
 }
 
+
+// =====================================================================================================================
+// Training step around CLAM_SB.forward (utils/core_utils.py:409-423: loss = CE(logits, label); loss.backward();
+// optimizer.step()) for one bag and one weight set, 192-d features.
+//
+// Backward with recomputation (1,544 algorithmic HBM bytes per instance over forward + backward): the forward keeps only
+// A_raw [N] and M [L1]; the backward re-reads the feature tile, recomputes h1 and the gate, and forms
+//   dM = Wcls^T dlogits (+ dM_ext),  s = dM . M,  alpha_i = softmax(A)_i,  dA_i = alpha_i (dM . h1_i - s) (+ dA_ext_i)
+//   dpre_a = dA Wc b (1 - a^2),  dpre_b = dA Wc a b (1 - b),  dh1 = alpha dM + Wa^T dpre_a + Wb^T dpre_b,  dz = dh1 [h1 > 0]
+// and the parameter gradients as per-chunk sums added to global memory with atomics (model_clam.py:59-63, 147-183).
+// clam_bwd_prep_kernel: one CTA: softmax statistics of A_raw, dM, s, classifier gradients, zeroes the other gradients.
+// clam_bwd192_kernel: one CTA per 64-instance chunk.
+// =====================================================================================================================
+struct ClamGrads { float* p[10]; };
+
+__global__ void __launch_bounds__(256) clam_bwd_prep_kernel(const float* __restrict__ a_raw, int N, const float* __restrict__ M,
+                                                            const float* __restrict__ dlogits, const float* __restrict__ dM_ext,
+                                                            const float* __restrict__ Wcls, const __grid_constant__ ClamGrads g,
+                                                            int L1, int D, int C, float* __restrict__ ctx) {
+    __shared__ float red[8];
+    const int tid = threadIdx.x;
+    float mx = -INFINITY;
+    for (int i = tid; i < N; i += 256) mx = fmaxf(mx, a_raw[i]);
+    const float gmax = block_reduce_max_128(mx, red);
+    float sm = 0.f;
+    for (int i = tid; i < N; i += 256) sm += expf(a_raw[i] - gmax);
+    const float total = block_reduce_sum_128(sm, red);
+    float part = 0.f;
+    for (int j = tid; j < L1; j += 256) {
+        float dm = dM_ext ? dM_ext[j] : 0.f;
+        for (int c = 0; c < C; ++c) dm = fmaf(Wcls[c * L1 + j], dlogits[c], dm);
+        ctx[4 + j] = dm;
+        part = fmaf(dm, M[j], part);
+    }
+    const float s = block_reduce_sum_128(part, red);
+    if (tid == 0) { ctx[0] = gmax; ctx[1] = (N > 0) ? 1.0f / total : 0.f; ctx[2] = s; }
+    for (int idx = tid; idx < C * L1; idx += 256) { const int c = idx / L1; g.p[8][idx] = dlogits[c] * M[idx - c * L1]; }
+    for (int c = tid; c < C; c += 256) g.p[9][c] = dlogits[c];
+    const int sizes[8] = {L1 * 192, L1, D * L1, D, D * L1, D, D, 1};
+    for (int k = 0; k < 8; ++k)
+        for (int idx = tid; idx < sizes[k]; idx += 256) g.p[k][idx] = 0.f;
+}
+
+template <int TN>
+__global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restrict__ feats, int N,
+                                                          const __grid_constant__ ClamModel w, const float* __restrict__ a_raw,
+                                                          const float* __restrict__ dA_ext, const float* __restrict__ ctx,
+                                                          const __grid_constant__ ClamGrads g, int L1, int D, int ch) {
+    extern __shared__ __align__(16) float smem_clam[];
+    const int ldh = L1 + 4, ldp = 2 * D + 1;
+    float* sX = smem_clam;                                   // [ch][196]   ch = 64 instances, 32 for the large heads
+    float* sW = sX + ch * CL_XS;                          // [L1][KC + 4]  W1 slice; later dz [64][L1 + 4]
+    float* sH = sW + clam_sw_floats(L1);                     // [ch][L1 + 4]
+    float* sG = sH + ch * ldh;                            // [2][D][L1]    Wa, Wb
+    float* sAB = sG + 2 * D * L1;                            // [64][2D + 1]  a | b
+    float* sDP = sAB + ch * ldp;                          // [64][2D + 1]  dpre_a | dpre_b
+    float* sDA = sDP + ch * ldp;                          // [64] dA, [64] alpha
+    float* sV = sDA + 2 * ch;                             // b1 [L1] | ba [D] | bb [D] | Wc [D] | bc [1] | pad | dM [L1]
+    float* sDZ = sW;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int i0 = blockIdx.x * ch;
+    const int n_valid = min(ch, N - i0);
+    const int nsmall = L1 + 3 * D + 1;
+    float* sDM = sV + ((nsmall + 3) & ~3);
+
+    {
+        const float4* src = reinterpret_cast<const float4*>(feats + static_cast<size_t>(i0) * 192);
+        const uint32_t dst0 = smem_u32(sX);
+        for (int idx = tid; idx < ch * 48; idx += nthreads) {
+            const int r = idx / 48, c4 = idx - r * 48;
+            const int nbytes = (r < n_valid) ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (r * CL_XS + c4 * 4) * 4),
+                         "l"(src + (r < n_valid ? idx : 0)), "r"(nbytes) : "memory");
+        }
+        for (int idx = tid; idx < D * L1 / 4; idx += nthreads) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG + idx * 4)), "l"(w.p[2] + idx * 4) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG + D * L1 + idx * 4)), "l"(w.p[4] + idx * 4) : "memory");
+        }
+        for (int idx = tid; idx < nsmall; idx += nthreads) {
+            const float* src1 = idx < L1 ? w.p[1] + idx : idx < L1 + D ? w.p[3] + (idx - L1) : idx < L1 + 2 * D ? w.p[5] + (idx - L1 - D)
+                              : idx < L1 + 3 * D ? w.p[6] + (idx - L1 - 2 * D) : w.p[7];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sV + idx)), "l"(src1) : "memory");
+        }
+        for (int idx = tid; idx < L1; idx += nthreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sDM + idx)), "l"(ctx + 4 + idx) : "memory");
+    }
+    clam_fc1_192<TN>(w.p[0], sV, L1, sX, sW, sH, ldh, ch == 64);   // waits for every cp.async above, ends with a __syncthreads
+    const float gmax = ctx[0], inv_total = ctx[1], s_dot = ctx[2];
+    const float* ba = sV + L1; const float* bb = ba + D; const float* Wc = bb + D;
+
+    const int parts = nthreads / ch;
+    const int inst = tid % ch, part = tid / ch;
+    const int dn = D / parts, d0 = part * dn;
+    // ---- gate recomputation: a, b of this thread's units; part 0 also forms alpha_i and dA_i
+    {
+        const uint32_t h_addr = smem_u32(sH + inst * ldh);
+        for (int d = d0; d < d0 + dn; ++d) {
+            float a0 = ba[d], a1 = 0.f, b0 = bb[d], b1v = 0.f;
+            const uint32_t wa_addr = smem_u32(sG + d * L1), wb_addr = smem_u32(sG + (D + d) * L1);
+#pragma unroll 4
+            for (int j = 0; j < L1; j += 4) {
+                const float4 h4 = lds_f4(h_addr + j * 4);
+                const float4 wa = lds_f4(wa_addr + j * 4), wb = lds_f4(wb_addr + j * 4);
+                a0 = fmaf(wa.x, h4.x, a0); a1 = fmaf(wa.y, h4.y, a1); a0 = fmaf(wa.z, h4.z, a0); a1 = fmaf(wa.w, h4.w, a1);
+                b0 = fmaf(wb.x, h4.x, b0); b1v = fmaf(wb.y, h4.y, b1v); b0 = fmaf(wb.z, h4.z, b0); b1v = fmaf(wb.w, h4.w, b1v);
+            }
+            sAB[inst * ldp + d] = tanhf(a0 + a1);
+            sAB[inst * ldp + D + d] = 1.0f / (1.0f + expf(-(b0 + b1v)));
+        }
+        if (part == 0) {
+            float dot = 0.f;
+            for (int j = 0; j < L1; ++j) dot = fmaf(sDM[j], sH[inst * ldh + j], dot);
+            float alpha = 0.f, dA = 0.f;
+            if (inst < n_valid) {
+                alpha = expf(a_raw[i0 + inst] - gmax) * inv_total;
+                dA = alpha * (dot - s_dot) + (dA_ext ? dA_ext[i0 + inst] : 0.f);
+            }
+            sDA[inst] = dA;
+            sDA[ch + inst] = alpha;
+        }
+    }
+    __syncthreads();
+    // ---- dpre_a, dpre_b
+    {
+        const float dA = sDA[inst];
+        for (int d = d0; d < d0 + dn; ++d) {
+            const float a = sAB[inst * ldp + d], b = sAB[inst * ldp + D + d];
+            const float t = dA * Wc[d];
+            sDP[inst * ldp + d] = t * b * (1.0f - a * a);
+            sDP[inst * ldp + D + d] = t * a * b * (1.0f - b);
+        }
+    }
+    __syncthreads();
+    // ---- dz = (alpha dM + Wa^T dpre_a + Wb^T dpre_b) [h1 > 0]     (sDZ aliases the W1 staging buffer: fc1 is done)
+    {
+        const float alpha = sDA[ch + inst];
+        const int jn = L1 / parts, j0 = part * jn;
+        for (int j = j0; j < j0 + jn; ++j) {
+            float acc = alpha * sDM[j];
+            for (int d = 0; d < D; ++d) {
+                acc = fmaf(sG[d * L1 + j], sDP[inst * ldp + d], acc);
+                acc = fmaf(sG[(D + d) * L1 + j], sDP[inst * ldp + D + d], acc);
+            }
+            sDZ[inst * ldh + j] = (sH[inst * ldh + j] > 0.f) ? acc : 0.f;
+        }
+    }
+    __syncthreads();
+    // ---- parameter gradients of this chunk -> global (atomics)
+    // dW1 [L1][192]: thread tile = 8 output rows x 4 columns, loop over the 64 instances
+    for (int task = tid; task < 48 * (L1 / 8); task += nthreads) {
+        const int jg = task / 48, kq = task - jg * 48;
+        float4 acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t x_addr = smem_u32(sX + kq * 4), z_addr = smem_u32(sDZ + jg * 8);
+        for (int i = 0; i < n_valid; ++i) {
+            const float4 x4 = lds_f4(x_addr + i * CL_XS * 4);
+            const float4 z0 = lds_f4(z_addr + i * ldh * 4), z1 = lds_f4(z_addr + i * ldh * 4 + 16);
+            const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc[q].x = fmaf(z[q], x4.x, acc[q].x); acc[q].y = fmaf(z[q], x4.y, acc[q].y);
+                acc[q].z = fmaf(z[q], x4.z, acc[q].z); acc[q].w = fmaf(z[q], x4.w, acc[q].w);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float* dst = g.p[0] + static_cast<size_t>(jg * 8 + q) * 192 + kq * 4;
+            atomicAdd(dst, acc[q].x); atomicAdd(dst + 1, acc[q].y); atomicAdd(dst + 2, acc[q].z); atomicAdd(dst + 3, acc[q].w);
+        }
+    }
+    // dWa, dWb [D][L1]
+    for (int task = tid; task < 2 * D * L1; task += nthreads) {
+        const int which = task / (D * L1), rem = task - which * D * L1;
+        const int d = rem / L1, j = rem - d * L1;
+        float acc = 0.f;
+        for (int i = 0; i < n_valid; ++i) acc = fmaf(sDP[i * ldp + which * D + d], sH[i * ldh + j], acc);
+        atomicAdd(g.p[which ? 4 : 2] + rem, acc);
+    }
+    // db1 [L1], dba, dbb, dWc [D], dbc
+    for (int task = tid; task < L1 + 3 * D + 1; task += nthreads) {
+        float acc = 0.f;
+        if (task < L1) {
+            for (int i = 0; i < n_valid; ++i) acc += sDZ[i * ldh + task];
+            atomicAdd(g.p[1] + task, acc);
+        } else if (task < L1 + 2 * D) {
+            const int d2 = task - L1;                        // 0..D-1: dba, D..2D-1: dbb
+            for (int i = 0; i < n_valid; ++i) acc += sDP[i * ldp + d2];
+            atomicAdd(d2 < D ? g.p[3] + d2 : g.p[5] + (d2 - D), acc);
+        } else if (task < L1 + 3 * D) {
+            const int d = task - L1 - 2 * D;
+            for (int i = 0; i < n_valid; ++i) acc = fmaf(sDA[i], sAB[i * ldp + d] * sAB[i * ldp + D + d], acc);
+            atomicAdd(g.p[6] + d, acc);
+        } else {
+            for (int i = 0; i < n_valid; ++i) acc += sDA[i];
+            atomicAdd(g.p[7], acc);
+        }
+    }
+}
+
+int clam_backward_launch(const float* feats, int N, const void* const* weights_host, const float* a_raw, const float* M,
+                         const float* dlogits, const float* dM_ext, const float* dA_ext, void* const* grads_host, int L0,
+                         int L1, int D, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!clam_is192(L0, L1, D)) return set_error("hb_clam_sb_backward: only 192-d features with L1 <= 128 are supported (L0=%d L1=%d D=%d)", L0, L1, D);
+    if (N < 1 || C < 1 || C > 64) return set_error("hb_clam_sb_backward: bad dims N=%d C=%d", N, C);
+    if (!feats || !weights_host || !a_raw || !M || !dlogits || !grads_host || !workspace) return set_error("hb_clam_sb_backward: null argument");
+    if ((reinterpret_cast<uintptr_t>(feats) & 15) != 0) return set_error("hb_clam_sb_backward: features must be 16 B aligned");
+    if (workspace_bytes < (4 + static_cast<size_t>(L1)) * sizeof(float)) return set_error("hb_clam_sb_backward: workspace too small");
+    ClamModel w;
+    ClamGrads g;
+    for (int k = 0; k < 10; ++k) {
+        w.p[k] = static_cast<const float*>(weights_host[k]);
+        g.p[k] = static_cast<float*>(grads_host[k]);
+        if (!w.p[k] || !g.p[k]) return set_error("hb_clam_sb_backward: weight / gradient pointer %d is null", k);
+    }
+    float* ctx = static_cast<float*>(workspace);
+    {
+        ProfScope ps(12, stream);
+        clam_bwd_prep_kernel<<<1, 256, 0, stream>>>(a_raw, N, M, dlogits, dM_ext, w.p[8], g, L1, D, C, ctx);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+    }
+    const int ldp = 2 * D + 1;
+    const int ch = L1 >= 64 ? 32 : CL_CH;                    // the large heads keep Wa, Wb, a, b, dpre in shared memory: smaller tile
+    const int threads = L1 >= 64 ? 256 : CL_THREADS;
+    if (D % (threads / ch) != 0 || L1 % (threads / ch) != 0)
+        return set_error("hb_clam_sb_backward: D=%d and L1=%d must be multiples of %d", D, L1, threads / ch);
+    const size_t smem = (static_cast<size_t>(ch) * CL_XS + clam_sw_floats(L1) + static_cast<size_t>(ch) * (L1 + 4) +
+                         2 * static_cast<size_t>(D) * L1 + 2 * static_cast<size_t>(ch) * ldp + 2 * ch +
+                         ((L1 + 3 * D + 1 + 3) & ~3) + L1 + 8) * sizeof(float);
+    if (smem > 220 * 1024) return set_error("hb_clam_sb_backward: shared memory %zu too large", smem);
+    auto kern = (L1 <= 16) ? clam_bwd192_kernel<4> : clam_bwd192_kernel<8>;
+    HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ProfScope ps(13, stream);
+    kern<<<(N + ch - 1) / ch, threads, smem, stream>>>(feats, N, w, a_raw, dA_ext, ctx, g, L1, D, ch);
+    count_launch();
+    HB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-tensor Adam with L2 weight decay, torch.optim.Adam semantics (utils/utils.py:100-107 get_optim):
+//   g += wd p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ADAM_MAX_TENSORS = 16;
+struct AdamTensors { float* p[ADAM_MAX_TENSORS]; const float* g[ADAM_MAX_TENSORS]; float* m[ADAM_MAX_TENSORS]; float* v[ADAM_MAX_TENSORS];
+                     int end[ADAM_MAX_TENSORS]; };
+
+__global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ AdamTensors t, int n_tensors, int total, float lr,
+                                                        float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k < n_tensors - 1 && idx >= t.end[k]) ++k;
+        const int off = idx - (k ? t.end[k - 1] : 0);
+        const float p = t.p[k][off];
+        const float g = t.g[k][off] + wd * p;
+        const float m = b1 * t.m[k][off] + (1.0f - b1) * g;
+        const float v = b2 * t.v[k][off] + (1.0f - b2) * g * g;
+        t.m[k][off] = m;
+        t.v[k][off] = v;
+        t.p[k][off] = p - (lr / bc1) * m / (sqrtf(v) / bc2_sqrt + eps);
+    }
+}
+
+int adam_step_launch(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                     const int* numel, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     int step, cudaStream_t stream) {
+    if (n_tensors < 1 || n_tensors > ADAM_MAX_TENSORS) return set_error("hb_adam_step: n_tensors must be 1..%d", ADAM_MAX_TENSORS);
+    if (step < 1) return set_error("hb_adam_step: step counts from 1");
+    AdamTensors t;
+    int total = 0;
+    for (int k = 0; k < n_tensors; ++k) {
+        if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || numel[k] < 0) return set_error("hb_adam_step: bad tensor %d", k);
+        t.p[k] = static_cast<float*>(params[k]); t.g[k] = static_cast<const float*>(grads[k]);
+        t.m[k] = static_cast<float*>(exp_avg[k]); t.v[k] = static_cast<float*>(exp_avg_sq[k]);
+        total += numel[k];
+        t.end[k] = total;
+    }
+    if (total == 0) return 0;
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+    int grid = (total + 255) / 256;
+    if (grid > 4 * num_sms()) grid = 4 * num_sms();
+    ProfScope ps(14, stream);
+    adam_step_kernel<<<grid, 256, 0, stream>>>(t, n_tensors, total, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt);
+    count_launch();
+    HB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace hb
 
 extern "C" {
@@ -585,5 +882,18 @@ int hb_clam_sb_forward(const float* feats, const int32_t* bag_offsets, int n_bag
     return hb::clam_forward_launch(feats, bag_offsets, n_bags, total_instances, max_bag_len, weights_host, n_models, L0,
                                    L1, D, C, a_raw, m_out, logits, y_prob, reinterpret_cast<long long*>(y_hat),
                                    workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int hb_clam_sb_backward(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
+                        const float* m_pooled, const float* dlogits, const float* dm_ext, const float* da_ext,
+                        void* const* grads_host, int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    return hb::clam_backward_launch(feats, n_instances, weights_host, a_raw, m_pooled, dlogits, dm_ext, da_ext, grads_host,
+                                    L0, L1, D, C, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int hb_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                 const int* numel, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                 void* stream) {
+    return hb::adam_step_launch(params, grads, exp_avg, exp_avg_sq, numel, n_tensors, lr, beta1, beta2, eps, weight_decay,
+                                step, static_cast<cudaStream_t>(stream));
 }
 }

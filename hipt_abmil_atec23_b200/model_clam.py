@@ -2,8 +2,10 @@
 
 CLAM_SB with gated attention — the model the HIPT-ABMIL pipeline trains and evaluates — runs its inference forward
 (`model(h)`, `model(h, attention_only=True)`, `return_features=True`) through the fused ragged-bag CUDA kernel in
-csrc/hb_clam.cu.  Calls that need autograd or the instance-clustering branch (training with `instance_eval=True`) are
-composed from torch ops on the same device; CLAM_MB and the ungated Attn_Net are kept constructible for checkpoint
+csrc/hb_clam.cu, and its training step (autograd enabled, HIPT sizes, dropout 0 as in the final ensemble config) through
+the same forward plus the fused recomputing backward (clam_engine.ClamSBFunction).  Calls that need the
+instance-clustering branch (`instance_eval=True`), active dropout or other feature sizes are composed from torch ops on
+the same device; CLAM_MB and the ungated Attn_Net are kept constructible for checkpoint
 compatibility and are not accelerated (out of scope).
 """
 import numpy as np
@@ -137,6 +139,14 @@ class CLAM_SB(nn.Module):
             if attention_only:
                 return res
             logits, Y_prob, Y_hat, A_raw, M = res
+            results_dict = {'features': M} if return_features else {}
+            return logits, Y_prob, Y_hat, A_raw, results_dict
+        fused_train_ok = (self.gate and not instance_eval and not attention_only and not h.requires_grad
+                          and not (self.training and self._has_active_dropout())
+                          and clam_engine.supports_fused_backward(self))
+        if fused_train_ok:
+            # training step (utils/core_utils.py:409-423): forward and backward both run the fused ragged-bag kernels
+            logits, Y_prob, Y_hat, A_raw, M = clam_engine.forward_single_autograd(self, h)
             results_dict = {'features': M} if return_features else {}
             return logits, Y_prob, Y_hat, A_raw, results_dict
         return self._forward_autograd(h, label, instance_eval, return_features, attention_only)

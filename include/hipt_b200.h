@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 2
+#define HB_ABI_VERSION 3
 
 /* GEMM epilogues */
 #define HB_EPI_BIAS_BF16 0        /* out_bf16[M,N]  = A W^T + bias                                  */
@@ -189,6 +189,27 @@ int hb_clam_sb_forward(const float* feats, const int32_t* bag_offsets, int n_bag
                        int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
                        float* a_raw, float* m_out, float* logits, float* y_prob, int64_t* y_hat, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step around CLAM_SB.forward for one bag (replaces autograd through models/model_clam.py:147-183 inside
+ * utils/core_utils.py:409-423 train_loop: loss.backward()).  192-d features, L1 <= 128, fp32.
+ * Inputs: the bag, the 10 weight tensors (order of hb_clam_sb_forward), a_raw [N] and m_pooled [L1] as produced by the
+ * forward, dlogits [C] = d loss / d logits, optional dm_ext [L1] (gradient arriving at M through results_dict
+ * ['features']) and da_ext [N] (gradient arriving at A_raw), or NULL.
+ * Output: grads_host[k] = device pointer of the gradient of weight k (same shapes), overwritten.
+ * workspace: (4 + L1) floats.  Gradients are summed over 64-instance chunks with atomics (fp32, order not fixed).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int hb_clam_sb_backward(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
+                        const float* m_pooled, const float* dlogits, const float* dm_ext, const float* da_ext,
+                        void* const* grads_host, int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* Multi-tensor Adam with L2 weight decay in one launch, torch.optim.Adam semantics (utils/utils.py:100-107 get_optim:
+ * optim.Adam(..., lr, weight_decay=reg)): g += wd p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ * p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps).  Up to 16 fp32 tensors; step counts from 1. */
+int hb_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                 const int* numel, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from oracle import hipt_oracle as O
 from tests.common import seeded_clam, seeded_modules
+from hipt_abmil_atec23_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 GOLD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -185,6 +186,92 @@ def test_clam_autograd_path_matches_fused(gold):
     with torch.no_grad():
         l2, _, _, a2, _ = model(bag)
     assert (logits - l2).abs().max().item() < 1e-4 and (a_raw - a2).abs().max().item() < 1e-4
+
+
+def _oracle_grads(sd_cpu, bag, label, extra=None):
+    """Gradients of CE(logits, label) (+ extra(logits, y_prob, a_raw, M)) through the CPU oracle (plain torch autograd)."""
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd_cpu.items() if not k.startswith("instance_classifiers")}
+    logits, y_prob, _, a_raw, res = O.clam_sb_forward(sd, bag, return_features=True)
+    loss = F.cross_entropy(logits, torch.tensor([label]))
+    if extra is not None:
+        loss = loss + extra(logits, y_prob, a_raw, res["features"])
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("size_arg,n", [("hipt_smaller", 64), ("hipt_smaller", 333), ("hipt_smallest", 50), ("hipt_small", 200),
+                                        ("hipt_medium", 130), ("hipt_big", 257)])
+def test_clam_training_step_gradients_match_reference(size_arg, n):
+    """a21: loss.backward() through CLAM_SB.forward runs the fused backward; gradients within 1e-3 (relative to the
+    largest entry of each tensor) of autograd through the CPU oracle; tolerance from BASELINE.json's north_star."""
+    model = seeded_clam(size_arg, 2).to(DEV).train()
+    sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    bag = torch.randn(n, 192, generator=torch.Generator().manual_seed(3))
+    logits, y_prob, y_hat, a_raw, res = model(bag.to(DEV), return_features=True)
+    assert logits.requires_grad and logits.grad_fn is not None and "ClamSB" in type(logits.grad_fn).__name__
+    extra = lambda lg, yp, ar, m: 0.3 * yp[0, 0] + 0.01 * (ar * ar).mean() + 0.1 * m.sum()
+    loss = F.cross_entropy(logits, torch.tensor([1], device=DEV)) + extra(logits, y_prob, a_raw, res["features"])
+    loss.backward()
+    ref_loss, ref = _oracle_grads(sd_cpu, bag, 1, extra)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3
+    for k, p in model.named_parameters():
+        if k.startswith("instance_classifiers"):
+            assert p.grad is None
+            continue
+        err = (p.grad.cpu() - ref[k]).abs().max().item()
+        assert err < 1e-3 * max(1e-2, ref[k].abs().max().item()), (k, err, ref[k].abs().max().item())
+
+
+def test_fused_adam_matches_torch_adam():
+    from hipt_abmil_atec23_b200.clam_engine import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(16, 192), (16,), (8, 16), (8,), (1, 8), (1,), (2, 16), (2,)]
+    p_ref = [torch.randn(s) for s in shapes]
+    p_our = [p.clone().to(DEV).requires_grad_(True) for p in p_ref]
+    p_ref = [p.requires_grad_(True) for p in p_ref]
+    ref = torch.optim.Adam(p_ref, lr=2e-3, weight_decay=1e-2)       # get_optim: Adam(lr=args.lr, weight_decay=args.reg)
+    our = FusedAdam(p_our, lr=2e-3, weight_decay=1e-2)
+    for step in range(4):
+        for a, b in zip(p_ref, p_our):
+            g = torch.randn(a.shape, generator=torch.Generator().manual_seed(100 * step + a.numel()))
+            a.grad = g.clone()
+            b.grad = g.to(DEV)
+        ref.step()
+        our.step()
+    for a, b in zip(p_ref, p_our):
+        assert (a.detach() - b.detach().cpu()).abs().max().item() < 1e-6
+
+
+def test_clam_three_training_steps_track_the_reference_loop():
+    """train_loop (utils/core_utils.py:409-423) for three bags: model(data) -> CE -> backward -> Adam step, fused kernels
+    against the same loop on the CPU oracle's parameters with torch.optim.Adam."""
+    from hipt_abmil_atec23_b200.clam_engine import FusedAdam
+    model = seeded_clam("hipt_smaller", 2).to(DEV).train()
+    ref_params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()
+                  if not k.startswith("instance_classifiers")}
+    opt = FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=2e-4, weight_decay=1e-5)
+    ref_opt = torch.optim.Adam(ref_params.values(), lr=2e-4, weight_decay=1e-5)
+    n0 = _lib.launch_count()
+    for step, (n, label) in enumerate([(70, 0), (129, 1), (64, 1)]):
+        bag = torch.randn(n, 192, generator=torch.Generator().manual_seed(20 + step))
+        logits, _, _, _, _ = model(bag.to(DEV))
+        loss = F.cross_entropy(logits, torch.tensor([label], device=DEV))
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        rl, _, _, _, _ = O.clam_sb_forward(ref_params, bag)
+        rloss = F.cross_entropy(rl, torch.tensor([label]))
+        rloss.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        assert abs(loss.item() - rloss.item()) < 1e-4
+    assert _lib.launch_count() - n0 >= 3 * 6                        # work table, scores, combine, prep, backward, adam per step
+    for k, p in model.named_parameters():
+        # attention_c.bias shifts every score equally: its gradient is identically zero (softmax is shift-invariant), what
+        # is left is rounding noise of either sign, and Adam turns any non-zero value into a full +-lr step -- in the
+        # reference as well.  Every other parameter must track.
+        if k in ref_params and not k.endswith("attention_c.bias"):
+            assert (p.detach().cpu() - ref_params[k].detach()).abs().max().item() < 2e-5, k
 
 
 def test_clam_ragged_bags_and_fold_ensemble():
