@@ -17,9 +17,9 @@ HEADERS = ["hb_ptx.cuh", "hb_internal.h", os.path.join("..", "..", "include", "h
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC",
-    "-shared",
+    "-Xcompiler", "-fPIC", "-diag-suppress", "128",
 ]
+OBJ_DIR = os.path.join(PKG_DIR, "lib", "obj")
 
 
 def _nvcc():
@@ -41,13 +41,26 @@ def build(force=False, verbose=False):
     """Compile every CUDA source into one shared library. Returns the library path."""
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    # one nvcc per translation unit, in parallel, then one link
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, log = [], ""
+    for src, obj, pr in procs:
+        out = pr.communicate()[0]
+        log += out
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + out)
+        objs.append(obj)
+    res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs,
+                         cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB_PATH
 
 

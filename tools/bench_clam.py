@@ -41,6 +41,30 @@ def run(size, folds, reps=20):
             "algorithmic_GBps": bytes_alg / ms / 1e6, "feature_MB": total * 768 / 1e6}
 
 
+def run_train(size, n, steps=50):
+    """One bag per step as in the reference's train_loop: forward, CE, backward (fused recomputing kernel), Adam (one launch)."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    model = CLAM_SB(size_arg=size, dropout=0.0, n_classes=2).to(dev).train()
+    opt = clam_engine.FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=2e-4, weight_decay=1e-5)
+    bag = torch.randn((n, 192), generator=torch.Generator().manual_seed(5)).to(dev)
+    label = torch.tensor([1], device=dev)
+    def step():
+        logits, _, _, _, _ = model(bag)
+        F.cross_entropy(logits, label).backward()
+        opt.step(); opt.zero_grad()
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps): step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"size": size, "train_step": True, "instances": n, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
+            "algorithmic_GBps": n * 1544 / ms / 1e6}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", default=None)
@@ -49,3 +73,5 @@ if __name__ == "__main__":
     for size in ([a.size] if a.size else ["hipt_smaller", "hipt_big"]):
         for folds in ([a.folds] if a.folds else [1, 5]):
             print(json.dumps(run(size, folds)))
+        for n in (50, 1000, 20000):
+            print(json.dumps(run_train(size, n)))
