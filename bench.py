@@ -284,15 +284,21 @@ def run_ours(args):
             ent["gbs"] = KERNEL_BYTES_PER_LAUNCH[name] / (ms / cnt * 1e-3) / 1e9
         kernels[name] = ent
     top = next(iter(kernels))
+    traffic = None                      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(top, {}).get("dram_bytes_per_launch")
+    except Exception:
+        traffic = None
     if top in KERNEL_FLOPS_PER_REGION:
         ach = kernels[top]["tflops"]
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                    "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
     else:
         ach = kernels[top].get("gbs", 0.0)
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"]}
     model_tflops = value / world * EXECUTED_FLOPS_PER_REGION / 1e12      # executed, not the reference's dense count
 
     line = {"metric": METRIC, "value": value, "unit": "regions/s", "n_gpus": world, "steps": args.steps,
@@ -307,6 +313,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "finite": ok},
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
 
+    if rank == 0 and world == 1:
+        line["clam_config4"] = clam_config4(dev, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, spent, info = cpu_reference_sample(patches=args.ref_patches, regions_per_slide=R)
         line["cpu_baseline"] = {"value": v, "unit": "regions/s", "cores": os.cpu_count(), "kind": "port",
@@ -316,6 +324,64 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def clam_config4(dev, peaks):
+    """BASELINE.json config 4 beside the headline: CLAM_SB(hipt_smaller) over 256 ragged bags of 50-20,000 x 192-d instances
+    in one launch (772 algorithmic bytes per instance: features read once + one score written), and the one-bag training
+    step (forward + fused backward + one-launch Adam).  HBM-bound path: reported as GB/s against the measured copy peak."""
+    import math
+    import torch.nn.functional as F
+    from hipt_abmil_atec23_b200 import clam_engine
+    from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+    g = torch.Generator().manual_seed(4)
+    lens = torch.exp(math.log(50) + torch.rand(256, generator=g) * (math.log(20000) - math.log(50))).long().clamp(50, 20000)
+    offs = torch.zeros(257, dtype=torch.int32)
+    offs[1:] = torch.cumsum(lens, 0)
+    total = int(offs[-1])
+    feats = torch.randn((total, 192), generator=torch.Generator().manual_seed(5)).to(dev)
+    offs_d, mx = offs.to(dev), int(lens.max())
+    out = {"bags": 256, "instances": total, "bytes_per_instance": 772, "feature_MB": total * 768 / 1e6}
+    for folds in (1, 5):
+        models = []
+        for f in range(folds):
+            torch.manual_seed(10 + f)
+            models.append(CLAM_SB(size_arg="hipt_smaller", dropout=0.0, n_classes=2).eval().to(dev))
+        fn = lambda: clam_engine.forward_bags(models, feats, offs_d, max_bag_len=mx, want=("logits", "y_prob", "y_hat"))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = total * (768 + 4 * folds) / ms / 1e6
+        out[f"folds{folds}"] = {"ms": ms, "bags_per_s": 256 / ms * 1e3, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+    torch.manual_seed(2)
+    model = CLAM_SB(size_arg="hipt_smaller", dropout=0.0, n_classes=2).to(dev).train()
+    opt = clam_engine.FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=2e-4, weight_decay=1e-5)
+    bag, label = feats[:1000].contiguous(), torch.tensor([1], device=dev)
+
+    def step():
+        logits = model(bag)[0]
+        F.cross_entropy(logits, label).backward()
+        opt.step()
+        opt.zero_grad()
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(30):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    out["train_step_1000_instances"] = {"ms": e0.elapsed_time(e1) / 30, "steps_per_s": 30e3 / e0.elapsed_time(e1),
+                                        "note": "one bag per step as in train_loop: launch / host-latency bound"}
+    return out
 
 
 def main():

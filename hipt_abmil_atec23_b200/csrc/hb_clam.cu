@@ -257,7 +257,9 @@ __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const
 #pragma unroll
             for (int c = 0; c < TN; ++c) acc[g][i][c] = f2_pack(0.f, 0.f);
     // 32-instance tiles (backward of the large heads): the second instance of the thread tile repeats the first
-    const uint32_t x0_addr = smem_u32(sX + lane * CL_XS), x1_addr = two_halves ? smem_u32(sX + (lane + 32) * CL_XS) : x0_addr;
+    // plain shared-memory loads (not asm): the compiler may hoist and batch them across the unrolled iterations
+    const ulonglong2* x0p = reinterpret_cast<const ulonglong2*>(sX + lane * CL_XS);
+    const ulonglong2* x1p = two_halves ? reinterpret_cast<const ulonglong2*>(sX + (lane + 32) * CL_XS) : x0p;
     for (int kc = 0; kc < 192; kc += KC) {
         // stage W1[:, kc:kc+KC] as sW[col][k] (row stride KC + 4): straight 16-byte copies
         {
@@ -275,20 +277,17 @@ __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const
         for (int g = 0; g < GPW; ++g) {
             const int grp = warp + nw * g;
             if (grp < n_groups) {
-                const uint32_t w_addr = smem_u32(sW + grp * TN * ldw);
-#pragma unroll 2
+                const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(sW + grp * TN * ldw);
+#pragma unroll 4
                 for (int k4 = 0; k4 < KC / 4; ++k4) {
-                    f32x2_t xa0, xa1, xb0, xb1;
-                    lds_2f2(x0_addr + (kc + 4 * k4) * 4, xa0, xa1);
-                    lds_2f2(x1_addr + (kc + 4 * k4) * 4, xb0, xb1);
+                    const ulonglong2 xa = x0p[kc / 4 + k4], xb = x1p[kc / 4 + k4];
 #pragma unroll
                     for (int c = 0; c < TN; ++c) {
-                        f32x2_t w0, w1;
-                        lds_2f2(w_addr + (c * ldw + 4 * k4) * 4, w0, w1);
-                        acc[g][0][c] = f2_fma(xa0, w0, acc[g][0][c]);
-                        acc[g][1][c] = f2_fma(xb0, w0, acc[g][1][c]);
-                        acc[g][0][c] = f2_fma(xa1, w1, acc[g][0][c]);
-                        acc[g][1][c] = f2_fma(xb1, w1, acc[g][1][c]);
+                        const ulonglong2 wv = wp[c * (ldw / 4) + k4];
+                        acc[g][0][c] = f2_fma(xa.x, wv.x, acc[g][0][c]);
+                        acc[g][1][c] = f2_fma(xb.x, wv.x, acc[g][1][c]);
+                        acc[g][0][c] = f2_fma(xa.y, wv.y, acc[g][0][c]);
+                        acc[g][1][c] = f2_fma(xb.y, wv.y, acc[g][1][c]);
                     }
                 }
             }
