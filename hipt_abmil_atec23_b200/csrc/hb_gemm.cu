@@ -587,7 +587,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int n0 = n_idx * BN;
             const int row = m0 + row_in_tile;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int c_first = (wg + it * NCHUNK) & (NWG - 1);
+            // chunk -> warpgroup assignment rotates with the tile count to balance NCHUNK % NWG != 0, except where the
+            // warpgroups' partial row statistics are summed afterwards: a rotating grouping would make a row's (sum, sum of
+            // squares) depend on WHICH tile of its CTA it was, i.e. on the rows sharing the launch (fp32 is not associative)
+            const int c_first = (RESID || OUT_TOKENS) ? wg : ((wg + it * NCHUNK) & (NWG - 1));
             [[maybe_unused]] float st_sum = 0.f, st_sq = 0.f;   // row statistics of what this thread produced in the tile
             const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 

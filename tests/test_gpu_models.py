@@ -128,6 +128,33 @@ def test_config1_full_region(gold, hipt):
     assert _cos(out2, out) > 0.9995
 
 
+def test_full_size_regions_are_grouping_invariant_and_deterministic(hipt):
+    """Size-independent properties at BASELINE.json's full size (3 x 4096 x 4096 uint8): a region's embedding does not
+    depend on which other regions share its launch (so a slide's bag is bit-identical for any rank count, SURVEY §8d config
+    3), repeated runs are bit-identical, and the pinned-host pipeline returns the bits of the device-resident one."""
+    from hipt_abmil_atec23_b200.pipeline import SlidePipeline
+    gen = torch.Generator(device=DEV).manual_seed(1003)
+    regs = torch.randint(0, 256, (3, 3, 4096, 4096), dtype=torch.uint8, device=DEV, generator=gen)
+    together = hipt.forward_regions_u8(regs)                       # launches of two regions + one region
+    again = hipt.forward_regions_u8(regs)
+    alone = torch.cat([hipt.forward_regions_u8(regs[i:i + 1]) for i in range(3)])
+    swapped = hipt.forward_regions_u8(regs.flip(0)).flip(0)
+    assert torch.isfinite(together).all()
+    assert torch.equal(together, again) and torch.equal(together, alone) and torch.equal(together, swapped)
+    clam = [seeded_clam("hipt_smaller", 10 + f).to(DEV) for f in range(5)]
+    pipe = SlidePipeline(hipt, clam)
+    dev_out = pipe.run_device(regs)
+    host_out = pipe.run_host(regs.cpu().pin_memory())
+    for k in ("features", "logits", "a_raw", "y_hat"):
+        assert torch.equal(dev_out[k].cpu(), host_out[k]), k
+    # pooling does not depend on the order of the instances in the bag (up to fp32 summation order)
+    perm = torch.tensor([2, 0, 1], device=DEV)
+    r1 = pipe._pool(dev_out["features"])
+    r2 = pipe._pool(dev_out["features"][perm])
+    assert (r1["logits"] - r2["logits"]).abs().max().item() < 1e-5
+    assert (r1["a_raw"][:, perm] - r2["a_raw"]).abs().max().item() < 1e-5
+
+
 def test_batch_gt_1_rejected_like_reference(hipt):
     with pytest.raises(RuntimeError):
         hipt(torch.zeros(2, 3, 256, 256, device=DEV))
