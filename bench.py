@@ -216,8 +216,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU path for --impl ours")
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        os.environ["NCCL_DEBUG"] = os.environ.get("HB_NCCL_DEBUG", "WARN")
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION / WARN: send its log to stderr so that stdout
+        # carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
