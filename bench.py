@@ -218,6 +218,9 @@ def run_ours(args):
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION / WARN: send its log to stderr so that stdout
         # carries the one JSON line only
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
