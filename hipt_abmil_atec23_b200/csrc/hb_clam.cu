@@ -240,9 +240,10 @@ __device__ __forceinline__ void lds_2f2(uint32_t addr, f32x2_t& a, f32x2_t& b) {
 // 64-bit pairs of a float4 load (x row of the instance, W1 row of the output column in nn.Linear's own [L1][192]
 // layout) and no value is ever duplicated into a pair; h1 = relu(lo + hi + bias).  Thread tile = 2 instances (lane,
 // lane + 32) x TN columns; warp w owns column groups w, w + nw, ...; W1 reads are warp-uniform broadcasts.
-template <int TN>
-__device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const float* b1, int L1,
+template <int TN, int L1T>
+__device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const float* b1, int L1_rt,
                                              const float* sX, float* sW, float* sH, int ldh, bool two_halves = true) {
+    const int L1 = L1T ? L1T : L1_rt;                        // L1T != 0: every stride below is a compile-time constant
     constexpr int GPW = (TN == 8) ? 2 : 1;                   // column groups per warp: L1 <= 16 (TN 4, 4 warps), L1 = 32 (TN 8,
                                                              // 4 warps), L1 = 64 / 128 (TN 8, 8 warps)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -314,14 +315,15 @@ __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const
     }
 }
 
-template <int TN>
+template <int TN, int L1T>
 __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __restrict__ feats,
                                                                      const int32_t* __restrict__ bag_offsets,
                                                                      const __grid_constant__ ClamModels models,
-                                                                     int n_models, int n_bags, int total_instances, int L1,
-                                                                     int D, const int32_t* __restrict__ prefix,
+                                                                     int n_models, int n_bags, int total_instances, int L1_rt,
+                                                                     int D_rt, const int32_t* __restrict__ prefix,
                                                                      const int32_t* __restrict__ work, int work_cap,
                                                                      float* __restrict__ a_raw, float* __restrict__ partials) {
+    const int L1 = L1T ? L1T : L1_rt, D = L1T ? L1T / 2 : D_rt;    // the HIPT heads have D = L1 / 2 (model_clam.py:81)
     extern __shared__ __align__(16) float smem_clam[];
     const int ldh = L1 + 4;
     float* sX = smem_clam;                                   // [64][196]
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
                              : idx < L1 + 3 * D ? w.p[6] + (idx - L1 - 2 * D) : w.p[7];
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sV + idx)), "l"(src) : "memory");
         }
-        clam_fc1_192<TN>(w.p[0], sV, L1, sX, sW, sH, ldh);
+        clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh);
         __syncthreads();
 
         // ---- gated attention score
@@ -550,7 +552,15 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         const size_t smem = (static_cast<size_t>(CL_CH) * CL_XS + clam_sw_floats(L1) + static_cast<size_t>(CL_CH) * (L1 + 4) +
                              2 * static_cast<size_t>(D) * L1 + 5 * CL_CH + 8 + L1 + 3 * D + 4) * sizeof(float);
         const int threads = L1 >= 64 ? 256 : CL_THREADS;
-        auto kern = (L1 <= 16) ? clam_scores192_kernel<4> : clam_scores192_kernel<8>;
+        // the five HIPT heads (model_clam.py:81: 8/4, 16/8, 32/16, 64/32, 128/64) get compile-time strides
+        auto kern = (L1 <= 16) ? clam_scores192_kernel<4, 0> : clam_scores192_kernel<8, 0>;
+        if (D * 2 == L1) {
+            if (L1 == 8) kern = clam_scores192_kernel<4, 8>;
+            else if (L1 == 16) kern = clam_scores192_kernel<4, 16>;
+            else if (L1 == 32) kern = clam_scores192_kernel<8, 32>;
+            else if (L1 == 64) kern = clam_scores192_kernel<8, 64>;
+            else if (L1 == 128) kern = clam_scores192_kernel<8, 128>;
+        }
         HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         ProfScope ps(10, stream);
         kern<<<work_cap, threads, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags, total_instances, L1, D,
@@ -621,11 +631,12 @@ __global__ void __launch_bounds__(256) clam_bwd_prep_kernel(const float* __restr
         for (int idx = tid; idx < sizes[k]; idx += 256) g.p[k][idx] = 0.f;
 }
 
-template <int TN>
+template <int TN, int L1T>
 __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restrict__ feats, int N,
                                                           const __grid_constant__ ClamModel w, const float* __restrict__ a_raw,
                                                           const float* __restrict__ dA_ext, const float* __restrict__ ctx,
-                                                          const __grid_constant__ ClamGrads g, int L1, int D, int ch) {
+                                                          const __grid_constant__ ClamGrads g, int L1_rt, int D_rt, int ch) {
+    const int L1 = L1T ? L1T : L1_rt, D = L1T ? L1T / 2 : D_rt;
     extern __shared__ __align__(16) float smem_clam[];
     const int ldh = L1 + 4, ldp = 2 * D + 1;
     float* sX = smem_clam;                                   // [ch][196]   ch = 64 instances, 32 for the large heads
@@ -664,7 +675,7 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
         for (int idx = tid; idx < L1; idx += nthreads)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sDM + idx)), "l"(ctx + 4 + idx) : "memory");
     }
-    clam_fc1_192<TN>(w.p[0], sV, L1, sX, sW, sH, ldh, ch == 64);   // waits for every cp.async above, ends with a __syncthreads
+    clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh, ch == 64);   // waits for every cp.async above, ends with a __syncthreads
     const float gmax = ctx[0], inv_total = ctx[1], s_dot = ctx[2];
     const float* ba = sV + L1; const float* bb = ba + D; const float* Wc = bb + D;
 
@@ -809,7 +820,14 @@ int clam_backward_launch(const float* feats, int N, const void* const* weights_h
                          2 * static_cast<size_t>(D) * L1 + 2 * static_cast<size_t>(ch) * ldp + 2 * ch +
                          ((L1 + 3 * D + 1 + 3) & ~3) + L1 + 8) * sizeof(float);
     if (smem > 220 * 1024) return set_error("hb_clam_sb_backward: shared memory %zu too large", smem);
-    auto kern = (L1 <= 16) ? clam_bwd192_kernel<4> : clam_bwd192_kernel<8>;
+    auto kern = (L1 <= 16) ? clam_bwd192_kernel<4, 0> : clam_bwd192_kernel<8, 0>;
+    if (D * 2 == L1) {
+        if (L1 == 8) kern = clam_bwd192_kernel<4, 8>;
+        else if (L1 == 16) kern = clam_bwd192_kernel<4, 16>;
+        else if (L1 == 32) kern = clam_bwd192_kernel<8, 32>;
+        else if (L1 == 64) kern = clam_bwd192_kernel<8, 64>;
+        else if (L1 == 128) kern = clam_bwd192_kernel<8, 128>;
+    }
     HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ProfScope ps(13, stream);
     kern<<<(N + ch - 1) / ch, threads, smem, stream>>>(feats, N, w, a_raw, dA_ext, ctx, g, L1, D, ch);
