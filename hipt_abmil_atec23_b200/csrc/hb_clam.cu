@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
     float* sW = sX + CL_CH * CL_XS;                          // [L1][KC + 4]  W1 slice
     float* sH = sW + clam_sw_floats(L1);                     // [64][L1 + 4]
     float* sG = sH + CL_CH * ldh;                            // [2][D][L1]    Wa, Wb
-    float* sA = sG + 2 * D * L1;                             // [4][64]       per-part score partials
-    float* sE = sA + 4 * CL_CH;                              // [64]
+    float* sA = sG + 2 * D * L1;                             // [max(4, D/4)][64]  per-task score partials (reused: chunk sums)
+    float* sE = sA + (D / 4 > 4 ? D / 4 : 4) * CL_CH;        // [64]
     float* red = sE + CL_CH;                                 // [8]
     float* sV = red + 8;                                     // b1 [L1] | ba [D] | bb [D] | Wc [D] | bc [1]
     const int nthreads = blockDim.x;
@@ -359,7 +359,6 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
     }
     __syncthreads();
 
-    const int parts = nthreads >> 6;                         // gate: `parts` threads per instance, each D / parts units
     const int inst = tid & 63, half = tid >> 6;
     const bool valid = half == 0 && inst < n_valid;
     for (int mi = 0; mi < n_models; ++mi) {
@@ -378,29 +377,53 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
         clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh);
         __syncthreads();
 
-        // ---- gated attention score
+        // ---- gated attention score, register-tiled like the first Linear: warp task = 4 gate units (their Wa and Wb rows)
+        // x the 64 instances (lane, lane + 32), FMAs packed along L1 on natural float4 halves; every task leaves its share
+        // of the score, sum_d Wc[d] tanh(a_d) sigmoid(b_d), in sA[task][instance]
+        const int n_gt = D / 4;
         {
             const float* ba = sV + L1; const float* bb = ba + D; const float* Wc = bb + D;
-            const uint32_t h_addr = smem_u32(sH + inst * ldh);
-            const int dn = D / parts, d0 = half * dn;
-            float A = 0.f;
-            for (int d = d0; d < d0 + dn; ++d) {
-                float a0 = ba[d], a1 = 0.f, b0 = bb[d], b1v = 0.f;
-                const uint32_t wa_addr = smem_u32(sG + d * L1), wb_addr = smem_u32(sG + (D + d) * L1);
-#pragma unroll 4
-                for (int j = 0; j < L1; j += 4) {
-                    const float4 h4 = lds_f4(h_addr + j * 4);
-                    const float4 wa = lds_f4(wa_addr + j * 4), wb = lds_f4(wb_addr + j * 4);
-                    a0 = fmaf(wa.x, h4.x, a0); a1 = fmaf(wa.y, h4.y, a1); a0 = fmaf(wa.z, h4.z, a0); a1 = fmaf(wa.w, h4.w, a1);
-                    b0 = fmaf(wb.x, h4.x, b0); b1v = fmaf(wb.y, h4.y, b1v); b0 = fmaf(wb.z, h4.z, b0); b1v = fmaf(wb.w, h4.w, b1v);
+            const int warp = tid >> 5, lane = tid & 31, nw = nthreads >> 5;
+            const ulonglong2* h0p = reinterpret_cast<const ulonglong2*>(sH + lane * ldh);
+            const ulonglong2* h1p = reinterpret_cast<const ulonglong2*>(sH + (lane + 32) * ldh);
+            for (int task = warp; task < n_gt; task += nw) {
+                f32x2_t acc[2][8];                           // [instance][a0..a3, b0..b3]
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[i][u] = f2_pack(0.f, 0.f);
+                const ulonglong2* wap = reinterpret_cast<const ulonglong2*>(sG + (task * 4) * L1);
+                const ulonglong2* wbp = reinterpret_cast<const ulonglong2*>(sG + (D + task * 4) * L1);
+#pragma unroll 2
+                for (int j4 = 0; j4 < L1 / 4; ++j4) {
+                    const ulonglong2 ha = h0p[j4], hb = h1p[j4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const ulonglong2 wa = wap[u * (L1 / 4) + j4], wb = wbp[u * (L1 / 4) + j4];
+                        acc[0][u] = f2_fma(ha.x, wa.x, acc[0][u]);         acc[1][u] = f2_fma(hb.x, wa.x, acc[1][u]);
+                        acc[0][u] = f2_fma(ha.y, wa.y, acc[0][u]);         acc[1][u] = f2_fma(hb.y, wa.y, acc[1][u]);
+                        acc[0][4 + u] = f2_fma(ha.x, wb.x, acc[0][4 + u]); acc[1][4 + u] = f2_fma(hb.x, wb.x, acc[1][4 + u]);
+                        acc[0][4 + u] = f2_fma(ha.y, wb.y, acc[0][4 + u]); acc[1][4 + u] = f2_fma(hb.y, wb.y, acc[1][4 + u]);
+                    }
                 }
-                A = fmaf(Wc[d], tanhf(a0 + a1) * (1.0f / (1.0f + expf(-(b0 + b1v)))), A);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float A = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int d = task * 4 + u;
+                        float a0, a1, b0, b1v;
+                        f2_unpack(acc[i][u], a0, a1);
+                        f2_unpack(acc[i][4 + u], b0, b1v);
+                        A = fmaf(Wc[d], tanhf(a0 + a1 + ba[d]) * (1.0f / (1.0f + expf(-(b0 + b1v + bb[d])))), A);
+                    }
+                    sA[task * CL_CH + lane + 32 * i] = A;
+                }
             }
-            sA[half * CL_CH + inst] = A;
         }
         __syncthreads();
         float A = sV[L1 + 3 * D];
-        for (int q = 0; q < parts; ++q) A += sA[q * CL_CH + inst];
+        for (int q = 0; q < n_gt; ++q) A += sA[q * CL_CH + inst];
         if (valid) a_raw[static_cast<size_t>(mi) * total_instances + start + i0 + inst] = A;
 
         // ---- chunk-local softmax partial
@@ -550,7 +573,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     HB_CUDA_OK(cudaGetLastError());
     if (max_chunks > 0 && clam_is192(L0, L1, D)) {
         const size_t smem = (static_cast<size_t>(CL_CH) * CL_XS + clam_sw_floats(L1) + static_cast<size_t>(CL_CH) * (L1 + 4) +
-                             2 * static_cast<size_t>(D) * L1 + 5 * CL_CH + 8 + L1 + 3 * D + 4) * sizeof(float);
+                             2 * static_cast<size_t>(D) * L1 + ((D / 4 > 4 ? D / 4 : 4) + 1) * CL_CH + 8 + L1 + 3 * D + 4) * sizeof(float);
         const int threads = L1 >= 64 ? 256 : CL_THREADS;
         // the five HIPT heads (model_clam.py:81: 8/4, 16/8, 32/16, 64/32, 128/64) get compile-time strides
         auto kern = (L1 <= 16) ? clam_scores192_kernel<4, 0> : clam_scores192_kernel<8, 0>;
