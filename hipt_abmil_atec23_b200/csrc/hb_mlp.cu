@@ -328,9 +328,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
             for (int c = g; c < MLP_KB; c += 4) {
                 const bool last = (c + 4 >= MLP_KB);
-                const float bl0 = __ldg(b2 + c * 64 + lane), bl1 = __ldg(b2 + c * 64 + 32 + lane);
+                const float4* b4 = reinterpret_cast<const float4*>(b2 + c * 64);        // broadcast loads (L1-resident)
                 const uint32_t a_row = smem_u32(sA + c * 16384) + row_in_tile * 128;
-                float st_sum = 0.f, st_sq = 0.f;
+                f32x2_t st_sum2 = f2_pack(0.f, 0.f), st_sq2 = st_sum2;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v[32];
@@ -341,7 +341,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         __syncwarp();
                         if (lane == 0) arrive_leader(o_empty);
                     }
-                    const float bl = h ? bl1 : bl0;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t addr = a_row + (((h * 4 + q) ^ sw) << 4);
@@ -349,21 +348,29 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                      : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(addr));
                         const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-                        float o[8];
+                        const float4 ba = __ldg(b4 + h * 8 + 2 * q), bb = __ldg(b4 + h * 8 + 2 * q + 1);
+                        const f32x2_t bias2[4] = {f2_pack(ba.x, ba.y), f2_pack(ba.z, ba.w), f2_pack(bb.x, bb.y), f2_pack(bb.z, bb.w)};
+                        uint32_t pk[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float res = (e & 1) ? __uint_as_float(rw[e >> 1] & 0xffff0000u) : __uint_as_float(rw[e >> 1] << 16);
-                            const float bb = __shfl_sync(0xffffffffu, bl, 8 * q + e);
-                            o[e] = res + __uint_as_float(v[8 * q + e]) + bb;
-                            st_sum += o[e];
-                            st_sq = fmaf(o[e], o[e], st_sq);
+                        for (int e = 0; e < 4; ++e) {            // packed pairs: (residual + bias) + accumulator, same rounding
+                            const f32x2_t res2 = f2_pack(__uint_as_float(rw[e] << 16), __uint_as_float(rw[e] & 0xffff0000u));
+                            const f32x2_t acc2 = f2_pack(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]));
+                            const f32x2_t o2 = f2_add(f2_add(res2, acc2), bias2[e]);
+                            st_sum2 = f2_add(st_sum2, o2);
+                            st_sq2 = f2_fma(o2, o2, st_sq2);
+                            float o0, o1;
+                            f2_unpack(o2, o0, o1);
+                            pk[e] = pack_bf16x2(o0, o1);
                         }
-                        sts_u4(addr, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+                        sts_u4(addr, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                     }
                 }
-                if (row < M)
-                    *reinterpret_cast<float2*>(stats_out + (static_cast<size_t>(c) * stats_stride + row) * 2) = make_float2(st_sum, st_sq);
+                if (row < M) {
+                    float s0, s1, q0, q1;
+                    f2_unpack(st_sum2, s0, s1);
+                    f2_unpack(st_sq2, q0, q1);
+                    *reinterpret_cast<float2*>(stats_out + (static_cast<size_t>(c) * stats_stride + row) * 2) = make_float2(s0 + s1, q0 + q1);
+                }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
