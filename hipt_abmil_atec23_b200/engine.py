@@ -202,6 +202,31 @@ class VitEngine:
                 done += cur
         return out
 
+    # ------------------------------------------------------------------------------- attention maps (heatmap helpers)
+    def last_selfattention(self, run_prefix, n_seq, seq_len):
+        """Attention probabilities of the LAST block, [n_seq, heads, seq_len, seq_len] fp32 (get_last_selfattention,
+        vision_transformer.py:255-262 / vision_transformer4k.py:248-255; consumer: hipt_heatmap_utils.py:328-335).
+        `run_prefix()` launches the forward with the plan limited to blocks 0 .. depth-2, which leaves the residual stream
+        entering the last block in the workspace; norm1, the qkv Linear and the softmax of that one block are torch ops on
+        its rows (this is the visualisation path, SURVEY.md §8f rank 4, not the extraction hot path)."""
+        import torch.nn.functional as F
+        blk = self._module.blocks[-1]
+        if self.depth > 1:
+            self.set_depth_limit(self.depth - 1)
+        try:
+            run_prefix()
+        finally:
+            self.set_depth_limit(0)
+        if self.depth == 1:
+            raise NotImplementedError("attention-map export needs at least two blocks")
+        x = self.buffer(1, n_seq * seq_len, self.dim, torch.bfloat16).float().view(n_seq, seq_len, self.dim)
+        y = F.layer_norm(x, (self.dim,), blk.norm1.weight.float(), blk.norm1.bias.float(), self.eps)
+        qkv = F.linear(y, blk.attn.qkv.weight.float(), blk.attn.qkv.bias.float() if blk.attn.qkv.bias is not None else None)
+        hd = self.dim // self.heads
+        qkv = qkv.reshape(n_seq, seq_len, 3, self.heads, hd).permute(2, 0, 3, 1, 4)
+        att = (qkv[0] @ qkv[1].transpose(-2, -1)) * (hd ** -0.5)
+        return att.softmax(dim=-1)
+
     # -------------------------------------------------------------------------------------------- test hooks
     def set_depth_limit(self, n):
         _lib.check(self.lib.hb_vit_plan_set_depth_limit(self.plan, n))

@@ -123,8 +123,17 @@ class VisionTransformer(nn.Module):
         ps = self.patch_embed.patch_size
         return interpolate_pos_table(self.pos_embed, npatch, w // ps, h // ps).unsqueeze(0).to(x.device)
 
+    @torch.no_grad()
     def get_last_selfattention(self, x):
-        raise NotImplementedError("attention-map export is outside the accelerated hot path (SURVEY.md §8f rank 4)")
+        """[B, 3, 256, 256] -> attention probabilities of the last block [B, heads, 257, 257] (vision_transformer.py:255-262)."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 256, 256):
+            raise RuntimeError(f"ViT-256 CUDA path expects [B,3,256,256] inputs, got {tuple(x.shape)}")
+        eng = self._engine(x.device)
+        outs = []
+        for b0 in range(0, x.shape[0], eng.max_seqs):
+            xb = x[b0:b0 + eng.max_seqs].contiguous()
+            outs.append(eng.last_selfattention(lambda: eng.forward_patches(xb), xb.shape[0], 257))
+        return torch.cat(outs)
 
     def get_intermediate_layers(self, x, n=1):
         raise NotImplementedError("intermediate-layer export is outside the accelerated hot path")

@@ -52,8 +52,21 @@ class VisionTransformer4K(nn.Module):
     def interpolate_pos_encoding(self, x, w, h):
         return interpolate_pos_table(self.pos_embed, x.shape[1] - 1, w, h).unsqueeze(0).to(x.device)
 
+    @torch.no_grad()
     def get_last_selfattention(self, x):
-        raise NotImplementedError("attention-map export is outside the accelerated hot path (SURVEY.md §8f rank 4)")
+        """[B, 384, w, h] -> attention probabilities of the last block [B, heads, 1+w*h, 1+w*h] (vision_transformer4k.py:248-255)."""
+        if x.dim() != 4 or x.shape[1] != self.input_embed_dim:
+            raise RuntimeError(f"ViT-4K CUDA path expects [B,{self.input_embed_dim},w,h] inputs, got {tuple(x.shape)}")
+        B, C, w, h = x.shape
+        eng = self._engine(x.device)
+        cap = max(1, eng.max_rows // (w * h + 1))
+        outs = []
+        for b0 in range(0, B, cap):
+            xb = x[b0:b0 + cap]
+            n = xb.shape[0]
+            tokens = xb.flatten(2, 3).transpose(1, 2).reshape(n * w * h, C).to(torch.bfloat16).contiguous()
+            outs.append(eng.last_selfattention(lambda: eng.forward_grid(tokens, n, w, h), n, w * h + 1))
+        return torch.cat(outs)
 
     def get_intermediate_layers(self, x, n=1):
         raise NotImplementedError("intermediate-layer export is outside the accelerated hot path")

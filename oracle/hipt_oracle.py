@@ -68,6 +68,22 @@ def block(sd, pre, x, heads, eps=1e-6):
     return x + y
 
 
+def last_selfattention(sd, tokens, heads):
+    """get_last_selfattention, vision_transformer.py:255-262 / vision_transformer4k.py:248-255: blocks 0..depth-2 as usual,
+    then the last block's attention probabilities (Block.forward(return_attention=True) :147-149) [B, heads, N, N]."""
+    n = _depth(sd)
+    t = tokens
+    for i in range(n - 1):
+        t = block(sd, f"blocks.{i}.", t, heads)
+    pre = f"blocks.{n - 1}."
+    C = t.shape[-1]
+    y = F.layer_norm(t, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
+    B, N, _ = y.shape
+    hd = C // heads
+    qkv = F.linear(y, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"]).reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    return ((qkv[0] @ qkv[1].transpose(-2, -1)) * (hd ** -0.5)).softmax(dim=-1)
+
+
 def _depth(sd):
     return 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
 

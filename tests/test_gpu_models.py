@@ -155,6 +155,30 @@ def test_full_size_regions_are_grouping_invariant_and_deterministic(hipt):
     assert (r1["a_raw"][:, perm] - r2["a_raw"]).abs().max().item() < 1e-5
 
 
+def test_last_selfattention_maps(hipt):
+    """get_last_selfattention of both ViTs (used by the reference's hipt_heatmap_utils.get_region_attention_scores :328-335,
+    which reads attention[:, :, 0, 1:]) against the oracle; bf16 residual stream -> probabilities within 2e-3."""
+    px = torch.randint(0, 256, (3, 3, 256, 256), dtype=torch.uint8, generator=torch.Generator().manual_seed(31))
+    x = O.eval_transforms_u8(px)
+    sd = {k: v.detach().cpu() for k, v in hipt.model256.state_dict().items()}
+    att = hipt.model256.get_last_selfattention(x.to(DEV)).cpu()
+    ref = O.last_selfattention(sd, O.vit256_tokens(sd, x), 6)
+    assert att.shape == (3, 6, 257, 257)
+    assert (att.sum(-1) - 1).abs().max().item() < 1e-4
+    assert (att - ref).abs().max().item() < 2e-3, (att - ref).abs().max().item()
+    assert (att[:, :, 0, 1:] - ref[:, :, 0, 1:]).abs().max().item() < 2e-3
+    # the regular forward is unaffected by the depth-limited pass
+    out1 = hipt.model256(x.to(DEV))
+    hipt.model256.get_last_selfattention(x.to(DEV))
+    assert torch.equal(out1, hipt.model256(x.to(DEV)))
+    sd4 = {k: v.detach().cpu() for k, v in hipt.model4k.state_dict().items()}
+    grid = torch.randn(2, 384, 16, 16, generator=torch.Generator().manual_seed(32))
+    att4 = hipt.model4k.get_last_selfattention(grid.to(DEV)).cpu()
+    ref4 = O.last_selfattention(sd4, O.vit4k_tokens(sd4, grid), 6)
+    assert att4.shape == (2, 6, 257, 257)
+    assert (att4 - ref4).abs().max().item() < 2e-3, (att4 - ref4).abs().max().item()
+
+
 def test_batch_gt_1_rejected_like_reference(hipt):
     with pytest.raises(RuntimeError):
         hipt(torch.zeros(2, 3, 256, 256, device=DEV))
