@@ -54,7 +54,7 @@ KERNEL_FLOPS_PER_REGION = {
 }
 VIT4K_FLOPS_PER_REGION = 1_706_365_440
 EXECUTED_FLOPS_PER_REGION = sum(KERNEL_FLOPS_PER_REGION.values()) + VIT4K_FLOPS_PER_REGION
-KERNEL_BYTES_PER_LAUNCH = {            # HBM-bound row kernels: bytes that must move per launch
+KERNEL_BYTES_PER_LAUNCH = {            # HBM-bound row kernels: bytes that must move per region
     "im2col": 3 * 4096 * 4096 * (1 + 2),
 }
 METRIC = "4K regions/sec (HIPT_4K extraction + CLAM_SB 5-fold pooling)"
@@ -286,8 +286,8 @@ def run_ours(args):
                "avg_launch_us": 1000.0 * ms / cnt}
         if name in KERNEL_FLOPS_PER_REGION:        # executed FLOPs of this kernel per step / its measured time per step
             ent["tflops"] = KERNEL_FLOPS_PER_REGION[name] * R / (ms / args.steps * 1e-3) / 1e12
-        if name in KERNEL_BYTES_PER_LAUNCH:
-            ent["gbs"] = KERNEL_BYTES_PER_LAUNCH[name] / (ms / cnt * 1e-3) / 1e9
+        if name in KERNEL_BYTES_PER_LAUNCH:       # bytes per region; one timed scope covers the regions of one ViT-256 launch
+            ent["gbs"] = KERNEL_BYTES_PER_LAUNCH[name] * R * args.steps / (ms * 1e-3) / 1e9
         kernels[name] = ent
     top = next(iter(kernels))
     traffic = None                      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
