@@ -320,6 +320,7 @@ def run_ours(args):
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
 
     if rank == 0 and world == 1:
+        line["vit256_config2"] = vit256_config2(hipt, dev, peaks)
         line["clam_config4"] = clam_config4(dev, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         vals, spent, info = [], 0.0, {}
@@ -336,6 +337,29 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def vit256_config2(hipt, dev, peaks):
+    """BASELINE.json config 2: the ViT-256 (ViT-S/16) stage alone on a batch of 256 synthetic 256 x 256 patches (uint8,
+    normalisation folded into the patch embed), bf16; patches/s and executed TFLOP/s against the sustained bf16 peak."""
+    from hipt_abmil_atec23_b200.hipt_model_utils import HIPT_MEAN, HIPT_STD
+    eng = hipt.model256._engine(dev)
+    px = torch.randint(0, 256, (256, 3, 256, 256), dtype=torch.uint8, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    fn = lambda: eng.forward_patches(px, mean=HIPT_MEAN, std=HIPT_STD, want_f32=False)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    flops = EXECUTED_FLOPS_PER_REGION - VIT4K_FLOPS_PER_REGION
+    return {"batch": 256, "ms": ms, "patches_per_s": 256 / ms * 1e3, "tflops_executed": flops / ms / 1e9,
+            "frac_of_bf16_sustained": flops / ms / 1e9 / peaks["tflops_sustained"],
+            "note": "one launch sequence over 256 patches (half the two-region launch the slide path uses)"}
 
 
 def clam_config4(dev, peaks):
