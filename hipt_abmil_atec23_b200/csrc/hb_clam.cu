@@ -22,6 +22,7 @@
 // Kernel 2 (combine): one CTA per (bag, model) merges the chunk partials with the usual max-rescaling and applies the
 // bag classifier.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "hb_ptx.cuh"
@@ -451,6 +452,278 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core scores kernel (192-d features, L1 = 16 or 32, n_models * L1 <= 80): the first Linear of EVERY fold in one
+// tcgen05 GEMM per 128-instance tile, at fp32-level accuracy by operand splitting.
+//
+// kind::tf32 reads fp32 words and ignores the low 13 mantissa bits, i.e. it multiplies hi(x) = x & 0xFFFFE000.  With
+// lo(x) = x - hi(x) (exact in fp32):   x w = hi(x) hi(w) + hi(x) lo(w) + lo(x) hi(w) + O(2^-21 |x w|)
+//   term 1: A = X tile as loaded by TMA,           B = W1        (the hardware truncates both)
+//   term 2: A = the same X tile,                   B = lo(W1)    (precomputed per launch in shared memory)
+//   term 3: A = lo(X) tile (written by 4 warps),   B = W1
+// All folds' W1 are stacked along N (N = n_models * L1), so the 98 KB feature tile is read from HBM once AND multiplied once
+// for the whole ensemble.  Persistent CTAs walk the (bag, 128-instance chunk) work table.
+//   warp 0     TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a 2/3-stage ring
+//   warp 1     MMA issuer (12 MMAs M128 x N x K8 per slice), double-buffered TMEM accumulator
+//   warps 2-9  lo(X): two threads per row (four 16-byte pieces each), swizzled pieces in, same positions out
+//   warps 10-13, 14-17  two epilogue warpgroups (even / odd tiles = TMEM buffer 0 / 1): thread = row; per fold: TMEM -> +b1,
+//              ReLU -> gate -> score -> chunk softmax partials
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 576, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 6;
+__host__ __device__ inline bool clam_tc_ok(int L0, int L1, int D, int n_models) {
+    return L0 == 192 && (L1 == 16 || L1 == 32) && D * 2 == L1 && n_models * L1 <= 80;
+}
+// shared memory besides the X ring: both W operands, fold constants, two epilogue scratch areas, barriers, alignment slack
+__host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int D) {
+    const int ntot = n_models * L1;
+    return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 +
+           (static_cast<size_t>(n_models) * ((((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3)) + 2 * (8 + 128 + 128 * (L1 + 1) + 2)) * sizeof(float) + 32 * 8;
+}
+// as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
+__host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
+    const long long room = 232448LL - static_cast<long long>(clam_tc_fixed_bytes(n_models, L1, D));
+    int st = static_cast<int>(room / (2 * TC_SLICE_BYTES));
+    return st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+}
+// floats of per-fold epilogue constants: b1 [L1] | Wa [D][L1] | Wb [D][L1] | ba [D] | bb [D] | Wc [D] | bc
+__host__ __device__ inline int clam_tc_fold_floats(int L1, int D) { return ((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3; }
+
+template <int L1>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* __restrict__ bag_offsets,
+                      const __grid_constant__ ClamModels models, int n_models, int n_bags, int total_instances,
+                      const int32_t* __restrict__ prefix, const int32_t* __restrict__ work, int work_cap,
+                      float* __restrict__ a_raw, float* __restrict__ partials) {
+    constexpr int D = L1 / 2;
+    extern __shared__ uint8_t smem_raw_tc[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+    const int ntot = n_models * L1;
+    const int stages = clam_tc_stages(n_models, L1, D);
+    uint8_t* sXr = smem;                                        // [stages][X 16 KB | lo(X) 16 KB]
+    uint8_t* sWh = sXr + stages * 2 * TC_SLICE_BYTES;           // [6 slices][ntot rows][128 B]  W1 (all folds stacked)
+    uint8_t* sWl = sWh + TC_NSL * ntot * 128;                   // same, lo(W1)
+    float* sC = reinterpret_cast<float*>(sWl + TC_NSL * ntot * 128);          // [n_models][fold constants]
+    const int fold_floats = clam_tc_fold_floats(L1, D);
+    constexpr int SCR = 8 + 128 + 128 * (L1 + 1) + 2;           // per epilogue warpgroup: [8] reductions | [128] column partials |
+    float* sScr = sC + n_models * fold_floats;                  //                         [128][L1 + 1] e_i * h1_i
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + 2 * SCR);
+    uint64_t* x_full = bars;              // [6]
+    uint64_t* x_empty = bars + 6;         // [6]  MMA commit
+    uint64_t* lo_full = bars + 12;        // [6]  256 split threads
+    uint64_t* acc_full = bars + 18;       // [2]
+    uint64_t* acc_empty = bars + 20;      // [2]  128 epilogue threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&map_x);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&lo_full[i], 256); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_mbar_init();
+    }
+    const uint32_t tmem_cols = (2 * ntot <= 32) ? 32 : (2 * ntot <= 64) ? 64 : (2 * ntot <= 128) ? 128 : 256;
+    if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+    // W1 (every fold) -> shared memory in the K-major SWIZZLE_128B layout of the B operand, hi as is, lo = w - trunc(w);
+    // fold constants behind it
+    for (int idx = tid; idx < ntot * 192; idx += TC_THREADS) {
+        const int n = idx / 192, k = idx - n * 192;
+        const int m = n / L1, j = n - m * L1;
+        const float w = __ldg(models.m[m].p[0] + j * 192 + k);
+        const int sl = k >> 5, kk = k & 31;
+        const uint32_t off = sl * ntot * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+        *reinterpret_cast<float*>(sWh + off) = w;
+        *reinterpret_cast<float*>(sWl + off) = w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    }
+    for (int m = 0; m < n_models; ++m) {
+        float* c = sC + m * fold_floats;
+        const ClamModel& w = models.m[m];
+        for (int i = tid; i < L1; i += TC_THREADS) c[i] = __ldg(w.p[1] + i);
+        for (int i = tid; i < D * L1; i += TC_THREADS) { c[L1 + i] = __ldg(w.p[2] + i); c[L1 + D * L1 + i] = __ldg(w.p[4] + i); }
+        for (int i = tid; i < D; i += TC_THREADS) {
+            c[L1 + 2 * D * L1 + i] = __ldg(w.p[3] + i); c[L1 + 2 * D * L1 + D + i] = __ldg(w.p[5] + i);
+            c[L1 + 2 * D * L1 + 2 * D + i] = __ldg(w.p[6] + i);
+        }
+        if (tid == 0) c[L1 + 2 * D * L1 + 3 * D] = __ldg(w.p[7]);
+    }
+    fence_proxy_async_smem();                                   // generic writes of W -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_work = prefix[n_bags];
+    const uint32_t acc_stride = tmem_cols / 2;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+                const int bag = work[2 * wi], chunk = work[2 * wi + 1];
+                const int row0 = bag_offsets[bag] + chunk * TC_M;
+                for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
+                    const uint32_t st = q % stages, use = q / stages;
+                    mbar_wait(&x_empty[st], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&x_full[st], TC_SLICE_BYTES);
+                    tma_load_2d(sXr + st * 2 * TC_SLICE_BYTES, &map_x, &x_full[st], sl * TC_KS, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = umma_idesc_tf32(TC_M, ntot);
+        uint32_t q = 0, t = 0;
+        for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x, ++t) {
+            const uint32_t b = t & 1;
+            if (t >= 2) mbar_wait(&acc_empty[b], ((t >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + b * acc_stride;
+            for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
+                const uint32_t st = q % stages, use = q / stages;
+                const uint64_t dx = umma_desc_k128(smem_u32(sXr + st * 2 * TC_SLICE_BYTES));
+                const uint64_t dl = umma_desc_k128(smem_u32(sXr + st * 2 * TC_SLICE_BYTES + TC_SLICE_BYTES));
+                const uint64_t dwh = umma_desc_k128(smem_u32(sWh + sl * ntot * 128));
+                const uint64_t dwl = umma_desc_k128(smem_u32(sWl + sl * ntot * 128));
+                mbar_wait(&x_full[st], use & 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        umma_tf32_ss(d_tmem, dx + 2 * kk, dwh + 2 * kk, idesc, (sl | kk) != 0);
+                        umma_tf32_ss(d_tmem, dx + 2 * kk, dwl + 2 * kk, idesc, 1);
+                    }
+                }
+                __syncwarp();
+                mbar_wait(&lo_full[st], use & 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_tf32_ss(d_tmem, dl + 2 * kk, dwh + 2 * kk, idesc, 1);
+                    umma_commit(&x_empty[st]);
+                    if (sl == TC_NSL - 1) umma_commit(&acc_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 10) {
+        // ------------------------------------------------------------------------------------------ lo(X)
+        const int r = ((warp - 2) & 3) * 32 + lane, half = (warp - 2) >> 2;
+        uint32_t q = 0;
+        for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+            for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
+                const uint32_t st = q % stages, use = q / stages;
+                const uint32_t xs = smem_u32(sXr + st * 2 * TC_SLICE_BYTES) + r * 128, ls = xs + TC_SLICE_BYTES;
+                mbar_wait(&x_full[st], use & 1);
+#pragma unroll
+                for (int c0 = half * 4; c0 < half * 4 + 4; ++c0) {
+                    const int c = c0 ^ (r & 7);                  // lo() is element-wise, so any piece order works: this one
+                                                                 // keeps the 8 rows of a quarter-warp on 8 different pieces
+                    const uint4 v = lds_u4(xs + c * 16);
+                    uint4 o;
+                    o.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+                    o.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+                    o.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+                    o.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+                    sts_u4(ls + c * 16, o);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&lo_full[st]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ epilogue
+        const int eg = (warp - 10) >> 2;                          // epilogue warpgroup = TMEM buffer = tile parity
+        const int et = (tid - 320) & 127;                        // 0..127 inside the warpgroup
+        const int r = (warp & 3) * 32 + lane;                    // tile row = TMEM lane (warp % 4 = lane quadrant)
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        float* sRed = sScr + eg * SCR;
+        float* sPart = sRed + 8;
+        float* sE = sPart + 128;
+        const uint32_t bar_id = 2 + eg;
+        for (uint32_t t = eg; static_cast<long long>(blockIdx.x) + static_cast<long long>(t) * gridDim.x < n_work; t += 2) {
+            const int wi = blockIdx.x + t * gridDim.x;
+            const uint32_t b = eg;
+            const int bag = work[2 * wi], chunk = work[2 * wi + 1];
+            const int start = bag_offsets[bag];
+            const int n_valid = min(TC_M, bag_offsets[bag + 1] - start - chunk * TC_M);
+            const bool valid = r < n_valid;
+            mbar_wait(&acc_full[b], (t >> 1) & 1);
+            tc_fence_after();
+            for (int m = 0; m < n_models; ++m) {
+                const float* c = sC + m * fold_floats;
+                float h[L1];
+                {
+                    uint32_t v[L1];
+                    if constexpr (L1 == 16) tmem_ld_32x16(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[16]>(v));
+                    else tmem_ld_32x32(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[32]>(v));
+                    tmem_ld_wait();
+                    if (m == n_models - 1) {                     // last TMEM read of the tile: hand the accumulator back
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[b]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < L1; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + c[j], 0.f);
+                }
+                const float* Wa = c + L1; const float* Wb = Wa + D * L1;
+                const float* ba = Wb + D * L1; const float* bb = ba + D; const float* Wc = bb + D;
+                float A = Wc[D];                                 // bc
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    float a0 = ba[d], a1 = 0.f, b0 = bb[d], b1v = 0.f;
+#pragma unroll
+                    for (int j = 0; j < L1; j += 4) {
+                        const float4 wa = *reinterpret_cast<const float4*>(Wa + d * L1 + j);
+                        const float4 wb = *reinterpret_cast<const float4*>(Wb + d * L1 + j);
+                        a0 = fmaf(wa.x, h[j], a0); a1 = fmaf(wa.y, h[j + 1], a1); a0 = fmaf(wa.z, h[j + 2], a0); a1 = fmaf(wa.w, h[j + 3], a1);
+                        b0 = fmaf(wb.x, h[j], b0); b1v = fmaf(wb.y, h[j + 1], b1v); b0 = fmaf(wb.z, h[j + 2], b0); b1v = fmaf(wb.w, h[j + 3], b1v);
+                    }
+                    // tanh(a) = 1 - 2 / (1 + e^(2a)), sigmoid(b) = 1 / (1 + e^-b): exp2-based, |error| ~1e-6 (bar: 1e-3 on A)
+                    const float ta = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * (a0 + a1)));
+                    const float sb = __fdividef(1.0f, 1.0f + __expf(-(b0 + b1v)));
+                    A = fmaf(Wc[d], ta * sb, A);
+                }
+                if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = A;
+                // chunk-local softmax partial over the 128 rows (named barrier 2: the four epilogue warps)
+                float mx = valid ? A : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) sRed[warp & 3] = mx;
+                named_bar_sync(bar_id, 128);
+                mx = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
+                const float e = valid ? expf(A - mx) : 0.f;
+                float sum = e;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) sRed[4 + (warp & 3)] = sum;
+#pragma unroll
+                for (int j = 0; j < L1; ++j) sE[r * (L1 + 1) + j] = e * h[j];
+                named_bar_sync(bar_id, 128);
+                sum = (sRed[4] + sRed[5]) + (sRed[6] + sRed[7]);
+                {
+                    constexpr int G = 128 / L1;
+                    const int grp = et / L1, j = et - grp * L1;
+                    float acc = 0.f;
+                    for (int i = grp; i < TC_M; i += G) acc += sE[i * (L1 + 1) + j];
+                    sPart[et] = acc;
+                }
+                named_bar_sync(bar_id, 128);
+                float* out = partials + (static_cast<size_t>(m) * work_cap + wi) * (L1 + 2);
+                if (et == 0) { out[0] = mx; out[1] = sum; }
+                if (et < L1) {
+                    constexpr int G = 128 / L1;
+                    float v = 0.f;
+#pragma unroll
+                    for (int g2 = 0; g2 < G; ++g2) v += sPart[g2 * L1 + et];
+                    out[2 + et] = v;
+                }
+                named_bar_sync(bar_id, 128);                          // sRed / sE / sPart are rewritten by the next fold
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __restrict__ bag_offsets,
                                                            const __grid_constant__ ClamModels models, int n_bags, int L1,
                                                            int C, int work_cap, int CH, const int32_t* __restrict__ prefix,
@@ -568,6 +841,41 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
             if (!models.m[m].p[k]) return set_error("hb_clam: weight pointer %d of model %d is null", k, m);
         }
     float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + off_part);
+    static int tc_env = -1;
+    if (tc_env < 0) { const char* e = getenv("HB_CLAM_TC"); tc_env = (e && e[0] == '0') ? 0 : 1; }
+    if (tc_env && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
+        // tensor-core path: 128-instance chunks (fewer (bag, chunk) items than the bound computed for CH above)
+        clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, TC_M, prefix, work, work_cap);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+        CUtensorMap map_x;
+        if (encode_tmap_2d(&map_x, TMAP_F32, feats, static_cast<uint64_t>(total_instances), 192, 192 * 4, TC_M, TC_KS)) return -1;
+        const int ntot = n_models * L1;
+        const int stages = clam_tc_stages(n_models, L1, D);
+        if (stages < 2) return set_error("hb_clam: tensor-core path does not fit shared memory (n_models %d, L1 %d)", n_models, L1);
+        const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * 2 * TC_SLICE_BYTES;
+        (void)ntot;
+        auto kern = (L1 == 16) ? clam_scores_tc_kernel<16> : clam_scores_tc_kernel<32>;
+        HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        int grid = (total_instances / TC_M) + n_bags;
+        if (grid > work_cap) grid = work_cap;
+        if (grid > num_sms()) grid = num_sms();
+        {
+            ProfScope ps(10, stream);
+            kern<<<grid, TC_THREADS, smem, stream>>>(map_x, bag_offsets, models, n_models, n_bags, total_instances, prefix, work,
+                                                     work_cap, a_raw, partials);
+            count_launch();
+            HB_CUDA_OK(cudaGetLastError());
+        }
+        dim3 grid2(n_bags, n_models);
+        ProfScope ps2(11, stream);
+        clam_combine_kernel<<<grid2, 128, (L1 + C + 128 + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
+                                                                                        work_cap, TC_M, prefix, partials, m_out,
+                                                                                        logits, y_prob, y_hat);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, CH, prefix, work, work_cap);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
