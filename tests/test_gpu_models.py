@@ -342,8 +342,10 @@ def test_clam_ragged_bags_and_fold_ensemble():
                 continue
             bag = feats[offs[b]:offs[b + 1]]
             logits, y_prob, y_hat, a_raw, _ = O.clam_sb_forward(sd, bag)
-            assert (r["a_raw"][mi, offs[b]:offs[b + 1]].cpu() - a_raw[0]).abs().max().item() < 1e-3
-            assert (r["logits"][mi, b].cpu() - logits[0]).abs().max().item() < 1e-3
+            # bar (BASELINE.json north_star): 1e-3.  This call runs the split-TF32 tensor-core kernel (5 folds x L1 16): the
+            # hi/lo operand split keeps it at fp32 level, which the tighter bound pins.
+            assert (r["a_raw"][mi, offs[b]:offs[b + 1]].cpu() - a_raw[0]).abs().max().item() < 5e-5
+            assert (r["logits"][mi, b].cpu() - logits[0]).abs().max().item() < 5e-5
             assert (r["y_prob"][mi, b].cpu() - y_prob[0]).abs().max().item() < 1e-3
             assert int(r["y_hat"][mi, b]) == int(y_hat)
 
