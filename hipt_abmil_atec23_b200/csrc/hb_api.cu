@@ -76,6 +76,24 @@ int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t ro
     return 0;
 }
 
+int encode_tmap_u8_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
+    if (rank < 2 || rank > 5) return set_error("encode_tmap_u8_nd: rank %d", rank);
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("encode_tmap_u8_nd: base must be 16 B aligned");
+    cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5]; cuuint32_t e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) {
+        if (strides_bytes[i] & 15) return set_error("encode_tmap_u8_nd: stride %d is not a multiple of 16 bytes", i);
+        s[i] = strides_bytes[i];
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (uint8, rank %d) failed with CUresult %d", rank, static_cast<int>(r));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- launch profiler
 // Optional CUDA-event bracket around every kernel launch of the drivers below, on the launching stream, so bench.py
 // can report each kernel's measured share of a step (and the dominant kernel's roofline) from the timed region itself.
@@ -471,6 +489,31 @@ int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, si
     { ProfScope ps(HB_PROF_EMBED_GEMM, st); if (gemm_launch(g, st)) return -1; }
     { ProfScope ps(HB_PROF_CLS_ROWS, st);
       if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, nullptr, plan->xb, plan->stats1, n_patches, seq_len, D, st)) return -1; }
+    return run_blocks(plan, n_patches, seq_len, cls_f32, cls_bf16, st);
+}
+
+int hb_vit256_forward_u8(hb_vit_plan* plan, const void* image_u8, size_t chan_stride, size_t row_pitch, int grid_cols,
+                         int grid_rows, size_t image_stride_bytes, int n_images, int patch_begin, int n_patches,
+                         const void* embed_w_f16, const float* embed_b, float embed_scale, const float* pos_table,
+                         float* cls_f32, void* cls_bf16, void* stream) {
+    if (!plan || !image_u8 || !embed_w_f16 || !embed_b || !pos_table) return set_error("hb_vit256_forward_u8: null argument");
+    if (plan->cfg.dim != 384) return set_error("hb_vit256_forward_u8: the fused patch embed is built for dim 384");
+    if (grid_cols <= 0 || grid_rows <= 0 || n_images <= 0) return set_error("hb_vit256_forward_u8: bad region geometry");
+    if (n_patches <= 0) return 0;
+    if (patch_begin < 0 || patch_begin + n_patches > n_images * grid_cols * grid_rows)
+        return set_error("hb_vit256_forward_u8: patch range outside the image batch");
+    const int seq_len = 257;
+    if (static_cast<long long>(n_patches) * seq_len > plan->cfg.max_rows)
+        return set_error("hb_vit256_forward_u8: %d patches exceed the plan capacity of %d rows", n_patches, plan->cfg.max_rows);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (clear_stats(plan, st)) return -1;
+    { ProfScope ps(HB_PROF_EMBED_GEMM, st);
+      if (embed_u8_launch(image_u8, chan_stride, row_pitch, grid_cols, grid_rows, image_stride_bytes, n_images, patch_begin,
+                          n_patches, embed_w_f16, embed_b, embed_scale, pos_table, plan->xb, plan->stats1,
+                          static_cast<int>(plan->rows), st)) return -1; }
+    { ProfScope ps(HB_PROF_CLS_ROWS, st);
+      if (cls_rows_launch(static_cast<const float*>(plan->w[0]), pos_table, nullptr, plan->xb, plan->stats1, n_patches, seq_len,
+                          plan->cfg.dim, st)) return -1; }
     return run_blocks(plan, n_patches, seq_len, cls_f32, cls_bf16, st);
 }
 

@@ -31,6 +31,15 @@ enum TmapDtype { TMAP_BF16 = 0, TMAP_F32 = 1, TMAP_U8 = 2 };
 int encode_tmap_2d(CUtensorMap* map, TmapDtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                    uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
+// n-D uint8 tensor (dims fastest first, strides in bytes for dims 1..n-1), no swizzle: dense box in shared memory
+int encode_tmap_u8_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
+// fused unfold + normalise + patch embed from uint8 regions (hb_embed.cu)
+int embed_u8_launch(const void* image_u8, size_t chan_stride, size_t row_pitch, int grid_cols, int grid_rows,
+                    size_t image_stride_bytes, int n_images, int patch_begin, int n_patches, const void* w_f16,
+                    const float* bias, float scale, const float* pos_table, void* xb_bf16, float* stats, int stats_stride,
+                    cudaStream_t stream);
+
 struct GemmAux {                                 // epilogue side inputs / outputs, passed to the kernel by value
     const float* colvec2;                        // LNFOLD: c[N] = sum_k gamma_k W_jk (bias slot carries d[N])
     const float* row_stats;                      // LNFOLD: [n_part][stats_stride][2] partial (sum, sum of squares) of the rows behind A

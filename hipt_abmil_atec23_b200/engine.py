@@ -155,6 +155,26 @@ class VitEngine:
             self._embed_cache[key] = ent
         return ent
 
+    def embed_weights_f16(self, mean, std):
+        """Operands of the fused uint8 patch embed (hb_vit256_forward_u8): fp16(W / std_c) as [384, 768] in K order (c, i, j),
+        bias b - sum_k fp16(W / std)[k] mean_c (the ROUNDED weights, so the mean term cancels exactly against the MMA), and the
+        accumulator scale 1/255 (ToTensor).  fp16 keeps 11 significant bits of the weights (bf16: 8)."""
+        key = ("f16", tuple(float(v) for v in mean), tuple(float(v) for v in std))
+        ent = self._embed_cache.get(key)
+        if ent is None:
+            proj = self._module.patch_embed.proj
+            W = proj.weight.detach().double().cpu()
+            b = proj.bias.detach().double().cpu()
+            m = torch.tensor(key[1], dtype=torch.float64).view(1, 3, 1, 1)
+            s = torch.tensor(key[2], dtype=torch.float64).view(1, 3, 1, 1)
+            wr = (W / s).to(torch.float16)
+            if not torch.isfinite(wr).all():
+                raise RuntimeError("patch-embed weights overflow fp16 after folding the normalisation")
+            bias = b - (wr.double() * m).sum(dim=(1, 2, 3))
+            ent = (wr.reshape(W.shape[0], -1).to(self.device).contiguous(), bias.float().to(self.device).contiguous(), 1.0 / 255.0)
+            self._embed_cache[key] = ent
+        return ent
+
     # ------------------------------------------------------------------------------------------------ forwards
     def forward_patches(self, image, patch_begin=0, n_patches=None, mean=None, std=None, want_f32=True, out_bf16=None):
         """ViT-256 over patches of `image` (region [3,H,W], region batch [R,3,H,W] or patch batch [B,3,256,256]; fp32
@@ -166,7 +186,13 @@ class VitEngine:
         is_f32 = image.dtype == torch.float32
         if not is_f32 and mean is None:
             raise RuntimeError("uint8 input needs the (mean, std) of the normalisation to fold into the patch embed")
-        ew, eb = self.embed_weights(None if is_f32 else mean, None if is_f32 else std)
+        # uint8 regions: unfold + normalise + patch embed are one tensor-core kernel reading the bytes from HBM
+        fused = (not is_f32 and gc > 0 and self.dim == 384 and os.environ.get("HB_EMBED_UNFUSED") != "1"
+                 and cs % 16 == 0 and rp % 16 == 0 and istride % 16 == 0 and image.data_ptr() % 16 == 0)
+        if fused:
+            ew, eb, escale = self.embed_weights_f16(mean, std)
+        else:
+            ew, eb = self.embed_weights(None if is_f32 else mean, None if is_f32 else std)
         pos = self.pos_table(16, 16)
         with torch.cuda.device(self.device):
             cls_f32 = torch.empty((n, self.dim), dtype=torch.float32, device=self.device) if want_f32 else None
@@ -175,6 +201,13 @@ class VitEngine:
             done = 0
             while done < n:                         # minibatches of the plan capacity (hipt_4k.py:68-70)
                 cur = min(self.max_seqs, n - done)
+                if fused:
+                    _lib.check(self.lib.hb_vit256_forward_u8(
+                        self.plan, _lib.ptr(image), cs, rp, gc, ppi // gc, istride, total // ppi, patch_begin + done, cur,
+                        _lib.ptr(ew), _lib.ptr(eb), escale, _lib.ptr(pos),
+                        _lib.ptr(cls_f32[done:] if cls_f32 is not None else None), _lib.ptr(cls_bf16[done:]), _lib.stream_ptr()))
+                    done += cur
+                    continue
                 _lib.check(self.lib.hb_vit256_forward(
                     self.plan, _lib.ptr(image), int(is_f32), ps, cs, rp, gc, ppi, istride, patch_begin + done, cur, _lib.ptr(ew),
                     _lib.ptr(eb), _lib.ptr(pos), _lib.ptr(cls_f32[done:] if cls_f32 is not None else None),

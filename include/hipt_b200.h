@@ -169,6 +169,17 @@ int hb_vit256_forward(hb_vit_plan* plan, const void* image, int image_is_f32, si
                       int patch_begin, int n_patches, const void* embed_w_bf16, const float* embed_b,
                       const float* pos_table, float* cls_f32, void* cls_bf16, void* stream);
 
+/* hb_vit256_forward with the region unfold + ToTensor/Normalize + patch-embed conv fused into ONE tcgen05 GEMM that reads the
+ * uint8 regions straight from HBM (hipt_4k.py:64-65 unfold/rearrange, hipt_model_utils.py:113-118 eval_transforms,
+ * vision_transformer.py:165-170 PatchEmbed, :240-244 positional add): image_u8 = [n_images][3][grid_rows*256][grid_cols*256]
+ * bytes with the given channel / row / image strides (multiples of 16 bytes); patches are numbered image-major, then row-major
+ * over the region's 256 x 256 tiles.  embed_w_f16 = fp16 [384][768] of W / std (K order c, i, j), embed_b = b - sum W mean/std,
+ * embed_scale = 1/255 (applied to the accumulator).  Everything else as hb_vit256_forward. */
+int hb_vit256_forward_u8(hb_vit_plan* plan, const void* image_u8, size_t chan_stride, size_t row_pitch, int grid_cols,
+                         int grid_rows, size_t image_stride_bytes, int n_images, int patch_begin, int n_patches,
+                         const void* embed_w_f16, const float* embed_b, float embed_scale, const float* pos_table,
+                         float* cls_f32, void* cls_bf16, void* stream);
+
 /* ViT-4K over n_regions grids of tokens_per_region ViT-256 CLS tokens (hipt_4k.py:72-75; the reshape/transpose at :73
  * is the identity on token order).  cls256_bf16 [n_regions*tokens_per_region, in_dim]; phi_w_bf16 [dim, in_dim];
  * pos_table f32 [tokens_per_region+1, dim]; out_f32 [n_regions, dim]. */
