@@ -11,7 +11,7 @@ python tools/show_bench.py gpurun_out/${TAG}_bench.json
 if [ "${2:-}" = "ncu" ]; then
 SHORT="python bench.py --steps 1 --warmup 3 --regions-per-step 2 --no-cpu-baseline"
 $SHORT > gpurun_out/${TAG}_short.json 2> gpurun_out/${TAG}_short.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 236 -c 80 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_ll.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 232 -c 80 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_ll.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'mlp_fused_kernel|attention_tc_kernel' -s 8 -c 2 -o gpurun_out/${TAG}_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
