@@ -89,6 +89,38 @@ def test_tokens_before_blocks_match_oracle(hipt):
     assert (tok - ref1).abs().max().item() < 0.05
 
 
+def test_fused_u8_patch_embed_tokens_match_oracle(hipt):
+    """hb_vit256_forward_u8: unfold + ToTensor/Normalize + patch-embed conv + positional add from raw uint8 regions as one
+    tensor-core kernel (hipt_4k.py:64-65, hipt_model_utils.py:113-118, vision_transformer.py:165-170, 240-244), checked one
+    block downstream against the oracle on two regions of 2 x 3 patches each, every patch position and both tile halves."""
+    from hipt_abmil_atec23_b200.hipt_model_utils import HIPT_MEAN, HIPT_STD
+    reg = torch.randint(0, 256, (2, 3, 512, 768), dtype=torch.uint8, generator=torch.Generator().manual_seed(78))
+    sd = {k: v.detach().cpu() for k, v in hipt.model256.state_dict().items()}
+    patches = torch.cat([O.unfold_region(O.eval_transforms_u8(reg[i:i + 1])) for i in range(2)])      # [12, 3, 256, 256]
+    ref1 = O.block(sd, "blocks.0.", O.vit256_tokens(sd, patches), 6)
+    eng = hipt.model256._engine(DEV)
+    eng.set_depth_limit(1)
+    try:
+        eng.forward_patches(reg.to(DEV), mean=HIPT_MEAN, std=HIPT_STD, want_f32=False)
+        torch.cuda.synchronize()
+        tok = eng.buffer(1, 12 * 257, 384, torch.bfloat16).view(12, 257, 384).float().cpu()
+    finally:
+        eng.set_depth_limit(0)
+    assert _cos(tok, ref1) > 0.9999
+    assert (tok - ref1).abs().max().item() < 0.05
+    # and the unfused route (HB_EMBED_UNFUSED=1: im2col + GEMM with bf16 weights) lands on the same tokens
+    os.environ["HB_EMBED_UNFUSED"] = "1"
+    try:
+        eng.set_depth_limit(1)
+        eng.forward_patches(reg.to(DEV), mean=HIPT_MEAN, std=HIPT_STD, want_f32=False)
+        torch.cuda.synchronize()
+        tok2 = eng.buffer(1, 12 * 257, 384, torch.bfloat16).view(12, 257, 384).float().cpu()
+    finally:
+        os.environ.pop("HB_EMBED_UNFUSED", None)
+        eng.set_depth_limit(0)
+    assert _cos(tok, tok2) > 0.9999
+
+
 def test_mini_region_forward_fp32_with_crop(gold, hipt):
     g = gold["mini_region"]
     reg = torch.randint(0, 256, g["shape"], dtype=torch.uint8, generator=torch.Generator().manual_seed(g["pixels_seed"]))
