@@ -1,4 +1,4 @@
-// hb_clam.cu — CLAM_SB gated-attention MIL pooling over ragged bags, all in fp32.
+// hb_clam.cu — CLAM_SB gated-attention MIL pooling over ragged bags (forward, training-step backward, Adam), fp32 accuracy.
 //
 // Reference semantics (models/model_clam.py):
 //   h1 = relu(fc(h))                                     :83-85   attention_net[0..1]
@@ -8,19 +8,18 @@
 //   logits = classifiers(M); Y_prob = softmax; Y_hat = top1  :181-183
 // Dropout layers are identities at inference (model.eval()).
 //
-// Kernel 1, HIPT sizes (192-d features, L1 <= 128: clam_scores192_kernel): one CTA per 64-instance chunk of one bag.
-// The [64 x 192] fp32 feature tile is read from HBM ONCE (coalesced 128-bit loads) into shared memory and reused by
-// every weight set ("fold"); the first Linear runs as a register-tiled SGEMM on packed f32x2 FMAs (thread tile = 2
-// instances x 4 or 8 output columns, W1 staged k-major 64 rows at a time); the gate reads h1 rows as float4 and the
-// gate weights as shared-memory broadcasts, two threads per instance; chunk-local softmax partials (max, sum exp,
-// sum exp * h1) use warp-shuffle reductions.  Algorithmic HBM bytes: 772 per instance.
-// Kernel 1, any other size (clam_scores_kernel): one CTA per 128-instance chunk, one instance per thread.  The feature tile is staged
-// through shared memory with coalesced 128-bit loads (row stride padded to 65 words: conflict-free per-thread rows),
-// the first Linear is computed 16 output columns at a time against a k-major weight tile read as broadcast float4,
-// h1 stays in shared memory for the gate and for the chunk-local softmax partial (max, sum exp, sum exp*h1).
-// Several weight sets ("folds") loop inside the CTA so the tile is fetched from HBM once.
-// Kernel 2 (combine): one CTA per (bag, model) merges the chunk partials with the usual max-rescaling and applies the
-// bag classifier.
+// Forward = work table -> score kernel -> combine:
+//   clam_work_table_kernel   ragged bags -> flat (bag, chunk) list, so only CTAs with work are launched
+//   clam_scores_tc_kernel    192-d features, L1 = 16 / 32, n_models * L1 <= 80: the first Linear of every fold as ONE tcgen05
+//                            kind::tf32 GEMM per 128-instance tile with hi / lo operand splitting (fp32-level accuracy),
+//                            persistent CTAs, TMA ring; gate, score and chunk softmax partials in the epilogue warpgroups
+//   clam_scores192_kernel    192-d features, any L1 <= 128 (the large heads, tiny inputs, > 5 folds): one CTA per
+//                            64-instance chunk, tile staged once with cp.async and reused by every fold, first Linear and gate
+//                            as register-tiled SGEMMs on packed f32x2 FMAs (packed along K: operands are natural float4 halves)
+//   clam_scores_kernel       any other feature size (e.g. the 1024-d demo checkpoint): one instance per thread
+//   clam_combine_kernel      one CTA per (bag, model): merges the chunk partials (max-rescaling), classifier, softmax, argmax
+// Algorithmic HBM bytes: 772 per instance forward (features read once for all folds + one score), 1,544 with the
+// recomputing backward (clam_bwd_prep_kernel + clam_bwd192_kernel); adam_step_kernel updates every tensor in one launch.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
