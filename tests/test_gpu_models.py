@@ -382,6 +382,42 @@ def test_clam_ragged_bags_and_fold_ensemble():
             assert int(r["y_hat"][mi, b]) == int(y_hat)
 
 
+def test_clam_forward_writes_stay_inside_their_buffers():
+    """Guard words around every output and the workspace of hb_clam_sb_forward (tensor-core and CUDA-core score kernels, ragged
+    bags incl. a partial last chunk and an empty bag): nothing outside the documented extents is written."""
+    import ctypes as C
+    from hipt_abmil_atec23_b200 import clam_engine
+    lib = _lib.load()
+    lens = [300, 0, 129, 1000, 57]
+    total = sum(lens)
+    offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
+    feats = torch.randn(total, 192, generator=torch.Generator().manual_seed(8)).to(DEV)
+    GUARD, SENT = 64, 12345.0
+    for size_arg, n_models in (("hipt_smaller", 5), ("hipt_smaller", 8), ("hipt_big", 2)):
+        models = [seeded_clam(size_arg, 10 + i).to(DEV) for i in range(n_models)]
+        L1 = models[0].attention_net[0].out_features
+        D = clam_engine._gate_module(models[0]).attention_c.in_features
+        keep = [clam_engine._weights(m, DEV) for m in models]
+        arr = (C.c_void_p * (10 * n_models))(*[t.data_ptr() for w in keep for t in w])
+        def guarded(n, dtype=torch.float32):
+            buf = torch.full((n + 2 * GUARD,), SENT, dtype=dtype, device=DEV)
+            return buf, buf[GUARD:GUARD + n]
+        a_buf, a_raw = guarded(n_models * total)
+        m_buf, m_out = guarded(n_models * len(lens) * L1)
+        l_buf, logits = guarded(n_models * len(lens) * 2)
+        p_buf, y_prob = guarded(n_models * len(lens) * 2)
+        ws_bytes = lib.hb_clam_workspace_bytes(max(lens), len(lens), n_models, L1)
+        w_buf, ws = guarded(ws_bytes // 4 + 4)
+        y_hat = torch.empty(n_models * len(lens), dtype=torch.int64, device=DEV)
+        _lib.check(lib.hb_clam_sb_forward(_lib.ptr(feats), _lib.ptr(offs), len(lens), total, max(lens), arr, n_models, 192, L1, D, 2,
+                                          _lib.ptr(a_raw), _lib.ptr(m_out), _lib.ptr(logits), _lib.ptr(y_prob), _lib.ptr(y_hat),
+                                          _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        for name, buf in (("a_raw", a_buf), ("m", m_buf), ("logits", l_buf), ("y_prob", p_buf), ("workspace", w_buf)):
+            assert bool((buf[:GUARD] == SENT).all()) and bool((buf[-GUARD:] == SENT).all()), (size_arg, n_models, name)
+        assert bool(torch.isfinite(a_raw).all()) and bool((a_raw != SENT).all())
+
+
 def test_clam_demo_checkpoint_trained_weights():
     from hipt_abmil_atec23_b200.model_clam import CLAM_SB
     g = torch.load(os.path.join(GOLD_DIR, "clam_demo_ckpt.pt"), map_location="cpu")
