@@ -164,6 +164,57 @@ def forward_single_autograd(model, h):
     return logits, y_prob, y_hat, a_raw, m
 
 
+class TrainStep:
+    """One optimisation step of train_loop (utils/core_utils.py:409-425: model(data) -> CrossEntropyLoss -> backward ->
+    optimizer.step -> zero_grad) for a CLAM_SB on the fused kernels with nothing else in between: forward (work table, scores,
+    combine), backward with the loss fused in (hb_clam_sb_backward_ce), Adam (FusedAdam: one launch).  Buffers are allocated
+    once; `step(bag, label)` returns the loss as a device scalar (no host synchronisation).  The autograd route
+    (CLAM_SB.forward + loss.backward()) gives the same gradients; this one removes its per-step Python / autograd overhead."""
+
+    def __init__(self, model, optimizer, max_instances):
+        if not supports_fused_backward(model):
+            raise RuntimeError("TrainStep covers the HIPT head sizes (192-d features, L1 <= 128)")
+        self.model, self.opt = model, optimizer
+        self.params = _param_list(model)
+        dev = self.params[0].device
+        self.dev = dev
+        self.L0, self.L1 = 192, self.params[0].shape[0]
+        self.D, self.C = self.params[2].shape[0], self.params[8].shape[0]
+        self.maxn = int(max_instances)
+        lib = _lib.load()
+        self.lib = lib
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        self.a_raw, self.m_out, self.logits, self.y_prob = f32(1, self.maxn), f32(1, self.L1), f32(1, self.C), f32(1, self.C)
+        self.loss = torch.empty((), dtype=torch.float32, device=dev)
+        self.offs = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.ws_f = torch.empty(max(lib.hb_clam_workspace_bytes(self.maxn, 1, 1, self.L1), 16), dtype=torch.uint8, device=dev)
+        self.ws_b = f32(4 + self.L1)
+        for p in self.params:
+            p.grad = torch.zeros_like(p)
+        self.warr = (C.c_void_p * 10)(*[p.data_ptr() for p in self.params])
+        self.garr = (C.c_void_p * 10)(*[p.grad.data_ptr() for p in self.params])
+
+    @torch.no_grad()
+    def step(self, bag, label):
+        """bag [N, 192] fp32 CUDA, label int64 CUDA tensor with one element."""
+        N = bag.shape[0]
+        if N > self.maxn or N < 1:
+            raise RuntimeError(f"bag of {N} instances outside 1..{self.maxn}")
+        if bag.dtype != torch.float32 or not bag.is_contiguous():
+            bag = bag.float().contiguous()
+        lib, st = self.lib, _lib.stream_ptr()
+        with torch.cuda.device(self.dev):
+            self.offs[1] = N
+            _lib.check(lib.hb_clam_sb_forward(_lib.ptr(bag), _lib.ptr(self.offs), 1, N, N, self.warr, 1, self.L0, self.L1, self.D,
+                                              self.C, _lib.ptr(self.a_raw), _lib.ptr(self.m_out), _lib.ptr(self.logits),
+                                              _lib.ptr(self.y_prob), None, _lib.ptr(self.ws_f), self.ws_f.numel(), st))
+            _lib.check(lib.hb_clam_sb_backward_ce(_lib.ptr(bag), N, self.warr, _lib.ptr(self.a_raw), _lib.ptr(self.m_out),
+                                                  _lib.ptr(self.logits), _lib.ptr(label), _lib.ptr(self.loss), self.garr, self.L0,
+                                                  self.L1, self.D, self.C, _lib.ptr(self.ws_b), self.ws_b.numel() * 4, st))
+        self.opt.step()
+        return self.loss
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr, betas, eps, weight_decay) semantics with every fp32 CUDA tensor of a group updated by
     ONE hb_adam_step launch (the reference's get_optim builds optim.Adam(lr=args.lr, weight_decay=args.reg),

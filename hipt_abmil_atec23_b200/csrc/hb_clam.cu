@@ -936,9 +936,27 @@ struct ClamGrads { float* p[10]; };
 __global__ void __launch_bounds__(256) clam_bwd_prep_kernel(const float* __restrict__ a_raw, int N, const float* __restrict__ M,
                                                             const float* __restrict__ dlogits, const float* __restrict__ dM_ext,
                                                             const float* __restrict__ Wcls, const __grid_constant__ ClamGrads g,
-                                                            int L1, int D, int C, float* __restrict__ ctx) {
+                                                            int L1, int D, int C, float* __restrict__ ctx,
+                                                            const float* __restrict__ logits, const long long* __restrict__ label,
+                                                            float* __restrict__ loss_out) {
     __shared__ float red[8];
+    __shared__ float s_dl[64];
     const int tid = threadIdx.x;
+    // cross-entropy mode (nn.CrossEntropyLoss of the bag logits against the slide label, core_utils.py:413): dlogits =
+    // softmax(logits) - onehot(label), loss = logsumexp(logits) - logits[label]; otherwise dlogits comes from the caller
+    if (logits != nullptr) {
+        if (tid == 0) {
+            float mxl = logits[0];
+            for (int c = 1; c < C; ++c) mxl = fmaxf(mxl, logits[c]);
+            float se = 0.f;
+            for (int c = 0; c < C; ++c) se += expf(logits[c] - mxl);
+            const int y = static_cast<int>(*label);
+            for (int c = 0; c < C; ++c) s_dl[c] = expf(logits[c] - mxl) / se - (c == y ? 1.f : 0.f);
+            if (loss_out) *loss_out = logf(se) + mxl - logits[y];
+        }
+        __syncthreads();
+        dlogits = s_dl;
+    }
     float mx = -INFINITY;
     for (int i = tid; i < N; i += 256) mx = fmaxf(mx, a_raw[i]);
     const float gmax = block_reduce_max_128(mx, red);
@@ -1121,10 +1139,12 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
 
 int clam_backward_launch(const float* feats, int N, const void* const* weights_host, const float* a_raw, const float* M,
                          const float* dlogits, const float* dM_ext, const float* dA_ext, void* const* grads_host, int L0,
-                         int L1, int D, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                         int L1, int D, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                         const float* logits = nullptr, const long long* label = nullptr, float* loss_out = nullptr) {
     if (!clam_is192(L0, L1, D)) return set_error("hb_clam_sb_backward: only 192-d features with L1 <= 128 are supported (L0=%d L1=%d D=%d)", L0, L1, D);
     if (N < 1 || C < 1 || C > 64) return set_error("hb_clam_sb_backward: bad dims N=%d C=%d", N, C);
-    if (!feats || !weights_host || !a_raw || !M || !dlogits || !grads_host || !workspace) return set_error("hb_clam_sb_backward: null argument");
+    if (!feats || !weights_host || !a_raw || !M || !grads_host || !workspace) return set_error("hb_clam_sb_backward: null argument");
+    if (!dlogits && !(logits && label)) return set_error("hb_clam_sb_backward: need dlogits, or logits and label");
     if ((reinterpret_cast<uintptr_t>(feats) & 15) != 0) return set_error("hb_clam_sb_backward: features must be 16 B aligned");
     if (workspace_bytes < (4 + static_cast<size_t>(L1)) * sizeof(float)) return set_error("hb_clam_sb_backward: workspace too small");
     ClamModel w;
@@ -1137,7 +1157,8 @@ int clam_backward_launch(const float* feats, int N, const void* const* weights_h
     float* ctx = static_cast<float*>(workspace);
     {
         ProfScope ps(12, stream);
-        clam_bwd_prep_kernel<<<1, 256, 0, stream>>>(a_raw, N, M, dlogits, dM_ext, w.p[8], g, L1, D, C, ctx);
+        clam_bwd_prep_kernel<<<1, 256, 0, stream>>>(a_raw, N, M, dlogits, dM_ext, w.p[8], g, L1, D, C, ctx, dlogits ? nullptr : logits,
+                                                    label, loss_out);
         count_launch();
         HB_CUDA_OK(cudaGetLastError());
     }
@@ -1242,5 +1263,13 @@ int hb_adam_step(void* const* params, const void* const* grads, void* const* exp
                  void* stream) {
     return hb::adam_step_launch(params, grads, exp_avg, exp_avg_sq, numel, n_tensors, lr, beta1, beta2, eps, weight_decay,
                                 step, static_cast<cudaStream_t>(stream));
+}
+int hb_clam_sb_backward_ce(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
+                           const float* m_pooled, const float* logits, const int64_t* label, float* loss_out,
+                           void* const* grads_host, int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    return hb::clam_backward_launch(feats, n_instances, weights_host, a_raw, m_pooled, nullptr, nullptr, nullptr, grads_host, L0,
+                                    L1, D, C, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), logits,
+                                    reinterpret_cast<const long long*>(label), loss_out);
 }
 }

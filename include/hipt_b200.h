@@ -215,6 +215,14 @@ int hb_clam_sb_backward(const float* feats, int n_instances, const void* const* 
                         void* const* grads_host, int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* hb_clam_sb_backward with the loss of train_loop fused in (utils/core_utils.py:413 loss = loss_fn(logits, label) with
+ * nn.CrossEntropyLoss, :423 loss.backward()): dlogits = softmax(logits) - onehot(label) is formed on the device from the forward's
+ * logits [C] and the label (int64, device), loss_out (device, may be NULL) = logsumexp(logits) - logits[label]. */
+int hb_clam_sb_backward_ce(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
+                           const float* m_pooled, const float* logits, const int64_t* label, float* loss_out,
+                           void* const* grads_host, int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* Multi-tensor Adam with L2 weight decay in one launch, torch.optim.Adam semantics (utils/utils.py:100-107 get_optim:
  * optim.Adam(..., lr, weight_decay=reg)): g += wd p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
  * p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps).  Up to 16 fp32 tensors; step counts from 1. */

@@ -357,6 +357,32 @@ def test_clam_three_training_steps_track_the_reference_loop():
             assert (p.detach().cpu() - ref_params[k].detach()).abs().max().item() < 2e-5, k
 
 
+def test_clam_lean_train_step_matches_the_autograd_route():
+    """clam_engine.TrainStep (forward, backward with the cross-entropy fused in, one-launch Adam; no autograd) against the
+    CLAM_SB.forward + F.cross_entropy + loss.backward() + FusedAdam route on the same bags: losses and parameters agree."""
+    from hipt_abmil_atec23_b200.clam_engine import FusedAdam, TrainStep
+    ma = seeded_clam("hipt_smaller", 2).to(DEV).train()
+    mb = seeded_clam("hipt_smaller", 2).to(DEV).train()
+    oa = FusedAdam(filter(lambda p: p.requires_grad, ma.parameters()), lr=2e-4, weight_decay=1e-5)
+    from hipt_abmil_atec23_b200.clam_engine import _param_list
+    ob = FusedAdam(_param_list(mb), lr=2e-4, weight_decay=1e-5)
+    ts = TrainStep(mb, ob, max_instances=400)
+    for step, (n, label) in enumerate([(70, 0), (333, 1), (128, 1), (1, 0)]):
+        bag = torch.randn(n, 192, generator=torch.Generator().manual_seed(40 + step)).to(DEV)
+        y = torch.tensor([label], device=DEV)
+        logits = ma(bag)[0]
+        la = F.cross_entropy(logits, y)
+        la.backward()
+        oa.step()
+        oa.zero_grad()
+        lb = ts.step(bag, y)
+        assert abs(la.item() - lb.item()) < 1e-5
+    for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        if k.startswith("instance_classifiers") or k.endswith("attention_c.bias"):
+            continue
+        assert (pa - pb).abs().max().item() < 1e-6, k
+
+
 def test_clam_ragged_bags_and_fold_ensemble():
     from hipt_abmil_atec23_b200 import clam_engine
     gen = torch.Generator().manual_seed(4)
