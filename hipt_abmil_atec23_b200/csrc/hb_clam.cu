@@ -476,7 +476,7 @@ __host__ __device__ inline bool clam_tc_ok(int L0, int L1, int D, int n_models) 
 __host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int D) {
     const int ntot = n_models * L1;
     return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 +
-           (static_cast<size_t>(n_models) * ((((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3)) + 2 * (8 + 128 + 128 * (L1 + 1) + 2)) * sizeof(float) + 32 * 8;
+           (static_cast<size_t>(n_models) * ((((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3)) + 2 * (8 + 128)) * sizeof(float) + 40 * 8;
 }
 // as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
 __host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
@@ -503,8 +503,8 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     uint8_t* sWl = sWh + TC_NSL * ntot * 128;                   // same, lo(W1)
     float* sC = reinterpret_cast<float*>(sWl + TC_NSL * ntot * 128);          // [n_models][fold constants]
     const int fold_floats = clam_tc_fold_floats(L1, D);
-    constexpr int SCR = 8 + 128 + 128 * (L1 + 1) + 2;           // per epilogue warpgroup: [8] reductions | [128] column partials |
-    float* sScr = sC + n_models * fold_floats;                  //                         [128][L1 + 1] e_i * h1_i
+    constexpr int SCR = 8 + 128;                                // per epilogue warpgroup: [8] reductions | [4 warps][L1] column partials
+    float* sScr = sC + n_models * fold_floats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + 2 * SCR);
     uint64_t* x_full = bars;              // [6]
     uint64_t* x_empty = bars + 6;         // [6]  MMA commit
@@ -636,7 +636,6 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         float* sRed = sScr + eg * SCR;
         float* sPart = sRed + 8;
-        float* sE = sPart + 128;
         const uint32_t bar_id = 2 + eg;
         for (uint32_t t = eg; static_cast<long long>(blockIdx.x) + static_cast<long long>(t) * gridDim.x < n_work; t += 2) {
             const int wi = blockIdx.x + t * gridDim.x;
@@ -681,7 +680,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
                     A = fmaf(Wc[d], ta * sb, A);
                 }
                 if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = A;
-                // chunk-local softmax partial over the 128 rows (named barrier 2: the four epilogue warps)
+                // chunk-local softmax partial over the 128 rows (one named barrier per epilogue warpgroup)
                 float mx = valid ? A : -INFINITY;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -693,28 +692,32 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 if (lane == 0) sRed[4 + (warp & 3)] = sum;
+                // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles instead of 5 L1): each step
+                // a lane hands over the half of its columns its partner keeps; the surviving column ends up on
+                // lane bits (4..): column = lane >> (5 - log2 L1)
 #pragma unroll
-                for (int j = 0; j < L1; ++j) sE[r * (L1 + 1) + j] = e * h[j];
+                for (int j = 0; j < L1; ++j) h[j] *= e;
+#pragma unroll
+                for (int half = L1 / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+                    const bool up = lane & bit;
+#pragma unroll
+                    for (int j = 0; j < half; ++j) {
+                        const float keep = up ? h[j + half] : h[j], send = up ? h[j] : h[j + half];
+                        h[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                    }
+                }
+                if constexpr (L1 == 16) h[0] += __shfl_xor_sync(0xffffffffu, h[0], 1);      // 16 columns over 32 lanes: pairs share one
+                {
+                    constexpr int SH = (L1 == 16) ? 1 : 0;
+                    if (L1 == 32 || (lane & 1) == 0) sPart[(warp & 3) * L1 + (lane >> SH)] = h[0];
+                }
                 named_bar_sync(bar_id, 128);
                 sum = (sRed[4] + sRed[5]) + (sRed[6] + sRed[7]);
-                {
-                    constexpr int G = 128 / L1;
-                    const int grp = et / L1, j = et - grp * L1;
-                    float acc = 0.f;
-                    for (int i = grp; i < TC_M; i += G) acc += sE[i * (L1 + 1) + j];
-                    sPart[et] = acc;
-                }
-                named_bar_sync(bar_id, 128);
                 float* out = partials + (static_cast<size_t>(m) * work_cap + wi) * (L1 + 2);
                 if (et == 0) { out[0] = mx; out[1] = sum; }
-                if (et < L1) {
-                    constexpr int G = 128 / L1;
-                    float v = 0.f;
-#pragma unroll
-                    for (int g2 = 0; g2 < G; ++g2) v += sPart[g2 * L1 + et];
-                    out[2 + et] = v;
-                }
-                named_bar_sync(bar_id, 128);                          // sRed / sE / sPart are rewritten by the next fold
+                if (et < L1) out[2 + et] = (sPart[et] + sPart[L1 + et]) + (sPart[2 * L1 + et] + sPart[3 * L1 + et]);
+                // no trailing barrier: the next fold's first barrier orders these reads before its writes of sRed[4..7] / sPart
+                // (its maxima go to sRed[0..3], which nobody reads after the barrier above)
             }
         }
     }
