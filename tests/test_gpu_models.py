@@ -119,6 +119,11 @@ def test_fused_u8_patch_embed_tokens_match_oracle(hipt):
         os.environ.pop("HB_EMBED_UNFUSED", None)
         eng.set_depth_limit(0)
     assert _cos(tok, tok2) > 0.9999
+    # a single [3, H, W] region and a patch sub-range of the batch go through the same kernel
+    _, one = eng.forward_patches(reg[1].to(DEV), mean=HIPT_MEAN, std=HIPT_STD, want_f32=False)
+    _, both = eng.forward_patches(reg.to(DEV), mean=HIPT_MEAN, std=HIPT_STD, want_f32=False)
+    _, sub = eng.forward_patches(reg.to(DEV), patch_begin=4, n_patches=5, mean=HIPT_MEAN, std=HIPT_STD, want_f32=False)
+    assert torch.equal(one, both[6:]) and torch.equal(sub, both[4:9])
 
 
 def test_mini_region_forward_fp32_with_crop(gold, hipt):
