@@ -310,6 +310,33 @@ def test_clam_training_step_gradients_match_reference(size_arg, n):
         assert err < 1e-3 * max(1e-2, ref[k].abs().max().item()), (k, err, ref[k].abs().max().item())
 
 
+def test_clam_five_classes_forward_and_gradients():
+    """n_classes = 5 (the subtyping tasks of main.py:443-459) through the tensor-core score kernel, the fused backward and the
+    lean training step, against the CPU oracle."""
+    from hipt_abmil_atec23_b200.clam_engine import FusedAdam, TrainStep, _param_list
+    model = seeded_clam("hipt_smaller", 7, 0.0, 5).to(DEV).train()
+    sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    bag = torch.randn(300, 192, generator=torch.Generator().manual_seed(9))
+    logits, y_prob, y_hat, a_raw, _ = model(bag.to(DEV))
+    rl, rp, rh, ra, _ = O.clam_sb_forward(sd_cpu, bag)
+    assert logits.shape == (1, 5) and (logits.detach().cpu() - rl).abs().max().item() < 1e-3
+    assert (a_raw.detach().cpu() - ra).abs().max().item() < 1e-3 and int(y_hat) == int(rh)
+    F.cross_entropy(logits, torch.tensor([3], device=DEV)).backward()
+    ref_loss, ref = _oracle_grads(sd_cpu, bag, 3)
+    for k, p in model.named_parameters():
+        if k.startswith("instance_classifiers"):
+            continue
+        err = (p.grad.cpu() - ref[k]).abs().max().item()
+        assert err < 1e-3 * max(1e-2, ref[k].abs().max().item()), (k, err)
+    m2 = seeded_clam("hipt_smaller", 7, 0.0, 5).to(DEV).train()
+    ts = TrainStep(m2, FusedAdam(_param_list(m2), lr=1e-3), 300)
+    loss = ts.step(bag.to(DEV), torch.tensor([3], device=DEV))
+    assert abs(loss.item() - ref_loss.item()) < 1e-4
+    for (k, p) in m2.named_parameters():
+        if not k.startswith("instance_classifiers"):
+            assert (p.grad.cpu() - ref[k]).abs().max().item() < 1e-3 * max(1e-2, ref[k].abs().max().item()), k
+
+
 def test_fused_adam_matches_torch_adam():
     from hipt_abmil_atec23_b200.clam_engine import FusedAdam
     torch.manual_seed(0)
