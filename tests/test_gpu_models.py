@@ -148,6 +148,13 @@ def test_u8_path_equals_fp32_path(hipt):
     out_f = torch.cat(outs)
     assert out_u8.shape == (2, 192)
     assert _min_row_cos(out_u8, out_f) > 0.9995
+    # the heatmap pipeline normalises with the ImageNet statistics (datasets/wsi_dataset.py:12-16): folded the same way
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    out_im = hipt.forward_regions_u8(reg, mean, std)
+    m = torch.tensor(mean).view(1, 3, 1, 1)
+    sdv = torch.tensor(std).view(1, 3, 1, 1)
+    outs = [hipt(((reg[i:i + 1].cpu().float() / 255.0 - m) / sdv).to(DEV)) for i in range(2)]
+    assert _min_row_cos(out_im, torch.cat(outs)) > 0.9995
 
 
 def test_config1_full_region(gold, hipt):
