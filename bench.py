@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — HIPT_4K + CLAM_SB slide inference throughput on B200 (BASELINE.json metric: 4K regions/s, slides/s).
+"""bench.py — HIPT_4K + CLAM_SB slide-set inference throughput on B200 (BASELINE.json metric: 4K regions/s, slides/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A STEP is one synthetic slide: `--regions-per-step` uint8 4096x4096 regions -> ViT-256 over their 256 patches ->
-ViT-4K -> [R,192] bag -> 5-fold CLAM_SB(hipt_smaller) ensemble (config 3/5 of BASELINE.json at one slide per step).
-`value` times K steps with the slide resident in HBM; `e2e` times the same K steps from PINNED HOST memory through
-hipt_abmil_atec23_b200.pipeline.SlidePipeline.run_host (H2D of every region and D2H of the results inside the timed
-region).  Multi-GPU: one process per GPU, each rank owns whole slides (no data-path collective), weak scaling, time =
-max over ranks.  `--impl reference` times the CPU oracle port of the reference path on the host cores.
+A STEP is one pass over BASELINE.json's config 3 / 5 work list: a FIXED synthetic slide set of 2,000 uint8 4096x4096 regions
+(ragged slides of 10...300 regions; region g is drawn from seed 1000 + g whatever rank owns it), every region through
+ViT-256 (256 patches) and ViT-4K, every slide's [n,192] bag through a 5-fold CLAM_SB(hipt_smaller) ensemble with per-region
+attention scores.  The regions are sharded over the N ranks by hipt_abmil_atec23_b200.sharding.SlideSetLayout (exactly
+balanced contiguous cuts); the rows of the slides cut by a rank boundary move in ONE NCCL all-gather per step, inside the
+timed region (STRONG scaling: the same 2,000 regions at every N).  `value` times K steps with each rank's regions resident in
+HBM; `e2e` times the same pass from PINNED HOST memory through ShardedSlideSet.run_host (H2D of every region and D2H of the
+results inside the timed region).  After the timed region every slide's bag is recomputed standalone (one slide at a time on
+one rank, no sharding) and must match the sharded pass bit for bit (`bags_identical`; `bags_digest` is equal at every N).
+`--impl reference` times the reference's own modules (oracle/_ref) on the host cores, one region per step.
 One JSON line on stdout (rank 0).
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -58,6 +63,7 @@ KERNEL_BYTES_PER_LAUNCH = {            # HBM-bound row kernels: bytes that must 
     "im2col": 3 * 4096 * 4096 * (1 + 2),
 }
 METRIC = "4K regions/sec (HIPT_4K extraction + CLAM_SB 5-fold pooling)"
+REGION_BYTES = 3 * 4096 * 4096
 
 
 def load_peaks():
@@ -124,6 +130,29 @@ def dist_env():
     return rank, world, local
 
 
+# ------------------------------------------------------------------------------------------------------ work list
+def ragged_slide_set(total, lo=10, hi=300, seed=6):
+    """Slides of lo..hi regions (uniform draws, fixed seed) until `total` regions are reached; the last slide is clipped."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    while sum(out) < total:
+        out.append(min(int(torch.randint(lo, hi + 1, (1,), generator=g)), total - sum(out)))
+    return out
+
+
+def uniform_slide_set(total, per_slide=50):
+    out = [per_slide] * (total // per_slide)
+    if total % per_slide:
+        out.append(total % per_slide)
+    return out
+
+
+def fill_region(dst, g, dev):
+    """Synthetic region g: uint8 noise from seed 1000 + g — independent of the rank that draws it."""
+    gen = torch.Generator(device=dev).manual_seed(1000 + g)
+    dst.random_(0, 256, generator=gen)
+
+
 def build_models(device, seed=0):
     from hipt_abmil_atec23_b200 import vision_transformer as vits
     from hipt_abmil_atec23_b200 import vision_transformer4k as vits4k
@@ -140,38 +169,70 @@ def build_models(device, seed=0):
     return hipt, folds
 
 
+def workload_config(args, slides, world=1, layout=None):
+    cfg = {"workload": f"BASELINE config 3/5: HIPT_4K (ViT-S/16 ViT-256 x 256 patches + ViT-4K) over a fixed synthetic slide set of "
+                       f"{sum(slides)} uint8 4096x4096 regions in {len(slides)} ragged slides (10..300 regions, seed 6), then 5-fold "
+                       f"CLAM_SB(hipt_smaller) pooling + per-region attention scores per slide; random-init weights",
+           "regions_per_step": sum(slides), "slides_per_step": len(slides), "regions_per_slide": slides,
+           "region_shape": [3, 4096, 4096], "clam_folds": 5, "sharding": args.policy,
+           "l2": "inputs larger than L2 (50.3 MB per region, every region distinct; activations 0.5 GB per region)"}
+    if layout is not None:
+        load = layout.load()
+        cfg.update({"regions_per_rank": load, "load_max_over_mean": max(load) / (sum(load) / len(load)),
+                    "slides_cut_by_a_rank_boundary": len(layout.spanning), "allgather_rows_per_rank": layout.pad_rows})
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_sample(patches=32, regions_per_slide=50, threads=None):
-    """Oracle port of the reference path on the host cores, on a bounded sample: ViT-256 over `patches` of one synthetic
-    region (scaled to 256), ViT-4K on one 16x16 grid, CLAM_SB 5-fold on one bag.  Returns (regions/s, seconds spent, info)."""
-    from oracle import hipt_oracle as O
-    from tests.common import seeded_clam, seeded_vits
+def cpu_reference_sample(state, threads=None, regions_per_slide=50):
+    """One region through the reference path on the host cores: eval_transforms + HIPT_4K.forward (unfold / rearrange copy,
+    ViT-256 over 256 patches, ViT-4K) and the region's share of a 5-fold CLAM_SB pass over a `regions_per_slide` bag.
+    Uses the reference's own modules from oracle/_ref when present (kind "reference"), else the oracle port (kind "port").
+    Returns (seconds per region, breakdown)."""
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    sd256, sd4k = seeded_vits(0)
-    folds = [seeded_clam("hipt_smaller", 10 + f).state_dict() for f in range(5)]
     g = torch.Generator().manual_seed(1)
-    px = torch.randint(0, 256, (patches, 3, 256, 256), dtype=torch.uint8, generator=g)
-    t_start = time.perf_counter()
+    region = torch.randint(0, 256, (1, 3, 4096, 4096), dtype=torch.uint8, generator=g)
     with torch.no_grad():
-        x = O.eval_transforms_u8(px)
-        O.vit256_forward(sd256, x[:4])                                   # warm-up (thread pool, allocator)
-        t0 = time.perf_counter()
-        cls = O.vit256_forward(sd256, x)
-        t256 = time.perf_counter() - t0
-        grid = cls.repeat(256 // patches + 1, 1)[:256].reshape(16, 16, 384).transpose(0, 1).transpose(0, 2).unsqueeze(0)
-        O.vit4k_forward(sd4k, grid)
-        t0 = time.perf_counter()
-        feat = O.vit4k_forward(sd4k, grid)
-        t4k = time.perf_counter() - t0
-        bag = feat.repeat(regions_per_slide, 1) + 0.01 * torch.randn(regions_per_slide, 192, generator=g)
-        t0 = time.perf_counter()
-        for sd in folds:
-            O.clam_sb_forward(sd, bag)
-        tclam = time.perf_counter() - t0
-    per_region = t256 * (256.0 / patches) + t4k + tclam / regions_per_slide
-    info = {"vit256_s_per_region": t256 * 256.0 / patches, "vit4k_s_per_region": t4k, "clam_s_per_slide": tclam}
-    return 1.0 / per_region, time.perf_counter() - t_start, info
+        if state["kind"] == "reference":
+            from oracle import ref_runner as R
+            m256, m4k, folds = state["models"]
+            t0 = time.perf_counter()
+            feat = R.hipt4k_forward(m256, m4k, R.eval_transforms_u8(region))
+            t_region = time.perf_counter() - t0
+            bag = feat.repeat(regions_per_slide, 1) + 0.01 * torch.randn(regions_per_slide, 192, generator=g)
+            t0 = time.perf_counter()
+            for f in folds:
+                f(bag)
+            t_clam = time.perf_counter() - t0
+        else:
+            from oracle import hipt_oracle as O
+            sd256, sd4k, folds = state["models"]
+            t0 = time.perf_counter()
+            feat = O.hipt4k_forward(sd256, sd4k, O.eval_transforms_u8(region))
+            t_region = time.perf_counter() - t0
+            bag = feat.repeat(regions_per_slide, 1) + 0.01 * torch.randn(regions_per_slide, 192, generator=g)
+            t0 = time.perf_counter()
+            for sd in folds:
+                O.clam_sb_forward(sd, bag)
+            t_clam = time.perf_counter() - t0
+    return t_region + t_clam / regions_per_slide, {"hipt4k_s_per_region": t_region, "clam5_s_per_slide": t_clam}
+
+
+def cpu_reference_state():
+    from oracle import ref_runner as R
+    if R.available():
+        return {"kind": "reference", "models": R.build_models(0)}
+    from tests.common import seeded_clam, seeded_vits
+    sd256, sd4k = seeded_vits(0)
+    return {"kind": "port", "models": (sd256, sd4k, [seeded_clam("hipt_smaller", 10 + f).state_dict() for f in range(5)])}
+
+
+def cpu_sample_text(state, cores):
+    what = ("the reference's own modules byte-compiled into oracle/_ref (vision_transformer, vision_transformer4k, model_clam) + "
+            "the restated hipt_4k.py:63-76 glue" if state["kind"] == "reference" else "oracle port (oracle/hipt_oracle.py)")
+    return (f"{what}, CPU fp32 torch, {cores} threads; one sample = ONE synthetic 4096x4096 region through eval_transforms + "
+            f"HIPT_4K.forward (256 patches, unfold copy included) + its 1/50 share of a 5-fold CLAM_SB pass over a 50-region bag")
 
 
 def run_reference(args):
@@ -179,31 +240,28 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    vals, spent = [], 0.0
+    slides = ragged_slide_set(args.regions)
+    state = cpu_reference_state()
+    secs = []
     for i in range(args.warmup + args.steps):
-        v, s, info = cpu_reference_sample(patches=args.ref_patches, regions_per_slide=args.regions_per_step, threads=cores)
-        spent += s
+        s, info = cpu_reference_sample(state, threads=cores)
         if i >= args.warmup:
-            vals.append(v)
-    value = len(vals) / sum(1.0 / v for v in vals)                        # steps / total time
-    sample = (f"oracle port (CPU fp32 torch, {cores} threads) per step: ViT-256 on {args.ref_patches} of 256 patches scaled x{256 // args.ref_patches}, "
-              f"ViT-4K on one grid, CLAM_SB 5-fold on one {args.regions_per_step}-region bag")
+            secs.append(s)
+    value = len(secs) / sum(secs)                                    # regions per second over the timed samples
+    cfg = workload_config(args, slides)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "regions/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.regions_per_step / value,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": "regions/s", "cores": cores, "kind": "port", "sample": sample},
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * sum(secs) / len(secs),
+            "step_is": "one bounded SAMPLE of the workload = one region (a full 2,000-region step would take "
+                       f"{sum(slides) / value / 60.0:.0f} min on these cores); value = regions / measured seconds, not extrapolated",
+            "regions_per_timed_step": 1,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "regions/s", "cores": cores, "kind": state["kind"],
+                             "sample": cpu_sample_text(state, cores), **info},
             "e2e": {"value": value, "unit": "regions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
-
-
-def workload_config(args):
-    return {"workload": "HIPT_4K(ViT-S/16 ViT-256 x256 patches + ViT-4K) on synthetic uint8 4096x4096 regions, then "
-                        "CLAM_SB(hipt_smaller) 5-fold gated-attention pooling per slide; random-init weights",
-            "regions_per_step": args.regions_per_step, "slides_per_step": 1,
-            "region_shape": [3, 4096, 4096], "clam_folds": 5,
-            "l2": "inputs larger than L2 (50.3 MB/region x regions_per_step, activations 0.5 GB/region)"}
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
@@ -212,13 +270,13 @@ def run_ours(args):
     import torch.distributed as dist
     from hipt_abmil_atec23_b200 import _lib
     from hipt_abmil_atec23_b200.pipeline import SlidePipeline
+    from hipt_abmil_atec23_b200.slideset import ShardedSlideSet, all_digests
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU path for --impl ours")
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION / WARN: send its log to stderr so that stdout
-        # carries the one JSON line only
-        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
+        # carries the one JSON line only (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -226,12 +284,17 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     peaks = load_peaks()
-    R = args.regions_per_step
     hipt, folds = build_models(dev)
-    pipe = SlidePipeline(hipt, folds)
 
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    regions = torch.randint(0, 256, (R, 3, 4096, 4096), dtype=torch.uint8, device=dev, generator=gen)
+    slides = ragged_slide_set(args.regions)
+    total = sum(slides)
+    runner = ShardedSlideSet(hipt, folds, slides, rank, world, policy=args.policy)
+    lay = runner.lay
+    n_local = runner.n_local
+    regions = torch.empty((max(n_local, 1), 3, 4096, 4096), dtype=torch.uint8, device=dev)[:n_local]
+    for i, g in enumerate(lay.regions):
+        fill_region(regions[i], g, dev)
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -253,41 +316,108 @@ def run_ours(args):
         barrier()
         return ms.item()
 
-    # ---------------------------------------------------------------- value: inputs resident in HBM
+    # ---------------------------------------------------------------- value: each rank's regions resident in HBM
     for _ in range(args.warmup):
-        out = pipe.run_device(regions)
+        out = runner.run_device(regions)
     torch.cuda.synchronize()
+    runner.gather_events = []
     launches0 = _lib.launch_count()
-    _lib.prof_enable(True)
     with ClockSampler(local) as clk:
-        ms_total = timed(lambda: pipe.run_device(regions), args.steps)
-    prof = _lib.prof_read()
-    _lib.prof_enable(False)
+        ms_total = timed(lambda: runner.run_device(regions, record_gather=True), args.steps)
     launches = _lib.launch_count() - launches0
+    gather = runner.gather_ms()
     ms_step = ms_total / args.steps
-    value = world * R * args.steps / (ms_total / 1000.0)
+    value = total * args.steps / (ms_total / 1000.0)
+    out = runner.run_device(regions)
+    torch.cuda.synchronize()
+    feats_dev = out["features"].clone()
+
+    # ---------------------------------------------------------------- bit-exactness: sharded pass vs every slide standalone
+    sharded = all_digests(runner.bag_digests(out), world)
+    alone_local = {}
+    chunk = torch.empty((16, 3, 4096, 4096), dtype=torch.uint8, device=dev)
+    t_check = time.perf_counter()
+    for s, n in enumerate(slides):
+        if n == 0 or s % world != rank:
+            continue
+        first = runner.layout.first_region[s]
+        bag = torch.empty((n, 192), dtype=torch.float32, device=dev)
+        for c0 in range(0, n, 16):
+            m = min(16, n - c0)
+            for j in range(m):
+                fill_region(chunk[j], first + c0 + j, dev)
+            bag[c0:c0 + m] = hipt.forward_regions_u8(chunk[:m])
+        alone_local[s] = hashlib.sha256(bag.cpu().numpy().tobytes()).hexdigest()
+    alone = all_digests(alone_local, world)
+    t_check = time.perf_counter() - t_check
+    bags_identical = (sorted(sharded) == sorted(alone) == [s for s, n in enumerate(slides) if n]
+                      and all(sharded[s] == alone[s] for s in alone))
+    bags_digest = hashlib.sha256("".join(sharded[s] for s in sorted(sharded)).encode()).hexdigest()[:16]
+    del chunk
 
     # ---------------------------------------------------------------- e2e: pinned host -> device -> host
-    host = torch.empty((R, 3, 4096, 4096), dtype=torch.uint8).pin_memory()
-    host.copy_(regions)
+    P = max(1, min(n_local, args.host_pool))
+    host = torch.empty((P, 3, 4096, 4096), dtype=torch.uint8).pin_memory()
+    host.copy_(regions[:P])
     torch.cuda.synchronize()
-    for _ in range(max(1, args.warmup // 2)):
-        res = pipe.run_host(host)
-    e2e_ms = timed(lambda: pipe.run_host(host), args.steps)
-    e2e_value = world * R * args.steps / (e2e_ms / 1000.0)
-    d2h = sum(v.numel() * v.element_size() for v in res.values())
-    ok = bool(torch.isfinite(res["features"]).all() and torch.isfinite(res["logits"]).all())
+    pool_index = [i % P for i in range(n_local)]
+    res = runner.run_host(host, pool_index)                            # warm-up (staging buffers, copy stream)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_ms = timed(lambda: runner.run_host(host, pool_index), e2e_steps)
+    e2e_value = total * e2e_steps / (e2e_ms / 1000.0)
+    d2h = sum(v.numel() * v.element_size() for v in res.values() if isinstance(v, torch.Tensor))
+    d2h_t = torch.tensor([d2h], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(d2h_t)
+    finite = bool(torch.isfinite(res["features"]).all()) and (res["logits"] is None or bool(torch.isfinite(res["logits"]).all()))
+    e2e_same = bool(torch.equal(res["features"][:P], feats_dev[:P].cpu()))     # host path == device path, bit for bit
+    del host
 
-    # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0's events)
+    # ---------------------------------------------------------------- secondary lines (same regions, same models)
+    uni = {}
+    if total % 50 == 0 and args.secondary_steps > 0 and args.policy == "contiguous":
+        u_slides = uniform_slide_set(total)                            # contiguous cuts: identical region ranges per rank
+        r2 = ShardedSlideSet(hipt, folds, u_slides, rank, world, policy=args.policy)
+        assert r2.lay.regions == lay.regions
+        if True:
+            r2.run_device(regions)
+            ms = timed(lambda: r2.run_device(regions), args.secondary_steps)
+            uni = {"slides": len(u_slides), "regions_per_slide": 50, "steps": args.secondary_steps,
+                   "value": total * args.secondary_steps / (ms / 1000.0), "unit": "regions/s",
+                   "slides_per_sec": len(u_slides) * args.secondary_steps / (ms / 1000.0),
+                   "slides_cut_by_a_rank_boundary": len(r2.layout.spanning)}
+        del r2
+    weak = {}
+    if total // world >= 16:                                           # round-1 line: 16 private regions per rank, one slide
+        pipe = SlidePipeline(hipt, folds)
+        for _ in range(2):
+            pipe.run_device(regions[:16])
+        ms = timed(lambda: pipe.run_device(regions[:16]), 6)
+        weak = {"value": world * 16 * 6 / (ms / 1000.0), "unit": "regions/s", "ms_per_step": ms / 6, "regions_per_rank_per_step": 16,
+                "scaling": "weak", "note": "round-1 headline: one 16-region slide per rank per step, no collective"}
+
+    # ---------------------------------------------------------------- per-kernel times + roofline of the dominant kernel
+    # hb_prof brackets every launch with two cudaEventRecords, so it is OFF for the headline above and ON for a separate
+    # pass over 32 of the same regions right after it (same kernels, same launch shapes: two regions per ViT-256 launch)
+    n_prof = min(n_local, 32)
+    pipe = SlidePipeline(hipt, folds)
+    pipe.run_device(regions[:n_prof])
+    torch.cuda.synchronize()
+    _lib.prof_enable(True)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        pipe.run_device(regions[:n_prof])
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
     step_kernel_ms = sum(ms for ms, _ in prof.values())
     kernels = {}
     for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        ent = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps, "share": ms / step_kernel_ms,
-               "avg_launch_us": 1000.0 * ms / cnt}
-        if name in KERNEL_FLOPS_PER_REGION:        # executed FLOPs of this kernel per step / its measured time per step
-            ent["tflops"] = KERNEL_FLOPS_PER_REGION[name] * R / (ms / args.steps * 1e-3) / 1e12
-        if name in KERNEL_BYTES_PER_LAUNCH:       # bytes per region; one timed scope covers the regions of one ViT-256 launch
-            ent["gbs"] = KERNEL_BYTES_PER_LAUNCH[name] * R * args.steps / (ms * 1e-3) / 1e9
+        ent = {"ms_per_region": ms / (prof_steps * n_prof), "launches_per_region": cnt / (prof_steps * n_prof),
+               "share": ms / step_kernel_ms, "avg_launch_us": 1000.0 * ms / cnt}
+        if name in KERNEL_FLOPS_PER_REGION:        # executed FLOPs of this kernel / its measured time
+            ent["tflops"] = KERNEL_FLOPS_PER_REGION[name] * n_prof * prof_steps / (ms * 1e-3) / 1e12
+        if name in KERNEL_BYTES_PER_LAUNCH:
+            ent["gbs"] = KERNEL_BYTES_PER_LAUNCH[name] * n_prof * prof_steps / (ms * 1e-3) / 1e9
         kernels[name] = ent
     top = next(iter(kernels))
     traffic = None                      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
@@ -300,7 +430,8 @@ def run_ours(args):
         ach = kernels[top]["tflops"]
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
-                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"}
+                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "measured_on": f"profiled pass over {n_prof} regions x {prof_steps} right after the timed region (hb_prof on)"}
     else:
         ach = kernels[top].get("gbs", 0.0)
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -308,31 +439,47 @@ def run_ours(args):
     model_tflops = value / world * EXECUTED_FLOPS_PER_REGION / 1e12      # executed, not the reference's dense count
 
     line = {"metric": METRIC, "value": value, "unit": "regions/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
-            "slides_per_sec": value / R,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, slides, world, runner.layout),
+            "slides_per_sec": len(slides) * args.steps / (ms_total / 1000.0),
             "model_tflops_per_gpu": model_tflops, "model_frac_of_bf16_sustained": model_tflops / peaks["tflops_sustained"],
+            "model_frac_dense_count": value / world * FLOPS_PER_REGION / 1e12 / peaks["tflops_sustained"],
             "flops_per_region": {"executed": EXECUTED_FLOPS_PER_REGION, "reference_dense": FLOPS_PER_REGION,
                                  "note": "last ViT-256 block computes only the CLS rows after its qkv GEMM"},
             "clocks": clk.result,
-            "e2e": {"value": e2e_value, "unit": "regions/s", "h2d_bytes_per_step": R * 3 * 4096 * 4096,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "finite": ok},
+            "collective": {"kind": "NCCL all_gather_into_tensor of the cut slides' rows (fp32 [pad_rows,192] per rank), one per step"
+                                   if runner.layout.needs_collective else "none needed (no slide is cut by a rank boundary)",
+                           "ms_per_step_rank0": (sum(gather) / len(gather)) if gather else 0.0,
+                           "ms_max_rank0": max(gather) if gather else 0.0,
+                           "bytes_per_rank": runner.layout.pad_rows * 192 * 4 if runner.layout.needs_collective else 0,
+                           "note": "CUDA events around the collective on the launching stream; includes waiting for the slowest rank"},
+            "bags_identical": bags_identical, "bags_digest": bags_digest,
+            "bags_check": f"every slide recomputed standalone (one slide at a time on rank slide % N, regions re-drawn from their "
+                          f"seeds) after the timed region, {t_check:.1f} s; sha256 of each [n,192] fp32 bag",
+            "e2e": {"value": e2e_value, "unit": "regions/s", "h2d_bytes_per_step": total * REGION_BYTES,
+                    "d2h_bytes_per_step": int(d2h_t.item()), "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "finite": finite,
+                    "features_equal_device_path": e2e_same,
+                    "host_pool": f"{P} distinct pinned regions per rank, local region i is copied from pool[i mod {P}] every step"},
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels}
+    if uni:
+        line["config3_uniform_40x50"] = uni
+    if weak:
+        line["weak_16_regions_per_rank"] = weak
 
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_sections:
         line["vit256_config2"] = vit256_config2(hipt, dev, peaks)
         line["clam_config4"] = clam_config4(dev, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        vals, spent, info = [], 0.0, {}
-        for _ in range(args.ref_regions):                   # bounded sample: ~10-30 s of CPU work on the box's host cores
-            v, s1, info = cpu_reference_sample(patches=args.ref_patches, regions_per_slide=R)
-            vals.append(v)
-            spent += s1
-        v = len(vals) / sum(1.0 / x for x in vals)
-        line["cpu_baseline"] = {"value": v, "unit": "regions/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"oracle port (CPU fp32 torch, {torch.get_num_threads()} threads): {args.ref_regions} x (ViT-256 on "
-                                          f"{args.ref_patches}/256 patches of one region, scaled to 256; ViT-4K on one grid; CLAM 5-fold on "
-                                          f"one {R}-region bag); {spent:.1f} s of CPU work", **info}
+        state = cpu_reference_state()
+        secs, info = [], {}
+        for i in range(1 + args.ref_regions):                   # bounded sample: ~15-30 s of CPU work on the box's host cores
+            s1, info = cpu_reference_sample(state)
+            if i:
+                secs.append(s1)
+        v = len(secs) / sum(secs)
+        line["cpu_baseline"] = {"value": v, "unit": "regions/s", "cores": os.cpu_count(), "kind": state["kind"],
+                                "sample": cpu_sample_text(state, torch.get_num_threads()) + f"; 1 warm-up + {args.ref_regions} timed samples, "
+                                          f"{sum(secs):.1f} s of CPU work", **info}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -363,9 +510,9 @@ def vit256_config2(hipt, dev, peaks):
 
 
 def clam_config4(dev, peaks):
-    """BASELINE.json config 4 beside the headline: CLAM_SB(hipt_smaller) over 256 ragged bags of 50-20,000 x 192-d instances
-    in one launch (772 algorithmic bytes per instance: features read once + one score written), and the one-bag training
-    step (forward + fused backward + one-launch Adam).  HBM-bound path: reported as GB/s against the measured copy peak."""
+    """BASELINE.json config 4 beside the headline: CLAM_SB over 256 ragged bags of 50-20,000 x 192-d instances in one launch
+    (772 algorithmic bytes per instance: features read once + one score written), and the one-bag training step (forward +
+    fused backward + one-launch Adam).  HBM-bound path: reported as GB/s against the measured copy peak."""
     import math
     import torch.nn.functional as F
     from hipt_abmil_atec23_b200 import clam_engine
@@ -378,24 +525,26 @@ def clam_config4(dev, peaks):
     feats = torch.randn((total, 192), generator=torch.Generator().manual_seed(5)).to(dev)
     offs_d, mx = offs.to(dev), int(lens.max())
     out = {"bags": 256, "instances": total, "bytes_per_instance": 772, "feature_MB": total * 768 / 1e6}
-    for folds in (1, 5):
-        models = []
-        for f in range(folds):
-            torch.manual_seed(10 + f)
-            models.append(CLAM_SB(size_arg="hipt_smaller", dropout=0.0, n_classes=2).eval().to(dev))
-        fn = lambda: clam_engine.forward_bags(models, feats, offs_d, max_bag_len=mx, want=("logits", "y_prob", "y_hat"))
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        gbs = total * (768 + 4 * folds) / ms / 1e6
-        out[f"folds{folds}"] = {"ms": ms, "bags_per_s": 256 / ms * 1e3, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+    for size in ("hipt_smaller", "hipt_big"):
+        for folds in (1, 5):
+            models = []
+            for f in range(folds):
+                torch.manual_seed(10 + f)
+                models.append(CLAM_SB(size_arg=size, dropout=0.0, n_classes=2).eval().to(dev))
+            fn = lambda: clam_engine.forward_bags(models, feats, offs_d, max_bag_len=mx, want=("logits", "y_prob", "y_hat"))
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            gbs = total * (768 + 4 * folds) / ms / 1e6
+            key = f"folds{folds}" if size == "hipt_smaller" else f"{size}_folds{folds}"
+            out[key] = {"ms": ms, "bags_per_s": 256 / ms * 1e3, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
     torch.manual_seed(2)
     model = CLAM_SB(size_arg="hipt_smaller", dropout=0.0, n_classes=2).to(dev).train()
     opt = clam_engine.FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=2e-4, weight_decay=1e-5)
@@ -438,13 +587,17 @@ def clam_config4(dev, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--regions-per-step", type=int, default=16, help="regions per synthetic slide (one slide per step)")
-    ap.add_argument("--ref-patches", type=int, default=256, help="patches per CPU-oracle sample (of 256 per region)")
-    ap.add_argument("--ref-regions", type=int, default=4, help="CPU-oracle samples in the cpu_baseline leg")
+    ap.add_argument("--regions", type=int, default=2000, help="regions in the fixed slide set (BASELINE config 3: 2,000)")
+    ap.add_argument("--policy", default="contiguous", choices=["contiguous", "lpt"], help="region sharding policy")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed passes of the pinned-host leg (at most --steps)")
+    ap.add_argument("--host-pool", type=int, default=64, help="distinct pinned host regions per rank in the e2e leg")
+    ap.add_argument("--secondary-steps", type=int, default=2, help="timed passes of the uniform 40 x 50 slide set")
+    ap.add_argument("--ref-regions", type=int, default=4, help="timed CPU samples in the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sections", action="store_true", help="skip the config-2 / config-4 sections")
     ap.add_argument("--min-warmup", type=int, default=3, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "ours":

@@ -6,7 +6,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/hipt_b200.h"
@@ -25,15 +27,32 @@ int set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-    static int cached[64] = {0};
+    static std::atomic<int> cached[64];              // zero-initialised; racing writers store the same value
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached[dev];
+    return n;
+}
+
+int set_max_dynamic_smem(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, uint64_t> done;     // kernel -> bit mask of devices already opted in
+    int dev = 0;
+    HB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lock(mu);
+        uint64_t& mask = done[func];
+        if (mask & (1ull << dev)) return 0;
+        HB_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        mask |= 1ull << dev;
+        return 0;
+    }
+    HB_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -98,15 +117,19 @@ int encode_tmap_u8_nd(CUtensorMap* map, const void* base, int rank, const uint64
 // Optional CUDA-event bracket around every kernel launch of the drivers below, on the launching stream, so bench.py
 // can report each kernel's measured share of a step (and the dominant kernel's roofline) from the timed region itself.
 std::atomic<long long> g_launches{0};
-static bool g_prof_on = false;
+// State shared by every thread that launches through the library (nn.DataParallel drives one replica per thread): the
+// on/off switch is atomic, the record list is guarded by a mutex that is only ever taken while profiling is on.
+static std::atomic<bool> g_prof_on{false};
 struct ProfRec { cudaEvent_t a, b; int kind; };
+static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
 static size_t g_prof_used = 0;
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-ProfScope::ProfScope(int kind, cudaStream_t st) : st_(st), idx_(-1) {
-    if (!g_prof_on) return;
+ProfScope::ProfScope(int kind, cudaStream_t st) : st_(st), idx_(-1), a_(nullptr), b_(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     if (g_prof_used == g_prof_recs.size()) {
         ProfRec r;
         if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
@@ -114,10 +137,12 @@ ProfScope::ProfScope(int kind, cudaStream_t st) : st_(st), idx_(-1) {
     }
     idx_ = static_cast<long long>(g_prof_used++);
     g_prof_recs[idx_].kind = kind;
-    cudaEventRecord(g_prof_recs[idx_].a, st_);
+    a_ = g_prof_recs[idx_].a;                       // copies: the vector may reallocate under another thread
+    b_ = g_prof_recs[idx_].b;
+    cudaEventRecord(a_, st_);
 }
 ProfScope::~ProfScope() {
-    if (idx_ >= 0) cudaEventRecord(g_prof_recs[idx_].b, st_);
+    if (idx_ >= 0) cudaEventRecord(b_, st_);
 }
 
 }  // namespace hb
@@ -278,7 +303,8 @@ int hb_im2col_patches(const void* image, int image_is_f32, size_t patch_stride, 
 long long hb_launch_count(void) { return g_launches.load(); }
 
 int hb_prof_enable(int on) {
-    g_prof_on = on != 0;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_on.store(on != 0);
     g_prof_used = 0;
     return 0;
 }
@@ -286,6 +312,7 @@ int hb_prof_enable(int on) {
 int hb_prof_read(double* ms_by_kind, long long* count_by_kind, int n_kinds) {
     if (!ms_by_kind || !count_by_kind) return set_error("hb_prof_read: null argument");
     for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.0; count_by_kind[i] = 0; }
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     for (size_t i = 0; i < g_prof_used; ++i) {
         HB_CUDA_OK(cudaEventSynchronize(g_prof_recs[i].b));
         float ms = 0.f;

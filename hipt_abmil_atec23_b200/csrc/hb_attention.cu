@@ -640,7 +640,7 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
     if (encode_tmap_2d(&map_out, TMAP_BF16, out_bf16, rows, D, static_cast<uint64_t>(D) * 2, 128, 64)) return -1;
     static bool attr_done = false;
     if (!attr_done) {
-        HB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel), ATC_SMEM)) return -1;
         attr_done = true;
     }
     const int n_items = n_seq * heads;
@@ -653,12 +653,20 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
     return 0;
 }
 
+static bool attention_force_v1() {          // comparison hook: HB_ATTENTION_V1=1 selects the round-1 tcgen05 kernel
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HB_ATTENTION_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
-                     cudaStream_t stream, int cls_only) {
+                     cudaStream_t stream, int cls_only, float* cls_probs) {
     if (n_seq <= 0) return 0;
     if (seq_len <= 0 || heads <= 0) return set_error("hb_attention: bad shape");
+    (void)cls_probs;
     if (seq_len == ATC_S && head_dim == 64 && !attention_force_legacy() && !cls_only)
-        return attention_tc_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream);
+        return attention_force_v1() ? attention_tc_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream)
+                                    : attention_tc2_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream);
     const int s_pad = (seq_len + 15) & ~15;
     const size_t smem = static_cast<size_t>(3) * s_pad * head_dim * 2;
     if (smem > 200 * 1024) return set_error("hb_attention: seq_len %d too long for the single-pass kernel", seq_len);
@@ -671,12 +679,12 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
     const unsigned grid = static_cast<unsigned>(n_seq) * heads;
     if (head_dim == 64) {
         auto k = attention_kernel<64>;
-        HB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(k), 200 * 1024)) return -1;
         k<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
                                               static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only);
     } else if (head_dim == 32) {
         auto k = attention_kernel<32>;
-        HB_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(k), 200 * 1024)) return -1;
         k<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
                                               static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only);
     } else {

@@ -52,6 +52,34 @@ constexpr int CLAM_MAX_MODELS = 8;
 struct ClamModel { const float* p[10]; };
 struct ClamModels { ClamModel m[CLAM_MAX_MODELS]; };
 
+// Training-mode dropout (nn.Dropout after the ReLU, model_clam.py:84-85, and inside both gate branches, :50-52).  The keep
+// decision of (instance, unit) is a pure function of a 64-bit seed — a counter-based hash, nothing is stored — so the
+// recomputing backward sees exactly the forward's masks.  Units: [0, L1) the ReLU outputs, [L1, L1 + D) branch a,
+// [L1 + D, L1 + 2 D) branch b.  keep <=> hash >= thresh, thresh = round(p * 2^32) (p = 1 drops everything, like torch).
+struct ClamDrop { uint32_t seed_lo, seed_hi, thresh_lo; int all; float scale; };     // scale = 1 / (1 - p); all: p >= 1
+__host__ __device__ __forceinline__ uint32_t clam_mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ float clam_keep(const ClamDrop& dr, uint32_t instance, uint32_t unit) {
+    if (dr.thresh_lo == 0u && !dr.all) return 1.0f;                              // dropout off
+    if (dr.all) return 0.0f;
+    const uint32_t h = clam_mix32(clam_mix32(instance * 0x9E3779B1u + dr.seed_lo) ^ (unit * 0x7FEB352Du + dr.seed_hi));
+    return h >= dr.thresh_lo ? dr.scale : 0.0f;
+}
+static ClamDrop clam_drop_make(float p, unsigned long long seed) {
+    ClamDrop d = {};
+    if (p <= 0.f) return d;
+    d.seed_lo = static_cast<uint32_t>(seed); d.seed_hi = static_cast<uint32_t>(seed >> 32);
+    if (p >= 1.f) { d.all = 1; return d; }
+    double t = static_cast<double>(p) * 4294967296.0 + 0.5;
+    if (t < 1.0) t = 1.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    d.thresh_lo = static_cast<uint32_t>(t);
+    d.scale = 1.0f / (1.0f - p);
+    return d;
+}
+
 __device__ __forceinline__ float block_reduce_max_128(float v, float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -242,7 +270,8 @@ __device__ __forceinline__ void lds_2f2(uint32_t addr, f32x2_t& a, f32x2_t& b) {
 // lane + 32) x TN columns; warp w owns column groups w, w + nw, ...; W1 reads are warp-uniform broadcasts.
 template <int TN, int L1T>
 __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const float* b1, int L1_rt,
-                                             const float* sX, float* sW, float* sH, int ldh, bool two_halves = true) {
+                                             const float* sX, float* sW, float* sH, int ldh, bool two_halves,
+                                             const ClamDrop& dr, uint32_t inst_base) {
     const int L1 = L1T ? L1T : L1_rt;                        // L1T != 0: every stride below is a compile-time constant
     constexpr int GPW = (TN == 8) ? 2 : 1;                   // column groups per warp: L1 <= 16 (TN 4, 4 warps), L1 = 32 (TN 8,
                                                              // 4 warps), L1 = 64 / 128 (TN 8, 8 warps)
@@ -308,7 +337,7 @@ __device__ __forceinline__ void clam_fc1_192(const float* __restrict__ W1, const
                     if (i == 1 && !two_halves) break;
                     float v0, v1;
                     f2_unpack(acc[g][i][c], v0, v1);
-                    sH[(lane + 32 * i) * ldh + col] = fmaxf(v0 + v1 + bias, 0.f);
+                    sH[(lane + 32 * i) * ldh + col] = fmaxf(v0 + v1 + bias, 0.f) * clam_keep(dr, inst_base + lane + 32 * i, col);
                 }
             }
         }
@@ -322,7 +351,8 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
                                                                      int n_models, int n_bags, int total_instances, int L1_rt,
                                                                      int D_rt, const int32_t* __restrict__ prefix,
                                                                      const int32_t* __restrict__ work, int work_cap,
-                                                                     float* __restrict__ a_raw, float* __restrict__ partials) {
+                                                                     float* __restrict__ a_raw, float* __restrict__ partials,
+                                                                     const ClamDrop dr) {
     const int L1 = L1T ? L1T : L1_rt, D = L1T ? L1T / 2 : D_rt;    // the HIPT heads have D = L1 / 2 (model_clam.py:81)
     extern __shared__ __align__(16) float smem_clam[];
     const int ldh = L1 + 4;
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
                              : idx < L1 + 3 * D ? w.p[6] + (idx - L1 - 2 * D) : w.p[7];
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sV + idx)), "l"(src) : "memory");
         }
-        clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh);
+        clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh, true, dr, static_cast<uint32_t>(i0));   // dropout: instance index inside its bag
         __syncthreads();
 
         // ---- gated attention score, register-tiled like the first Linear: warp task = 4 gate units (their Wa and Wb rows)
@@ -415,7 +445,9 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
                         float a0, a1, b0, b1v;
                         f2_unpack(acc[i][u], a0, a1);
                         f2_unpack(acc[i][4 + u], b0, b1v);
-                        A = fmaf(Wc[d], tanhf(a0 + a1 + ba[d]) * (1.0f / (1.0f + expf(-(b0 + b1v + bb[d])))), A);
+                        const uint32_t gi = static_cast<uint32_t>(i0 + lane + 32 * i);
+                        const float ka = clam_keep(dr, gi, L1 + d), kb = clam_keep(dr, gi, L1 + D + d);
+                        A = fmaf(Wc[d], (ka * tanhf(a0 + a1 + ba[d])) * (kb / (1.0f + expf(-(b0 + b1v + bb[d])))), A);
                     }
                     sA[task * CL_CH + lane + 32 * i] = A;
                 }
@@ -813,8 +845,12 @@ size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1) {
 int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
                         int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
                         float* a_raw, float* m_out, float* logits, float* y_prob, long long* y_hat, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream) {
+                        size_t workspace_bytes, cudaStream_t stream, float dropout_p, unsigned long long dropout_seed) {
     if (n_bags <= 0) return 0;
+    const ClamDrop dr = clam_drop_make(dropout_p, dropout_seed);
+    const bool dropping = dropout_p > 0.f;
+    if (dropping && !clam_is192(L0, L1, D))
+        return set_error("hb_clam: training-mode dropout is implemented for the HIPT heads (192-d features, L1 <= 128)");
     if (n_models < 1 || n_models > CLAM_MAX_MODELS) return set_error("hb_clam: n_models must be 1..%d", CLAM_MAX_MODELS);
     if (L0 % CLAM_KC != 0) return set_error("hb_clam: L0=%d must be a multiple of %d", L0, CLAM_KC);
     if (L1 < 1 || D < 1 || C < 1 || C > 64) return set_error("hb_clam: bad dims L1=%d D=%d C=%d", L1, D, C);
@@ -845,7 +881,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + off_part);
     static int tc_env = -1;
     if (tc_env < 0) { const char* e = getenv("HB_CLAM_TC"); tc_env = (e && e[0] == '0') ? 0 : 1; }
-    if (tc_env && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
+    if (tc_env && !dropping && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
         // tensor-core path: 128-instance chunks (fewer (bag, chunk) items than the bound computed for CH above)
         clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, TC_M, prefix, work, work_cap);
         count_launch();
@@ -858,7 +894,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * 2 * TC_SLICE_BYTES;
         (void)ntot;
         auto kern = (L1 == 16) ? clam_scores_tc_kernel<16> : clam_scores_tc_kernel<32>;
-        HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 232448)) return -1;
         int grid = (total_instances / TC_M) + n_bags;
         if (grid > work_cap) grid = work_cap;
         if (grid > num_sms()) grid = num_sms();
@@ -894,17 +930,17 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
             else if (L1 == 64) kern = clam_scores192_kernel<8, 64>;
             else if (L1 == 128) kern = clam_scores192_kernel<8, 128>;
         }
-        HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 220 * 1024)) return -1;
         ProfScope ps(10, stream);
         kern<<<work_cap, threads, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags, total_instances, L1, D,
-                                                  prefix, work, work_cap, a_raw, partials);
+                                                  prefix, work, work_cap, a_raw, partials, dr);
         count_launch();
         HB_CUDA_OK(cudaGetLastError());
     } else if (max_chunks > 0) {
         const size_t smem = (static_cast<size_t>(CH) * (CLAM_KC + 1) + CLAM_KC * CLAM_OB + CH + 4 +
                              static_cast<size_t>(CH) * (L1 + 1)) * sizeof(float);
         if (smem > 220 * 1024) return set_error("hb_clam: L1=%d too large for the fused kernel", L1);
-        HB_CUDA_OK(cudaFuncSetAttribute(clam_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(clam_scores_kernel), 220 * 1024)) return -1;
         ProfScope ps(10, stream);
         clam_scores_kernel<<<work_cap, CH, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags, total_instances,
                                                            L0, L1, D, prefix, work, work_cap, a_raw, partials);
@@ -986,7 +1022,8 @@ template <int TN, int L1T>
 __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restrict__ feats, int N,
                                                           const __grid_constant__ ClamModel w, const float* __restrict__ a_raw,
                                                           const float* __restrict__ dA_ext, const float* __restrict__ ctx,
-                                                          const __grid_constant__ ClamGrads g, int L1_rt, int D_rt, int ch) {
+                                                          const __grid_constant__ ClamGrads g, int L1_rt, int D_rt, int ch,
+                                                          const ClamDrop dr) {
     const int L1 = L1T ? L1T : L1_rt, D = L1T ? L1T / 2 : D_rt;
     extern __shared__ __align__(16) float smem_clam[];
     const int ldh = L1 + 4, ldp = 2 * D + 1;
@@ -1026,7 +1063,7 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
         for (int idx = tid; idx < L1; idx += nthreads)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sDM + idx)), "l"(ctx + 4 + idx) : "memory");
     }
-    clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh, ch == 64);   // waits for every cp.async above, ends with a __syncthreads
+    clam_fc1_192<TN, L1T>(w.p[0], sV, L1, sX, sW, sH, ldh, ch == 64, dr, static_cast<uint32_t>(i0));   // waits for every cp.async above, ends with a __syncthreads
     const float gmax = ctx[0], inv_total = ctx[1], s_dot = ctx[2];
     const float* ba = sV + L1; const float* bb = ba + D; const float* Wc = bb + D;
 
@@ -1046,7 +1083,7 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
                 a0 = fmaf(wa.x, h4.x, a0); a1 = fmaf(wa.y, h4.y, a1); a0 = fmaf(wa.z, h4.z, a0); a1 = fmaf(wa.w, h4.w, a1);
                 b0 = fmaf(wb.x, h4.x, b0); b1v = fmaf(wb.y, h4.y, b1v); b0 = fmaf(wb.z, h4.z, b0); b1v = fmaf(wb.w, h4.w, b1v);
             }
-            sAB[inst * ldp + d] = tanhf(a0 + a1);
+            sAB[inst * ldp + d] = tanhf(a0 + a1);                            // pre-dropout branch outputs
             sAB[inst * ldp + D + d] = 1.0f / (1.0f + expf(-(b0 + b1v)));
         }
         if (part == 0) {
@@ -1067,7 +1104,8 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
         const float dA = sDA[inst];
         for (int d = d0; d < d0 + dn; ++d) {
             const float a = sAB[inst * ldp + d], b = sAB[inst * ldp + D + d];
-            const float t = dA * Wc[d];
+            const float ka = clam_keep(dr, i0 + inst, L1 + d), kb = clam_keep(dr, i0 + inst, L1 + D + d);
+            const float t = dA * Wc[d] * ka * kb;                             // A = sum_d Wc_d (ka a)(kb b)
             sDP[inst * ldp + d] = t * b * (1.0f - a * a);
             sDP[inst * ldp + D + d] = t * a * b * (1.0f - b);
         }
@@ -1083,7 +1121,8 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
                 acc = fmaf(sG[d * L1 + j], sDP[inst * ldp + d], acc);
                 acc = fmaf(sG[(D + d) * L1 + j], sDP[inst * ldp + D + d], acc);
             }
-            sDZ[inst * ldh + j] = (sH[inst * ldh + j] > 0.f) ? acc : 0.f;
+            // h1 = keep * relu(z): a dropped unit has h1 = 0 and no gradient, a kept one carries the 1 / (1 - p) scale
+            sDZ[inst * ldh + j] = (sH[inst * ldh + j] > 0.f) ? acc * clam_keep(dr, i0 + inst, j) : 0.f;
         }
     }
     __syncthreads();
@@ -1131,7 +1170,9 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
             atomicAdd(d2 < D ? g.p[3] + d2 : g.p[5] + (d2 - D), acc);
         } else if (task < L1 + 3 * D) {
             const int d = task - L1 - 2 * D;
-            for (int i = 0; i < n_valid; ++i) acc = fmaf(sDA[i], sAB[i * ldp + d] * sAB[i * ldp + D + d], acc);
+            for (int i = 0; i < n_valid; ++i)
+                acc = fmaf(sDA[i] * clam_keep(dr, i0 + i, L1 + d) * clam_keep(dr, i0 + i, L1 + D + d),
+                           sAB[i * ldp + d] * sAB[i * ldp + D + d], acc);
             atomicAdd(g.p[6] + d, acc);
         } else {
             for (int i = 0; i < n_valid; ++i) acc += sDA[i];
@@ -1143,7 +1184,9 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
 int clam_backward_launch(const float* feats, int N, const void* const* weights_host, const float* a_raw, const float* M,
                          const float* dlogits, const float* dM_ext, const float* dA_ext, void* const* grads_host, int L0,
                          int L1, int D, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                         const float* logits = nullptr, const long long* label = nullptr, float* loss_out = nullptr) {
+                         const float* logits = nullptr, const long long* label = nullptr, float* loss_out = nullptr,
+                         float dropout_p = 0.f, unsigned long long dropout_seed = 0) {
+    const ClamDrop dr = clam_drop_make(dropout_p, dropout_seed);
     if (!clam_is192(L0, L1, D)) return set_error("hb_clam_sb_backward: only 192-d features with L1 <= 128 are supported (L0=%d L1=%d D=%d)", L0, L1, D);
     if (N < 1 || C < 1 || C > 64) return set_error("hb_clam_sb_backward: bad dims N=%d C=%d", N, C);
     if (!feats || !weights_host || !a_raw || !M || !grads_host || !workspace) return set_error("hb_clam_sb_backward: null argument");
@@ -1182,9 +1225,9 @@ int clam_backward_launch(const float* feats, int N, const void* const* weights_h
         else if (L1 == 64) kern = clam_bwd192_kernel<8, 64>;
         else if (L1 == 128) kern = clam_bwd192_kernel<8, 128>;
     }
-    HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 220 * 1024)) return -1;
     ProfScope ps(13, stream);
-    kern<<<(N + ch - 1) / ch, threads, smem, stream>>>(feats, N, w, a_raw, dA_ext, ctx, g, L1, D, ch);
+    kern<<<(N + ch - 1) / ch, threads, smem, stream>>>(feats, N, w, a_raw, dA_ext, ctx, g, L1, D, ch, dr);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1252,7 +1295,40 @@ int hb_clam_sb_forward(const float* feats, const int32_t* bag_offsets, int n_bag
                        size_t workspace_bytes, void* stream) {
     return hb::clam_forward_launch(feats, bag_offsets, n_bags, total_instances, max_bag_len, weights_host, n_models, L0,
                                    L1, D, C, a_raw, m_out, logits, y_prob, reinterpret_cast<long long*>(y_hat),
-                                   workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                                   workspace, workspace_bytes, static_cast<cudaStream_t>(stream), 0.f, 0ull);
+}
+int hb_clam_sb_forward_train(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
+                             int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
+                             float* a_raw, float* m_out, float* logits, float* y_prob, int64_t* y_hat, void* workspace,
+                             size_t workspace_bytes, float dropout_p, uint64_t dropout_seed, void* stream) {
+    if (!(dropout_p >= 0.f && dropout_p <= 1.f)) return hb::set_error("hb_clam_sb_forward_train: dropout_p %f outside [0, 1]", dropout_p);
+    return hb::clam_forward_launch(feats, bag_offsets, n_bags, total_instances, max_bag_len, weights_host, n_models, L0,
+                                   L1, D, C, a_raw, m_out, logits, y_prob, reinterpret_cast<long long*>(y_hat),
+                                   workspace, workspace_bytes, static_cast<cudaStream_t>(stream), dropout_p, dropout_seed);
+}
+int hb_clam_sb_backward_train(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
+                              const float* m_pooled, const float* dlogits, const float* dm_ext, const float* da_ext,
+                              const float* logits, const int64_t* label, float* loss_out, void* const* grads_host, int L0,
+                              int L1, int D, int C, void* workspace, size_t workspace_bytes, float dropout_p,
+                              uint64_t dropout_seed, void* stream) {
+    if (!(dropout_p >= 0.f && dropout_p <= 1.f)) return hb::set_error("hb_clam_sb_backward_train: dropout_p %f outside [0, 1]", dropout_p);
+    return hb::clam_backward_launch(feats, n_instances, weights_host, a_raw, m_pooled, dlogits, dm_ext, da_ext, grads_host, L0,
+                                    L1, D, C, workspace, workspace_bytes, static_cast<cudaStream_t>(stream),
+                                    dlogits ? nullptr : logits, reinterpret_cast<const long long*>(label), loss_out, dropout_p,
+                                    dropout_seed);
+}
+int hb_clam_dropout_masks(int n_instances, int L1, int D, float dropout_p, uint64_t dropout_seed, float* m1_host,
+                          float* ma_host, float* mb_host) {
+    if (n_instances < 0 || L1 < 1 || D < 1 || !m1_host || !ma_host || !mb_host) return hb::set_error("hb_clam_dropout_masks: bad argument");
+    const hb::ClamDrop dr = hb::clam_drop_make(dropout_p, dropout_seed);
+    for (int i = 0; i < n_instances; ++i) {
+        for (int j = 0; j < L1; ++j) m1_host[static_cast<size_t>(i) * L1 + j] = hb::clam_keep(dr, i, j);
+        for (int d = 0; d < D; ++d) {
+            ma_host[static_cast<size_t>(i) * D + d] = hb::clam_keep(dr, i, L1 + d);
+            mb_host[static_cast<size_t>(i) * D + d] = hb::clam_keep(dr, i, L1 + D + d);
+        }
+    }
+    return 0;
 }
 int hb_clam_sb_backward(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
                         const float* m_pooled, const float* dlogits, const float* dm_ext, const float* da_ext,

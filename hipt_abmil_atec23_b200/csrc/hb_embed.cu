@@ -200,11 +200,7 @@ int embed_u8_launch(const void* image_u8, size_t chan_stride, size_t row_pitch, 
     const uint32_t box[5] = {256, 4, 8, 1, 1};
     if (encode_tmap_u8_nd(&map_img, image_u8, 5, dims, strides, box)) return -1;
     if (encode_tmap_2d(&map_w, TMAP_BF16, w_f16, 384, 768, 768 * 2, 192, 64)) return -1;      // 2-byte elements: fp16 bits
-    static bool attr_done = false;
-    if (!attr_done) {
-        HB_CUDA_OK(cudaFuncSetAttribute(embed_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM));
-        attr_done = true;
-    }
+    if (set_max_dynamic_smem(reinterpret_cast<const void*>(embed_u8_kernel), EM_SMEM)) return -1;
     const int n_tiles = 2 * n_patches;
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
     embed_u8_kernel<<<grid, EM_THREADS, EM_SMEM, stream>>>(map_img, map_w, bias, scale, pos_table,

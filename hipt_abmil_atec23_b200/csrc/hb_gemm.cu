@@ -767,11 +767,7 @@ template <int BN, int EPI, int CG, int AST>
 static int launch_gemm_cg(const GemmArgs& g, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CG, EPI, AST>;
     auto kern = gemm_bf16_kernel<BN, EPI, CG, AST>;
-    static bool attr_done = false;     // per instantiation
-    if (!attr_done) {
-        HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
-    }
+    if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return -1;
     const int m_tiles = (g.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
     const int n_tiles = g.N / BN;
     const int slots = num_sms() / CG;

@@ -10,6 +10,9 @@ namespace hb {
 
 int set_error(const char* fmt, ...);          // records the message for hb_last_error(), returns -1
 int num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a process that
+// drives several GPUs (HIPT_4K(device256=cuda:0, device4k=cuda:1), nn.DataParallel replicas) opts in on each of them
+int set_max_dynamic_smem(const void* func, int bytes);
 
 #define HB_CUDA_OK(expr)                                                                              \
     do {                                                                                              \
@@ -23,6 +26,7 @@ struct ProfScope {                             // CUDA-event bracket on the laun
     ~ProfScope();
     cudaStream_t st_;
     long long idx_;
+    cudaEvent_t a_, b_;
 };
 
 enum TmapDtype { TMAP_BF16 = 0, TMAP_F32 = 1, TMAP_U8 = 2 };
@@ -77,7 +81,9 @@ int mlp_fused_launch(const void* xb_bf16, const void* w1g_bf16, const float* c1,
 int layernorm_launch(const void* x, int x_is_bf16, size_t x_row_stride, const float* gamma, const float* beta, float eps,
                      void* out_bf16, float* out_f32, int rows, int dim, cudaStream_t stream);
 int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_len, int heads, int head_dim, float scale,
-                     cudaStream_t stream, int cls_only = 0);
+                     cudaStream_t stream, int cls_only = 0, float* cls_probs = nullptr);
+// tcgen05 attention for seq_len 257 / head_dim 64 (hb_attention_tc.cu)
+int attention_tc2_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int heads, float scale, cudaStream_t stream);
 int im2col_launch(const void* image, int image_is_f32, size_t patch_stride, size_t chan_stride, size_t row_pitch,
                   int grid_cols, int patch_begin, int n_patches, void* a_bf16, cudaStream_t stream);
 int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, void* xb_bf16, float* stats, int n_seq,
@@ -86,7 +92,7 @@ int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, vo
 int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
                         int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
                         float* a_raw, float* m_out, float* logits, float* y_prob, long long* y_hat, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream);
+                        size_t workspace_bytes, cudaStream_t stream, float dropout_p = 0.f, unsigned long long dropout_seed = 0);
 size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1);
 
 }  // namespace hb

@@ -402,11 +402,7 @@ int mlp_fused_launch(const void* xb_bf16, const void* w1g_bf16, const float* c1,
     if (encode_tmap_2d(&map_w1, TMAP_BF16, w1g_bf16, MLP_H, MLP_D, MLP_D * 2, 32, 64)) return -1;
     if (encode_tmap_2d(&map_w2, TMAP_BF16, w2h_bf16, MLP_D, MLP_H, MLP_H * 2, 96, 64)) return -1;
     if (encode_tmap_2d(&map_out, TMAP_BF16, xb_bf16, M, MLP_D, MLP_D * 2, 32, 64)) return -1;
-    static bool attr_done = false;
-    if (!attr_done) {
-        HB_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM));
-        attr_done = true;
-    }
+    if (set_max_dynamic_smem(reinterpret_cast<const void*>(mlp_fused_kernel), MLP_SMEM)) return -1;
     const int n_tiles = (M + 255) / 256;
     const int slots = num_sms() / 2;
     const int grid = (n_tiles < slots ? n_tiles : slots) * 2;

@@ -215,17 +215,22 @@ class VitEngine:
                 done += cur
         return cls_f32, cls_bf16
 
-    def forward_grid(self, cls256_bf16, n_regions, w0, h0):
-        """ViT-4K over n_regions grids of w0*h0 ViT-256 CLS tokens: [n_regions*w0*h0, in_dim] bf16 -> [n_regions, dim]."""
+    def forward_grid(self, cls256_bf16, n_regions, w0, h0, out=None):
+        """ViT-4K over n_regions grids of w0*h0 ViT-256 CLS tokens: [n_regions*w0*h0, in_dim] bf16 -> [n_regions, dim]
+        (written into `out` [>= n_regions, dim] fp32 when given: the slide-set pass pools straight out of that buffer)."""
         assert self.kind == "vit4k"
         _lib.require_cuda(cls256_bf16, "cls256")
         T = w0 * h0
         assert cls256_bf16.dtype == torch.bfloat16 and cls256_bf16.is_contiguous()
-        assert cls256_bf16.shape == (n_regions * T, self.in_dim)
+        assert cls256_bf16.shape[0] >= n_regions * T and cls256_bf16.shape[1] == self.in_dim
         pos = self.pos_table(w0, h0)
         cap = max(1, self.max_rows // (T + 1))
         with torch.cuda.device(self.device):
-            out = torch.empty((n_regions, self.dim), dtype=torch.float32, device=self.device)
+            if out is None:
+                out = torch.empty((n_regions, self.dim), dtype=torch.float32, device=self.device)
+            else:
+                assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape[1] == self.dim
+                assert out.shape[0] >= n_regions
             done = 0
             while done < n_regions:
                 cur = min(cap, n_regions - done)
@@ -233,7 +238,7 @@ class VitEngine:
                     self.plan, _lib.ptr(cls256_bf16[done * T:]), cur, T, self.in_dim, _lib.ptr(self.phi_w),
                     _lib.ptr(self.phi_b), _lib.ptr(pos), _lib.ptr(out[done:]), _lib.stream_ptr()))
                 done += cur
-        return out
+        return out[:n_regions]
 
     # ------------------------------------------------------------------------------- attention maps (heatmap helpers)
     def last_selfattention(self, run_prefix, n_seq, seq_len):

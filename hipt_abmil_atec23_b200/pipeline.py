@@ -20,6 +20,7 @@ class SlidePipeline:
         self.device = torch.device(hipt.device256)
         self._stage = None
         self._copy_stream = None
+        self._offs = {}
 
     # ------------------------------------------------------------------------------------------------ device input
     @torch.no_grad()
@@ -30,7 +31,9 @@ class SlidePipeline:
 
     def _pool(self, feats):
         R = feats.shape[0]
-        offs = torch.tensor([0, R], dtype=torch.int32)
+        offs = self._offs.get(R)
+        if offs is None:                                           # built once per bag size, on the device
+            offs = self._offs[R] = torch.tensor([0, R], dtype=torch.int32, device=feats.device)
         r = clam_engine.forward_bags(self.clam_models, feats, offs, max_bag_len=R, want=("logits", "y_prob", "y_hat"))
         r["features"] = feats
         return r
@@ -61,8 +64,8 @@ class SlidePipeline:
                 with torch.cuda.stream(self._copy_stream):
                     if g >= 2:
                         self._copy_stream.wait_event(consumed[b])
-                    else:
-                        self._copy_stream.wait_stream(main)
+                    elif g == 0:                                   # g == 1: staging buffer 1 has no consumer yet in this call
+                        self._copy_stream.wait_stream(main)        # orders against the previous call's use of the buffers
                     self._stage[b, :n].copy_(regions_u8_pinned[r0:r0 + n], non_blocking=True)
                     copied[b].record(self._copy_stream)
                 main.wait_event(copied[b])

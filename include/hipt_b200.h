@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 3
+#define HB_ABI_VERSION 4
 
 /* GEMM epilogues */
 #define HB_EPI_BIAS_BF16 0        /* out_bf16[M,N]  = A W^T + bias                                  */
@@ -222,6 +222,28 @@ int hb_clam_sb_backward_ce(const float* feats, int n_instances, const void* cons
                            const float* m_pooled, const float* logits, const int64_t* label, float* loss_out,
                            void* const* grads_host, int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes,
                            void* stream);
+
+/* Training-mode CLAM_SB with ACTIVE dropout (the reference trains its final model at --drop_out 0.85, docs/README.md:186-193):
+ * nn.Dropout(p) after the ReLU (models/model_clam.py:84-85) and inside both gate branches of Attn_Net_Gated (:50-52).
+ * The keep decision of (instance, unit) is a counter-based hash of dropout_seed — nothing is stored, the recomputing
+ * backward regenerates the forward's masks; kept units are scaled by 1 / (1 - p) like torch.  Instance = index inside its
+ * bag; units [0,L1) ReLU outputs, [L1,L1+D) branch a, [L1+D,L1+2D) branch b.  HIPT heads only (192-d features, L1 <= 128).
+ * hb_clam_sb_forward_train: hb_clam_sb_forward + (dropout_p, dropout_seed).
+ * hb_clam_sb_backward_train: hb_clam_sb_backward (dlogits given) or hb_clam_sb_backward_ce (dlogits NULL: logits + label)
+ * with the same (dropout_p, dropout_seed) as the forward it differentiates.
+ * hb_clam_dropout_masks: the masks themselves ([N,L1], [N,D], [N,D] fp32 HOST arrays holding 0 or 1/(1-p)), for parity
+ * tests against the reference module and for the instance-clustering branch (inst_eval reads rows of the dropped h). */
+int hb_clam_sb_forward_train(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
+                             int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
+                             float* a_raw, float* m_out, float* logits, float* y_prob, int64_t* y_hat, void* workspace,
+                             size_t workspace_bytes, float dropout_p, uint64_t dropout_seed, void* stream);
+int hb_clam_sb_backward_train(const float* feats, int n_instances, const void* const* weights_host, const float* a_raw,
+                              const float* m_pooled, const float* dlogits, const float* dm_ext, const float* da_ext,
+                              const float* logits, const int64_t* label, float* loss_out, void* const* grads_host, int L0,
+                              int L1, int D, int C, void* workspace, size_t workspace_bytes, float dropout_p,
+                              uint64_t dropout_seed, void* stream);
+int hb_clam_dropout_masks(int n_instances, int L1, int D, float dropout_p, uint64_t dropout_seed, float* m1_host,
+                          float* ma_host, float* mb_host);
 
 /* Multi-tensor Adam with L2 weight decay in one launch, torch.optim.Adam semantics (utils/utils.py:100-107 get_optim:
  * optim.Adam(..., lr, weight_decay=reg)): g += wd p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;

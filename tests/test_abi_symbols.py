@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_error_string():
     from hipt_abmil_atec23_b200 import _lib
     lib = _lib.load()
-    assert lib.hb_abi_version() == 3
+    assert lib.hb_abi_version() == 4
     assert isinstance(lib.hb_last_error(), bytes)
     # [prefix: n_bags + 1 ints][work: 2 ints per (bag, chunk) item][partials: n_models x items x (L1 + 2) floats], items bounded
     # with the smallest chunk (32 instances); each part 16-byte aligned

@@ -271,6 +271,37 @@ def test_attention(n_seq, S, heads, hd):
     assert err < 2e-2, err
 
 
+@pytest.mark.parametrize("n_seq", [5, 160])
+def test_attention_tc_dominant_keys_and_large_scores(n_seq):
+    """The tcgen05 kernel merges two key halves with separate (max, sum) and handles key / query 256 outside the 128-wide
+    tiles: put the dominant key of a row in either half, at key 256, or nowhere (flat rows), with scores up to ~+-60."""
+    L = _lib()
+    S, heads, hd = 257, 6, 64
+    D = heads * hd
+    g = torch.Generator().manual_seed(31)
+    qkv = torch.randn((n_seq, S, 3, heads, hd), generator=g)
+    qkv[:, :, 0] *= 2.0                                            # larger logits
+    for s in range(n_seq):                                         # sequence s: key (s * 37) % 257 dominates every row of head s % 6
+        kd = (s * 37) % S
+        qkv[s, kd, 1, s % heads] = 0.0
+        qkv[s, kd, 1, s % heads, : hd // 2] = 3.0
+        qkv[s, :, 0, s % heads, : hd // 2] += 2.5
+    qkv[0, :, 1, 1] = 0.0                                          # head 1 of sequence 0: all scores equal (flat softmax)
+    qkv = qkv.reshape(n_seq * S, 3 * D).cuda().bfloat16()
+    scale = hd ** -0.5
+    out = L.attention(qkv, n_seq, S, heads, hd, scale)
+    q, k, v = qkv.float().view(n_seq, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = ((q @ k.transpose(-2, -1)) * scale).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(n_seq * S, D)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err
+    # row 256 (the tail tile) and rows 0 / 128 (first rows of the two full tiles) separately
+    o3, r3 = out.float().view(n_seq, S, D), ref.view(n_seq, S, D)
+    for row in (0, 127, 128, 255, 256):
+        assert (o3[:, row] - r3[:, row]).abs().max().item() < 3e-2, row
+
+
 @pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
 def test_im2col(dtype):
     L = _lib()

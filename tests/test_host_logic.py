@@ -147,3 +147,101 @@ def test_bag_assembly_world_size_2_gloo(counts):
     assert all(ok for _, ok, _ in res)
     owned = [set(b) for _, _, b in sorted(res)]
     assert owned[0] | owned[1] == {s for s, n in enumerate(counts) if n}    # every slide's bag exists somewhere
+
+
+# --------------------------------------------------------------------------------------------- slide-set layout (config 3/5)
+def _ragged_counts(total=2000, lo=10, hi=300, seed=6):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    while sum(out) < total:
+        out.append(min(int(torch.randint(lo, hi + 1, (1,), generator=g)), total - sum(out)))
+    return out
+
+
+@pytest.mark.parametrize("policy", ["contiguous", "lpt"])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_slide_set_layout_simulated_ranks(policy, world):
+    """Every rank's layout, run in one process: feature of global region g is the constant g; after the (simulated)
+    collective every slide's bag must be arange(first, first + n) on exactly one rank."""
+    from hipt_abmil_atec23_b200.sharding import SlideSetLayout, assemble_owned_bags
+    for counts in (_ragged_counts(), [50] * 40, [7], [301, 10, 20, 30], [0, 5, 0, 9]):
+        L = SlideSetLayout(counts, world, policy)
+        total = sum(counts)
+        assert sorted(g for lay in L.ranks for g in lay.regions) == list(range(total))
+        if policy == "contiguous":
+            assert max(L.load()) - min(L.load()) <= 1
+            assert len(L.spanning) <= max(world - 1, 0)
+        F = 4
+        caps = [max(len(lay.regions), 1) for lay in L.ranks]
+        sends = []
+        for lay in L.ranks:                                       # what each rank would contribute to the all-gather
+            send = torch.zeros(L.pad_rows, F)
+            if lay.send_index:
+                send[:len(lay.send_index)] = torch.tensor([lay.regions[i] for i in lay.send_index], dtype=torch.float32)[:, None]
+            sends.append(send)
+        gathered = torch.cat(sends) if L.needs_collective else torch.zeros(0, F)
+        owners = {}
+        for lay, cap in zip(L.ranks, caps):
+            pool = torch.full((cap + gathered.shape[0], F), -1.0)
+            if lay.regions:
+                pool[:len(lay.regions)] = torch.tensor(lay.regions, dtype=torch.float32)[:, None]
+            pool[cap:] = gathered
+            clam_in = torch.full((max(lay.bag_offsets[-1], 1), F), -1.0)
+            bags = assemble_owned_bags(L, lay, pool, cap, None, None, torch.tensor(lay.pool_rows(cap), dtype=torch.int64),
+                                       clam_in, collective=False)
+            assert bags.shape[0] == lay.bag_offsets[-1]
+            for i, s in enumerate(lay.owned):
+                bag = bags[lay.bag_offsets[i]:lay.bag_offsets[i + 1]]
+                want = torch.arange(L.first_region[s], L.first_region[s + 1], dtype=torch.float32)
+                assert torch.equal(bag[:, 0], want) and torch.equal(bag[:, 3], want), (policy, world, s)
+                assert s not in owners
+                owners[s] = lay.rank
+        assert sorted(owners) == [s for s, n in enumerate(counts) if n]
+        for s, home in L.home.items():
+            assert owners[s] == home and home in L.spanning[s]
+
+
+def _gloo_slideset_worker(rank, world, port, counts, policy, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from hipt_abmil_atec23_b200.sharding import SlideSetLayout, assemble_owned_bags
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = SlideSetLayout(counts, world, policy)
+    lay = L.ranks[rank]
+    cap = max(len(lay.regions), 1)
+    pool = torch.zeros(cap + (world * L.pad_rows if L.needs_collective else 0), 192)
+    if lay.regions:
+        pool[:len(lay.regions)] = torch.tensor(lay.regions, dtype=torch.float32)[:, None]
+    send = torch.zeros(L.pad_rows, 192)
+    clam_in = torch.empty(max(lay.bag_offsets[-1], 1), 192)
+    bags = assemble_owned_bags(L, lay, pool, cap, send, torch.tensor(lay.send_index, dtype=torch.int64),
+                               torch.tensor(lay.pool_rows(cap), dtype=torch.int64), clam_in)
+    ok = True
+    for i, s in enumerate(lay.owned):
+        want = torch.arange(L.first_region[s], L.first_region[s + 1], dtype=torch.float32)
+        bag = bags[lay.bag_offsets[i]:lay.bag_offsets[i + 1]]
+        ok &= bag.shape[0] == counts[s] and torch.equal(bag[:, 0], want) and torch.equal(bag[:, 191], want)
+    q.put((rank, ok, list(lay.owned), bool(L.needs_collective)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts,policy", [(None, "contiguous"), ([301, 10, 20, 30], "lpt"), ([7], "contiguous"),
+                                           ([12, 12, 12, 12], "contiguous")])
+def test_slide_set_assembly_world_size_2_gloo(counts, policy):
+    counts = _ragged_counts(200, 5, 40) if counts is None else counts
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + sum(counts) + len(policy)) % 2000
+    procs = [ctx.Process(target=_gloo_slideset_worker, args=(r, 2, port, counts, policy, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res)
+    owned = [set(o) for _, _, o, _ in sorted(res)]
+    assert not (owned[0] & owned[1])                                        # a bag is pooled on exactly one rank
+    assert owned[0] | owned[1] == {s for s, n in enumerate(counts) if n}
