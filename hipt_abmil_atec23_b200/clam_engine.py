@@ -30,6 +30,67 @@ def _weights(model, device):
     return out
 
 
+# ------------------------------------------------------------------------------------------------- training-mode dropout
+_M32 = 0xFFFFFFFF
+
+
+def _mul32(h, c):
+    """(h * c) mod 2^32 on int64 tensors holding uint32 values (the product itself would overflow int64)."""
+    return ((h & 0xFFFF) * c + ((((h >> 16) * c) & 0xFFFF) << 16)) & _M32
+
+
+def _mix32(h):
+    h = h ^ (h >> 16)
+    h = _mul32(h, 0x85EBCA6B)
+    h = h ^ (h >> 13)
+    h = _mul32(h, 0xC2B2AE35)
+    return h ^ (h >> 16)
+
+
+def dropout_keep(seed, instances, unit0, n_units, p):
+    """torch restatement of clam_keep() in csrc/hb_clam.cu for chosen instances: [len(instances), n_units] fp32 holding 0 or
+    1 / (1 - p) for units unit0 .. unit0 + n_units - 1 (units: [0,L1) ReLU outputs, [L1,L1+D) gate branch a, then branch b).
+    `instances`: int64 tensor of instance indices inside the bag (any device)."""
+    inst = instances.to(torch.int64).view(-1, 1)
+    if p <= 0.0:
+        return torch.ones((inst.shape[0], n_units), dtype=torch.float32, device=inst.device)
+    if p >= 1.0:
+        return torch.zeros((inst.shape[0], n_units), dtype=torch.float32, device=inst.device)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    lo, hi = seed & _M32, seed >> 32
+    thresh = min(max(int(float(torch.tensor(p, dtype=torch.float32)) * 4294967296.0 + 0.5), 1), 4294967295)
+    unit = torch.arange(unit0, unit0 + n_units, dtype=torch.int64, device=inst.device).view(1, -1)
+    a = _mix32((_mul32(inst, 0x9E3779B1) + lo) & _M32)
+    h = _mix32(a ^ ((_mul32(unit, 0x7FEB352D) + hi) & _M32))
+    scale = float(1.0 / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32)))
+    return (h >= thresh).to(torch.float32) * scale
+
+
+def dropout_masks(n_instances, L1, D, p, seed):
+    """(m1 [N,L1], ma [N,D], mb [N,D]) exactly as the kernels apply them — from the C library's own host routine
+    (hb_clam_dropout_masks); parity tests multiply them into the reference module's activations."""
+    lib = _lib.load()
+    m1 = torch.empty((n_instances, L1), dtype=torch.float32)
+    ma = torch.empty((n_instances, D), dtype=torch.float32)
+    mb = torch.empty((n_instances, D), dtype=torch.float32)
+    _lib.check(lib.hb_clam_dropout_masks(n_instances, L1, D, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, m1.data_ptr(), ma.data_ptr(),
+                                         mb.data_ptr()))
+    return m1, ma, mb
+
+
+def dropout_p(model):
+    """Dropout probability of a CLAM_SB as nn.Dropout will apply it (a YAML `drop_out: true` arrives as p = True = 1.0)."""
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            return float(m.p)
+    return 0.0
+
+
+def draw_seed():
+    """A fresh 62-bit dropout seed from torch's CPU generator (torch.manual_seed makes a training run reproducible)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
 def forward_bags(models, feats, bag_offsets, max_bag_len=None, want=("logits", "y_prob", "y_hat", "m")):
     """models: list of CLAM_SB (same size_arg / n_classes); feats [total, L0] fp32 CUDA; bag_offsets int32 [n_bags+1]
     (CUDA or CPU).  Returns dict with a_raw [n_models, total] and the requested per-bag outputs [n_models, n_bags, ...]."""
@@ -110,7 +171,7 @@ class ClamSBFunction(torch.autograd.Function):
     gradients flow to the 10 weight tensors (not to the bag: features are frozen HIPT_4K embeddings)."""
 
     @staticmethod
-    def forward(ctx, h, *params):
+    def forward(ctx, h, drop_p, drop_seed, *params):
         lib = _lib.load()
         dev = h.device
         if h.dtype != torch.float32 or not h.is_contiguous():
@@ -127,11 +188,12 @@ class ClamSBFunction(torch.autograd.Function):
             y_prob = torch.empty((1, Cc), dtype=torch.float32, device=dev)
             ws_bytes = lib.hb_clam_workspace_bytes(N, 1, 1, L1)
             ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-            _lib.check(lib.hb_clam_sb_forward(_lib.ptr(h), _lib.ptr(offs), 1, N, N, arr, 1, L0, L1, D, Cc, _lib.ptr(a_raw),
-                                              _lib.ptr(m_out), _lib.ptr(logits), _lib.ptr(y_prob), None, _lib.ptr(ws),
-                                              ws.numel(), _lib.stream_ptr()))
+            _lib.check(lib.hb_clam_sb_forward_train(_lib.ptr(h), _lib.ptr(offs), 1, N, N, arr, 1, L0, L1, D, Cc, _lib.ptr(a_raw),
+                                                    _lib.ptr(m_out), _lib.ptr(logits), _lib.ptr(y_prob), None, _lib.ptr(ws),
+                                                    ws.numel(), float(drop_p), int(drop_seed), _lib.stream_ptr()))
         ctx.save_for_backward(h, a_raw, m_out, y_prob, *w)
         ctx.dims = (N, L0, L1, D, Cc)
+        ctx.drop = (float(drop_p), int(drop_seed))
         return logits, y_prob, a_raw, m_out
 
     @staticmethod
@@ -151,17 +213,30 @@ class ClamSBFunction(torch.autograd.Function):
             warr = (C.c_void_p * 10)(*[t.data_ptr() for t in w])
             garr = (C.c_void_p * 10)(*[t.data_ptr() for t in grads])
             ws = torch.empty(4 + L1, dtype=torch.float32, device=dev)
-            _lib.check(lib.hb_clam_sb_backward(_lib.ptr(h), N, warr, _lib.ptr(a_raw), _lib.ptr(m_out), _lib.ptr(dl),
-                                               _lib.ptr(gm), _lib.ptr(ga), garr, L0, L1, D, Cc, _lib.ptr(ws),
-                                               ws.numel() * 4, _lib.stream_ptr()))
-        return (None, *grads)
+            _lib.check(lib.hb_clam_sb_backward_train(_lib.ptr(h), N, warr, _lib.ptr(a_raw), _lib.ptr(m_out), _lib.ptr(dl),
+                                                     _lib.ptr(gm), _lib.ptr(ga), None, None, None, garr, L0, L1, D, Cc,
+                                                     _lib.ptr(ws), ws.numel() * 4, ctx.drop[0], ctx.drop[1], _lib.stream_ptr()))
+        return (None, None, None, *grads)
 
 
-def forward_single_autograd(model, h):
-    """(logits, Y_prob, Y_hat, A_raw, M) with autograd through the fused kernels (training: main.py -> train_loop)."""
-    logits, y_prob, a_raw, m = ClamSBFunction.apply(h, *_param_list(model))
+def forward_single_autograd(model, h, drop_p=0.0, drop_seed=0):
+    """(logits, Y_prob, Y_hat, A_raw, M) with autograd through the fused kernels (training: main.py -> train_loop).
+    drop_p > 0: training-mode dropout with the masks of `drop_seed` in the forward and the backward."""
+    logits, y_prob, a_raw, m = ClamSBFunction.apply(h, float(drop_p), int(drop_seed), *_param_list(model))
     y_hat = torch.topk(logits, 1, dim=1)[1]
     return logits, y_prob, y_hat, a_raw, m
+
+
+def h1_rows(model, h, idx, drop_p=0.0, drop_seed=0):
+    """Rows `idx` of the [N, L1] instance features attention_net[0..2] produces (Linear, ReLU, Dropout) — the only part of `h`
+    the instance-clustering branch reads (inst_eval / inst_eval_out index_select 2 k_sample rows, model_clam.py:116-145).
+    A [len(idx), 192] x [192, L1] product in torch ops, differentiable w.r.t. fc.weight / fc.bias; with active dropout the
+    rows carry the same keep mask the fused kernels applied."""
+    fc = model.attention_net[0]
+    rows = torch.relu(torch.nn.functional.linear(h.index_select(0, idx), fc.weight, fc.bias))
+    if drop_p > 0.0:
+        rows = rows * dropout_keep(drop_seed, idx, 0, fc.out_features, drop_p)
+    return rows
 
 
 class TrainStep:
@@ -171,11 +246,15 @@ class TrainStep:
     once; `step(bag, label)` returns the loss as a device scalar (no host synchronisation).  The autograd route
     (CLAM_SB.forward + loss.backward()) gives the same gradients; this one removes its per-step Python / autograd overhead."""
 
-    def __init__(self, model, optimizer, max_instances):
+    def __init__(self, model, optimizer, max_instances, seed=0):
         if not supports_fused_backward(model):
             raise RuntimeError("TrainStep covers the HIPT head sizes (192-d features, L1 <= 128)")
         self.model, self.opt = model, optimizer
         self.params = _param_list(model)
+        if not all(p.requires_grad for p in self.params):
+            raise RuntimeError("TrainStep updates all 10 CLAM_SB tensors: a frozen parameter needs the autograd route")
+        self.drop_p = dropout_p(model)                       # nn.Dropout p of the module (0.85 in the reference's final config)
+        self.seed, self.n_steps = int(seed), 0
         dev = self.params[0].device
         self.dev = dev
         self.L0, self.L1 = 192, self.params[0].shape[0]
@@ -189,10 +268,11 @@ class TrainStep:
         self.offs = torch.zeros(2, dtype=torch.int32, device=dev)
         self.ws_f = torch.empty(max(lib.hb_clam_workspace_bytes(self.maxn, 1, 1, self.L1), 16), dtype=torch.uint8, device=dev)
         self.ws_b = f32(4 + self.L1)
-        for p in self.params:
-            p.grad = torch.zeros_like(p)
+        # the gradient buffers are OWNED here: optimizer.zero_grad(set_to_none=True) or a reassigned .grad cannot leave the
+        # backward kernel writing into freed memory; step() re-attaches them before the optimizer runs
+        self.grads = [torch.zeros_like(p) for p in self.params]
         self.warr = (C.c_void_p * 10)(*[p.data_ptr() for p in self.params])
-        self.garr = (C.c_void_p * 10)(*[p.grad.data_ptr() for p in self.params])
+        self.garr = (C.c_void_p * 10)(*[g.data_ptr() for g in self.grads])
 
     @torch.no_grad()
     def step(self, bag, label):
@@ -203,14 +283,25 @@ class TrainStep:
         if bag.dtype != torch.float32 or not bag.is_contiguous():
             bag = bag.float().contiguous()
         lib, st = self.lib, _lib.stream_ptr()
+        drop = self.drop_p if self.model.training else 0.0
+        seed = (self.seed + 0x9E3779B97F4A7C15 * (self.n_steps + 1)) & 0x3FFFFFFFFFFFFFFF      # a new mask every step
+        self.n_steps += 1
+        for p, w in zip(self.params, (self.warr[i] for i in range(10))):
+            if p.data_ptr() != w:
+                raise RuntimeError("a CLAM_SB parameter was re-allocated after TrainStep was built")
         with torch.cuda.device(self.dev):
             self.offs[1] = N
-            _lib.check(lib.hb_clam_sb_forward(_lib.ptr(bag), _lib.ptr(self.offs), 1, N, N, self.warr, 1, self.L0, self.L1, self.D,
-                                              self.C, _lib.ptr(self.a_raw), _lib.ptr(self.m_out), _lib.ptr(self.logits),
-                                              _lib.ptr(self.y_prob), None, _lib.ptr(self.ws_f), self.ws_f.numel(), st))
-            _lib.check(lib.hb_clam_sb_backward_ce(_lib.ptr(bag), N, self.warr, _lib.ptr(self.a_raw), _lib.ptr(self.m_out),
-                                                  _lib.ptr(self.logits), _lib.ptr(label), _lib.ptr(self.loss), self.garr, self.L0,
-                                                  self.L1, self.D, self.C, _lib.ptr(self.ws_b), self.ws_b.numel() * 4, st))
+            _lib.check(lib.hb_clam_sb_forward_train(_lib.ptr(bag), _lib.ptr(self.offs), 1, N, N, self.warr, 1, self.L0, self.L1,
+                                                    self.D, self.C, _lib.ptr(self.a_raw), _lib.ptr(self.m_out), _lib.ptr(self.logits),
+                                                    _lib.ptr(self.y_prob), None, _lib.ptr(self.ws_f), self.ws_f.numel(), drop, seed, st))
+            _lib.check(lib.hb_clam_sb_backward_train(_lib.ptr(bag), N, self.warr, _lib.ptr(self.a_raw), _lib.ptr(self.m_out), None,
+                                                     None, None, _lib.ptr(self.logits), _lib.ptr(label), _lib.ptr(self.loss),
+                                                     self.garr, self.L0, self.L1, self.D, self.C, _lib.ptr(self.ws_b),
+                                                     self.ws_b.numel() * 4, drop, seed, st))
+        for p, g in zip(self.params, self.grads):
+            if p.grad is not g:
+                p.grad = g
+        self.last_seed = seed
         self.opt.step()
         return self.loss
 
@@ -222,6 +313,19 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    def _launch(self, lib, group, chunk, step):
+        n = len(chunk)
+        grads = [p.grad.contiguous() for p in chunk]
+        parr = (C.c_void_p * n)(*[p.data_ptr() for p in chunk])
+        garr = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+        marr = (C.c_void_p * n)(*[self.state[p]["exp_avg"].data_ptr() for p in chunk])
+        varr = (C.c_void_p * n)(*[self.state[p]["exp_avg_sq"].data_ptr() for p in chunk])
+        narr = (C.c_int * n)(*[p.numel() for p in chunk])
+        with torch.cuda.device(chunk[0].device):
+            _lib.check(lib.hb_adam_step(parr, garr, marr, varr, narr, n, float(group["lr"]), float(group["betas"][0]),
+                                        float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
+                                        step, _lib.stream_ptr()))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -242,20 +346,14 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-            step = self.state[ps[0]]["step"] + 1
-            for i in range(0, len(ps), 16):
-                chunk = ps[i:i + 16]
-                n = len(chunk)
-                grads = [p.grad.contiguous() for p in chunk]
-                parr = (C.c_void_p * n)(*[p.data_ptr() for p in chunk])
-                garr = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
-                marr = (C.c_void_p * n)(*[self.state[p]["exp_avg"].data_ptr() for p in chunk])
-                varr = (C.c_void_p * n)(*[self.state[p]["exp_avg_sq"].data_ptr() for p in chunk])
-                narr = (C.c_int * n)(*[p.numel() for p in chunk])
-                with torch.cuda.device(chunk[0].device):
-                    _lib.check(lib.hb_adam_step(parr, garr, marr, varr, narr, n, float(group["lr"]), float(group["betas"][0]),
-                                                float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
-                                                step, _lib.stream_ptr()))
+            # torch.optim.Adam keeps one step count PER PARAMETER (a tensor whose grad was None on some steps lags behind):
+            # tensors are bucketed by their own count, one launch per bucket of up to 16
+            buckets = {}
             for p in ps:
-                self.state[p]["step"] = step
+                buckets.setdefault(self.state[p]["step"] + 1, []).append(p)
+            for step, bps in sorted(buckets.items()):
+                for i in range(0, len(bps), 16):
+                    self._launch(lib, group, bps[i:i + 16], step)
+            for p in ps:
+                self.state[p]["step"] += 1
         return loss

@@ -25,6 +25,16 @@
 
 namespace hb {
 
+#ifdef HB_EXP_TRACE
+// timing experiment only (tools/build_exp.sh NAME -DHB_EXP_TRACE, tools/exp_at2_trace.py): clock64 stamps of CTA 0
+__device__ long long g_at2_trace[4 * 64 * 16];
+#define AT2_TRACE(role, it, k) do { if (blockIdx.x == 0 && (it) < 64 && lane == 0 && (warp < 4 || (warp & 3) == 0)) g_at2_trace[((role) * 64 + (it)) * 16 + (k)] = clock64(); } while (0)
+#define AT2_TRACE_UNIT(k) do { if (blockIdx.x == 0 && tr_j < 64 && (threadIdx.x & 127) == 0) g_at2_trace[(tr_w * 64 + tr_j) * 16 + (k)] = clock64(); } while (0)
+#else
+#define AT2_TRACE(role, it, k) do { } while (0)
+#define AT2_TRACE_UNIT(k) do { } while (0)
+#endif
+
 constexpr int AT2_THREADS = 384;
 constexpr int AT2_S = 257;
 constexpr int AT2_KV_BYTES = 272 * 128;                 // [272 keys][64 bf16], 128-byte swizzled rows
@@ -55,11 +65,12 @@ __device__ __forceinline__ float at2_hi(uint32_t w) { return __uint_as_float(w &
 // One unit of a softmax thread: its row of S (128 scores in the unit's TMEM columns) -> P (bf16, back into columns 0..63).
 // `extra` is the score against key 256 (half B) or -inf (half A).  Returns the row's maximum (raw score units) and sum.
 __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, float scale_log2, float& m_out, float& l_out,
-                                                 float& p_extra) {
+                                                 float& p_extra, int tr_w = 0, int tr_j = 99, int tr_k = 0) {
     uint32_t sv[128];
 #pragma unroll
     for (int c = 0; c < 4; ++c) at2_ld32(t_unit + c * 32, sv + c * 32);
     tmem_ld_wait();
+    AT2_TRACE_UNIT(tr_k);
     float m0 = extra, m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
     m0 = fmaxf(m0, __uint_as_float(sv[0]));
 #pragma unroll
@@ -69,6 +80,7 @@ __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, f
     }
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     const float neg_m = -m * scale_log2;
+    AT2_TRACE_UNIT(tr_k + 1);
     const f32x2_t c2 = f2_pack(scale_log2, scale_log2), n2 = f2_pack(neg_m, neg_m);
     f32x2_t sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
@@ -87,6 +99,7 @@ __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, f
     }
     float s0, s1;
     f2_unpack(sum2, s0, s1);
+    AT2_TRACE_UNIT(tr_k + 2);
     p_extra = at2_ex2(fmaf(extra, scale_log2, neg_m));  // exp2(-inf) = 0 for half A
     m_out = m;
     l_out = s0 + s1 + p_extra;
@@ -193,6 +206,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (j > 0) mbar_wait(&u_free[2 * w + half], (j - 1) & 1);
+                AT2_TRACE(2 + w, j, 4 + 2 * half);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -202,6 +216,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                     if (half) umma_commit(&q_empty[w]);
                 }
                 __syncwarp();
+                AT2_TRACE(2 + w, j, 5 + 2 * half);
             }
         };
 
@@ -212,6 +227,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 mbar_wait(&p_full[2 * w + half], j & 1);
+                AT2_TRACE(2 + w, j, 2 * half);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t t_u = half ? t_b : t_a;
@@ -224,11 +240,24 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                     if (half) umma_commit(&kv_empty[st]);
                 }
                 __syncwarp();
+                AT2_TRACE(2 + w, j, 1 + 2 * half);
             }
             if (j + 1 < my_tiles) issue_s(j + 1);
         }
     } else if (warp == 3) {
         setmaxnreg_dec<56>();                                 // idle warp of the first warpgroup (the instruction is warpgroup-wide)
+#ifdef HB_EXP_TRACE
+        // observer: completion times of warpgroup 0's MMAs (s_full / o_full of its two units), role 2 slots 8..11
+        if (lane == 0) {
+            const int my_tiles0 = (n_tiles + 1) >> 1;
+            for (int j = 0; j < my_tiles0; ++j) {
+                mbar_wait(&s_full[0], j & 1); AT2_TRACE(2, j, 8);
+                mbar_wait(&s_full[1], j & 1); AT2_TRACE(2, j, 9);
+                mbar_wait(&o_full[0], j & 1); AT2_TRACE(2, j, 10);
+                mbar_wait(&o_full[1], j & 1); AT2_TRACE(2, j, 11);
+            }
+        }
+#endif
     } else {
         // ------------------------------------------------------------------------------------------ softmax warpgroups
         setmaxnreg_inc<224>();
@@ -249,8 +278,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
             const bool active = !tail || quad == ((it >> 1) & 3);       // warp-uniform: the tail tile has one real row
 
             // ---- score against key 256: q_r . k_256 (row 256 of K is row 0 of its own swizzle atom: unswizzled)
+            AT2_TRACE(w, j, 0);
             mbar_wait(&kv_full[st], (it >> 1) & 1);
             mbar_wait(&q_full[w], j & 1);
+            AT2_TRACE(w, j, 1);
             float s256 = 0.f;
             if (active) {
                 const uint4* k256 = reinterpret_cast<const uint4*>(sK + st * AT2_KV_BYTES + 2 * AT2_TILE_BYTES);
@@ -273,15 +304,23 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
             // ---- the two units: S -> P, each with its own statistics
             float m_a = 0.f, l_a = 1.f, m_b = 0.f, l_b = 1.f, p256 = 0.f, unused;
             mbar_wait(&s_full[2 * w], j & 1);
+            AT2_TRACE(w, j, 2);
             tc_fence_after();
+#ifdef HB_EXP_TRACE
+            if (active) at2_softmax_unit(t_row, -INFINITY, scale_log2, m_a, l_a, unused, w, j, 11);
+#else
             if (active) at2_softmax_unit(t_row, -INFINITY, scale_log2, m_a, l_a, unused);
+#endif
             tc_fence_before();
             mbar_arrive(&p_full[2 * w]);
+            AT2_TRACE(w, j, 3);
             mbar_wait(&s_full[2 * w + 1], j & 1);
+            AT2_TRACE(w, j, 4);
             tc_fence_after();
             if (active) at2_softmax_unit(t_row + 128, s256, scale_log2, m_b, l_b, p256);
             tc_fence_before();
             mbar_arrive(&p_full[2 * w + 1]);
+            AT2_TRACE(w, j, 5);
 
             // ---- merge weights of the two halves
             const float m = fmaxf(m_a, m_b);
@@ -293,11 +332,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
             uint32_t oa[64];
             uint4 res[8];
             mbar_wait(&o_full[2 * w], j & 1);
+            AT2_TRACE(w, j, 6);
             tc_fence_after();
             if (active) { at2_ld32(t_row + 64, oa); at2_ld32(t_row + 96, oa + 32); tmem_ld_wait(); }
             tc_fence_before();
             mbar_arrive(&u_free[2 * w]);
+            AT2_TRACE(w, j, 7);
             mbar_wait(&o_full[2 * w + 1], j & 1);
+            AT2_TRACE(w, j, 8);
             tc_fence_after();
             if (active) {
                 const uint4* v256 = reinterpret_cast<const uint4*>(sV + st * AT2_KV_BYTES + 2 * AT2_TILE_BYTES);
@@ -328,6 +370,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
             }
             tc_fence_before();
             mbar_arrive(&u_free[2 * w + 1]);
+            AT2_TRACE(w, j, 9);
             mbar_arrive(&kv_empty[st]);
 
             if (!tail) {
@@ -338,6 +381,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                 for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(o_row + ((q ^ sw) << 4)) = res[q];
                 fence_proxy_async_smem();
                 named_bar_sync(4 + w, 128);
+                AT2_TRACE(w, j, 10);
                 if (leader) {
                     tma_store_2d(&map_out, sO + w * AT2_TILE_BYTES, h * 64, seq * AT2_S + t * 128);
                     tma_store_commit();
@@ -372,5 +416,11 @@ int attention_tc2_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int he
     HB_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+#ifdef HB_EXP_TRACE
+extern "C" int hb_exp_read_at2_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_at2_trace, sizeof(long long) * 4 * 64 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // namespace hb

@@ -2,11 +2,12 @@
 
 CLAM_SB with gated attention — the model the HIPT-ABMIL pipeline trains and evaluates — runs its inference forward
 (`model(h)`, `model(h, attention_only=True)`, `return_features=True`) through the fused ragged-bag CUDA kernel in
-csrc/hb_clam.cu, and its training step (autograd enabled, HIPT sizes, dropout 0 as in the final ensemble config) through
-the same forward plus the fused recomputing backward (clam_engine.ClamSBFunction).  Calls that need the
-instance-clustering branch (`instance_eval=True`), active dropout or other feature sizes are composed from torch ops on
-the same device; CLAM_MB and the ungated Attn_Net are kept constructible for checkpoint
-compatibility and are not accelerated (out of scope).
+csrc/hb_clam.cu, and its training step (autograd enabled, HIPT sizes, any dropout probability: the reference's final
+model trains at 0.85) through the same forward plus the fused recomputing backward (clam_engine.ClamSBFunction) with the
+dropout masks regenerated inside both kernels.  The instance-clustering branch (`instance_eval=True`) runs on top of the
+fused outputs: it needs the scores and 2 k_sample rows of the instance features.  Other feature sizes in training,
+gradients w.r.t. the bag, CLAM_MB and the ungated Attn_Net are composed from torch ops on the same device (kept
+constructible for checkpoint compatibility, out of scope: SURVEY.md §2.1 #5).
 """
 import numpy as np
 import torch
@@ -132,24 +133,57 @@ class CLAM_SB(nn.Module):
     def forward(self, h, label=None, instance_eval=False, return_features=False, attention_only=False):
         if not h.is_cuda:
             raise RuntimeError("CLAM_SB runs only on CUDA (B200): there is no CPU path; move the bag to the GPU")
-        fused_ok = (self.gate and not instance_eval and not self._needs_autograd(h)
-                    and not (self.training and self._has_active_dropout()))
-        if fused_ok:
+        drop = clam_engine.dropout_p(self) if self.training else 0.0      # nn.Dropout is the identity in eval()
+        grad = self._needs_autograd(h)
+        if not self.gate or h.requires_grad or (grad or drop > 0.0) and not clam_engine.supports_fused_backward(self):
+            # ungated attention, gradients w.r.t. the bag, or training of a non-HIPT head: plain torch composition
+            return self._forward_autograd(h, label, instance_eval, return_features, attention_only)
+        seed = clam_engine.draw_seed() if drop > 0.0 else 0
+        if grad or drop > 0.0:
+            # training step (utils/core_utils.py:409-423 / :300-371): forward and backward both run the fused ragged-bag
+            # kernels, dropout masks (model_clam.py:84-85, :50-52) are regenerated from `seed` inside them
+            logits, Y_prob, Y_hat, A_raw, M = clam_engine.forward_single_autograd(self, h, drop, seed)
+        else:
             res = clam_engine.forward_single(self, h, attention_only=attention_only)
             if attention_only:
                 return res
             logits, Y_prob, Y_hat, A_raw, M = res
-            results_dict = {'features': M} if return_features else {}
-            return logits, Y_prob, Y_hat, A_raw, results_dict
-        fused_train_ok = (self.gate and not instance_eval and not attention_only and not h.requires_grad
-                          and not (self.training and self._has_active_dropout())
-                          and clam_engine.supports_fused_backward(self))
-        if fused_train_ok:
-            # training step (utils/core_utils.py:409-423): forward and backward both run the fused ragged-bag kernels
-            logits, Y_prob, Y_hat, A_raw, M = clam_engine.forward_single_autograd(self, h)
-            results_dict = {'features': M} if return_features else {}
-            return logits, Y_prob, Y_hat, A_raw, results_dict
-        return self._forward_autograd(h, label, instance_eval, return_features, attention_only)
+        if attention_only:
+            return A_raw
+        results_dict = {}
+        if instance_eval:
+            results_dict = self._instance_eval_fused(h, A_raw, label, drop, seed)
+        if return_features:
+            results_dict.update({'features': M})
+        return logits, Y_prob, Y_hat, A_raw, results_dict
+
+    def _instance_eval_fused(self, h, A_raw, label, drop, seed):
+        """The instance-clustering branch (model_clam.py:156-178) on top of the fused forward: it needs the softmaxed scores
+        and 2 * k_sample ROWS of the [N, L1] instance features, which clam_engine.h1_rows recomputes for just those rows."""
+        A = F.softmax(A_raw, dim=1)
+        k = self.k_sample
+        total_inst_loss = 0.0
+        all_preds, all_targets = [], []
+        inst_labels = F.one_hot(label, num_classes=self.n_classes).squeeze()
+        for i, classifier in enumerate(self.instance_classifiers):
+            if inst_labels[i].item() == 1:                                    # in-the-class: top-k positive, bottom-k negative
+                top_p_ids = torch.topk(A, k)[1][-1]
+                top_n_ids = torch.topk(-A, k, dim=1)[1][-1]
+                rows = clam_engine.h1_rows(self, h, torch.cat([top_p_ids, top_n_ids]), drop, seed)
+                targets = torch.cat([self.create_positive_targets(k, h.device), self.create_negative_targets(k, h.device)])
+            elif self.subtyping:                                              # out-of-the-class: top-k are negatives
+                rows = clam_engine.h1_rows(self, h, torch.topk(A, k)[1][-1], drop, seed)
+                targets = self.create_negative_targets(k, h.device)
+            else:
+                continue
+            logits = classifier(rows)
+            preds = torch.topk(logits, 1, dim=1)[1].squeeze(1)
+            all_preds.extend(preds.cpu().numpy())
+            all_targets.extend(targets.cpu().numpy())
+            total_inst_loss += self.instance_loss_fn(logits, targets)
+        if self.subtyping:
+            total_inst_loss /= len(self.instance_classifiers)
+        return {'instance_loss': total_inst_loss, 'inst_labels': np.array(all_targets), 'inst_preds': np.array(all_preds)}
 
     def _has_active_dropout(self):
         return any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules())

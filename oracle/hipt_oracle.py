@@ -223,3 +223,54 @@ def sd_digest(sd):
         if v.numel() <= 4096:
             h.update(sd[k].detach().contiguous().numpy().tobytes())
     return {"sum": tot, "sha1_small": h.hexdigest(), "n": len(sd)}
+
+
+# ---------------------------------------------------------------------------------------------------- CLAM_SB training mode
+def clam_sb_forward_train(sd, h, masks=None, label=None, instance_eval=False, k_sample=8, subtyping=False,
+                          n_classes=2, inst_loss=None):
+    """CLAM_SB.forward in TRAINING mode with explicit dropout masks and the instance-clustering branch, differentiable
+    w.r.t. the tensors of `sd` (models/model_clam.py:147-191):
+      masks = (m1 [N,L1], ma [N,D], mb [N,D]) holding 0 or 1/(1-p) — what nn.Dropout multiplies by after the ReLU (:84-85)
+              and after Tanh / Sigmoid inside Attn_Net_Gated (:50-52, applied BEFORE a * b at :62); None = no dropout
+      instance_eval: inst_eval :116-132 for the label's class (top-k / bottom-k of the SOFTMAXED scores, index_select on the
+              post-dropout h), inst_eval_out :135-145 for the other classes when subtyping, loss averaged over the
+              instance classifiers only when subtyping (:170-171)
+    Returns (logits, Y_prob, Y_hat, A_raw, results_dict)."""
+    g = _gate_prefix(sd)
+    h1 = F.relu(F.linear(h, sd["attention_net.0.weight"], sd["attention_net.0.bias"]))
+    if masks is not None:
+        h1 = h1 * masks[0]
+    a = torch.tanh(F.linear(h1, sd[g + "attention_a.0.weight"], sd[g + "attention_a.0.bias"]))
+    b = torch.sigmoid(F.linear(h1, sd[g + "attention_b.0.weight"], sd[g + "attention_b.0.bias"]))
+    if masks is not None:
+        a, b = a * masks[1], b * masks[2]
+    A = F.linear(a * b, sd[g + "attention_c.weight"], sd[g + "attention_c.bias"]).transpose(1, 0)
+    A_raw = A
+    A = F.softmax(A, dim=1)
+    res = {}
+    if instance_eval:
+        loss_fn = inst_loss or torch.nn.CrossEntropyLoss()
+        total, preds_all, targets_all = 0.0, [], []
+        onehot = F.one_hot(label, num_classes=n_classes).squeeze()
+        for i in range(n_classes):
+            W, bi = sd[f"instance_classifiers.{i}.weight"], sd[f"instance_classifiers.{i}.bias"]
+            if onehot[i].item() == 1:
+                top_p = torch.index_select(h1, 0, torch.topk(A, k_sample)[1][-1])
+                top_n = torch.index_select(h1, 0, torch.topk(-A, k_sample, dim=1)[1][-1])
+                targets = torch.cat([torch.ones(k_sample, dtype=torch.long), torch.zeros(k_sample, dtype=torch.long)])
+                lg = F.linear(torch.cat([top_p, top_n]), W, bi)
+            elif subtyping:
+                top_p = torch.index_select(h1, 0, torch.topk(A, k_sample)[1][-1])
+                targets = torch.zeros(k_sample, dtype=torch.long)
+                lg = F.linear(top_p, W, bi)
+            else:
+                continue
+            total = total + loss_fn(lg, targets)
+            preds_all.append(torch.topk(lg, 1, dim=1)[1].squeeze(1))
+            targets_all.append(targets)
+        if subtyping:
+            total = total / n_classes
+        res = {"instance_loss": total, "inst_labels": torch.cat(targets_all), "inst_preds": torch.cat(preds_all)}
+    M = A @ h1
+    logits = F.linear(M, sd["classifiers.weight"], sd["classifiers.bias"])
+    return logits, F.softmax(logits, dim=1), torch.topk(logits, 1, dim=1)[1], A_raw, res

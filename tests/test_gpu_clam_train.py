@@ -1,0 +1,143 @@
+"""CLAM_SB at the reference's TRAINING configuration on the CUDA path: active dropout (the final model trains at 0.85,
+docs/README.md:186-193) and the instance-clustering branch (models/model_clam.py:116-178), against goldens produced by the
+reference module itself (oracle/make_golden_train.py: known dropout masks injected through forward hooks) and against the
+CPU oracle.  Tolerance: 1e-3 on scores, logits, losses and gradients (BASELINE.json north_star / SURVEY.md §8d config 4).
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hipt_oracle as O
+from hipt_abmil_atec23_b200 import _lib, clam_engine
+from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clam_train_reference.pt")
+DEV = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, map_location="cpu")
+
+
+def _model(g, dropout=0.0):
+    torch.manual_seed(g["model_seed"])
+    return CLAM_SB(size_arg=g["size_arg"], dropout=dropout, n_classes=g["n_classes"], subtyping=g["subtyping"], k_sample=8)
+
+
+def _bag(g):
+    return torch.randn(g["n"], 192, generator=torch.Generator().manual_seed(g["bag_seed"]))
+
+
+def test_instance_eval_runs_on_the_fused_forward_and_matches_the_reference(gold):
+    """a18: instance_eval=True keeps the bag on the fused kernel (launch counter moves by the forward's three kernels) and
+    reproduces the reference module's instance loss, predictions and targets."""
+    for name, g in gold["inst_eval"].items():
+        model = _model(g).to(DEV).eval()
+        bag = _bag(g).to(DEV)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            logits, y_prob, y_hat, a_raw, res = model(bag, label=torch.tensor([g["label"]], device=DEV), instance_eval=True)
+        assert _lib.launch_count() - n0 == 3, name                       # work table, scores, combine: no torch fallback
+        assert (logits.cpu() - g["logits"]).abs().max().item() < 1e-3, name
+        assert (a_raw.cpu() - g["a_raw"]).abs().max().item() < 1e-3, name
+        assert abs(float(res["instance_loss"]) - float(g["instance_loss"])) < 1e-3, name
+        assert torch.equal(torch.as_tensor(res["inst_preds"]), g["inst_preds"]), name
+        assert torch.equal(torch.as_tensor(res["inst_labels"]), g["inst_labels"]), name
+
+
+def test_training_step_with_dropout_matches_the_reference_module(gold, monkeypatch):
+    """model.train(), dropout 0 / 0.25 / 0.5 / 0.85, with and without the instance branch: forward and backward run the fused
+    kernels with masks regenerated from the seed; loss and all gradients vs the reference run with the SAME masks."""
+    for name, g in gold["train"].items():
+        model = _model(g, g["dropout"]).to(DEV).train()
+        monkeypatch.setattr(clam_engine, "draw_seed", lambda s=g["mask_seed"]: s)
+        bag = _bag(g).to(DEV)
+        lab = torch.tensor([g["label"]], device=DEV)
+        n0 = _lib.launch_count()
+        logits, _, _, a_raw, res = model(bag, label=lab, instance_eval=g["instance_eval"])
+        assert "ClamSB" in type(logits.grad_fn).__name__, name
+        loss = F.cross_entropy(logits, lab)
+        total = 0.7 * loss + 0.3 * res["instance_loss"] if g["instance_eval"] else loss
+        total.backward()
+        assert _lib.launch_count() - n0 == 5, name                       # forward (3) + backward prep + backward
+        assert (logits.detach().cpu() - g["logits"]).abs().max().item() < 1e-3, name
+        assert (a_raw.detach().cpu() - g["a_raw"]).abs().max().item() < 1e-3, name
+        assert abs(total.item() - g["loss"].item()) < 1e-3, name
+        for k, p in model.named_parameters():
+            ref = g["grads"][k]
+            if ref is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, (name, k)
+                continue
+            err = (p.grad.cpu() - ref).abs().max().item()
+            assert err < 1e-3 * max(1e-2, ref.abs().max().item()), (name, k, err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("p", [0.25, 0.85, 1.0])
+def test_dropout_forward_matches_the_oracle_with_the_kernel_masks(p):
+    """Forward only, larger bag (several 64-instance chunks): A_raw / logits of the dropout forward vs the oracle fed with
+    hb_clam_dropout_masks; a different seed must give a different result; eval() ignores dropout."""
+    torch.manual_seed(5)
+    model = CLAM_SB(size_arg="hipt_smaller", dropout=p, n_classes=2).to(DEV).train()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    bag = torch.randn(1000, 192, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        lg, yp, yh, ar, m = clam_engine.forward_single_autograd(model, bag.to(DEV), p, 4242)
+        masks = clam_engine.dropout_masks(1000, 16, 8, p, 4242)
+        rl, _, _, ra, _ = O.clam_sb_forward_train(sd, bag, masks)
+        assert (ar.cpu() - ra).abs().max().item() < 1e-3 and (lg.cpu() - rl).abs().max().item() < 1e-3
+        if p < 1.0:
+            lg2, _, _, ar2, _ = clam_engine.forward_single_autograd(model, bag.to(DEV), p, 4243)
+            assert (ar2 - ar).abs().max().item() > 1e-3
+        ev = model.eval()(bag.to(DEV))
+        r0 = O.clam_sb_forward(sd, bag)
+        assert (ev[3].cpu() - r0[3]).abs().max().item() < 1e-3
+
+
+def test_lean_train_step_with_dropout_and_owned_gradients():
+    """TrainStep at dropout 0.85: gradients equal the oracle's for the step's own mask seed; the step survives
+    optimizer.zero_grad(set_to_none=True) (the gradient buffers are owned by TrainStep)."""
+    torch.manual_seed(2)
+    model = CLAM_SB(size_arg="hipt_smaller", dropout=0.85, n_classes=2).to(DEV).train()
+    opt = clam_engine.FusedAdam(clam_engine._param_list(model), lr=1e-3, weight_decay=0.5)
+    ts = clam_engine.TrainStep(model, opt, 200, seed=11)
+    bag = torch.randn(75, 192, generator=torch.Generator().manual_seed(8))
+    lab = torch.tensor([1], device=DEV)
+    for step in range(3):
+        sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        loss = ts.step(bag.to(DEV), lab)
+        masks = clam_engine.dropout_masks(75, 16, 8, 0.85, ts.last_seed)
+        rl = O.clam_sb_forward_train(sd, bag, masks)[0]
+        rloss = F.cross_entropy(rl, torch.tensor([1]))
+        rloss.backward()
+        assert abs(loss.item() - rloss.item()) < 1e-3
+        for k, g in zip(("attention_net.0.weight", "attention_net.0.bias"), ts.grads[:2]):
+            assert (g.cpu() - sd[k].grad).abs().max().item() < 1e-3 * max(1e-2, sd[k].grad.abs().max().item()), k
+        opt.zero_grad(set_to_none=True)                                 # the next step must re-attach its own buffers
+    assert all(p.grad is None for p in clam_engine._param_list(model))
+
+
+def test_fused_adam_keeps_one_step_count_per_parameter():
+    """torch.optim.Adam semantics when a parameter has grad None on some steps (instance_classifiers[label] in
+    train_loop_clam): its bias correction uses ITS step count."""
+    torch.manual_seed(0)
+    shapes = [(16, 192), (2, 16), (2,)]
+    p_ref = [torch.randn(s).requires_grad_(True) for s in shapes]
+    p_our = [p.detach().clone().to(DEV).requires_grad_(True) for p in p_ref]
+    ref = torch.optim.Adam(p_ref, lr=2e-3, weight_decay=1e-2)
+    our = clam_engine.FusedAdam(p_our, lr=2e-3, weight_decay=1e-2)
+    for step in range(6):
+        for i, (a, b) in enumerate(zip(p_ref, p_our)):
+            if i > 0 and step % 2 == i - 1:                             # tensors 1 and 2 skip alternate steps
+                a.grad, b.grad = None, None
+                continue
+            g = torch.randn(a.shape, generator=torch.Generator().manual_seed(100 * step + i))
+            a.grad, b.grad = g.clone(), g.to(DEV)
+        ref.step()
+        our.step()
+    for a, b in zip(p_ref, p_our):
+        assert (a.detach() - b.detach().cpu()).abs().max().item() < 1e-6
+    assert [int(our.state[p]["step"]) for p in p_our] == [6, 3, 3]

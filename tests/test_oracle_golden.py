@@ -113,3 +113,51 @@ def test_mil_fc(gold):
                  (yps2, g["y_probs"])):
         assert torch.allclose(a, b, atol=1e-5)
     assert torch.equal(yh, g["y_hat"]) and torch.equal(yh2, g["y_hat"])
+
+
+# ------------------------------------------------------------------------------------------ CLAM_SB training-mode goldens
+def _train_gold():
+    return torch.load(os.path.join(GOLD_DIR, "clam_train_reference.pt"), map_location="cpu")
+
+
+def test_clam_instance_eval_oracle_matches_reference():
+    from tests.common import seeded_clam
+    for name, g in _train_gold()["inst_eval"].items():
+        torch.manual_seed(g["model_seed"])
+        from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+        sd = CLAM_SB(size_arg=g["size_arg"], dropout=0.0, n_classes=g["n_classes"], subtyping=g["subtyping"]).state_dict()
+        bag = torch.randn(g["n"], 192, generator=torch.Generator().manual_seed(g["bag_seed"]))
+        with torch.no_grad():
+            logits, _, _, a_raw, res = O.clam_sb_forward_train(sd, bag, None, torch.tensor([g["label"]]), True, 8, g["subtyping"],
+                                                               g["n_classes"])
+        assert torch.allclose(logits, g["logits"], atol=1e-6) and torch.allclose(a_raw, g["a_raw"], atol=1e-6), name
+        assert torch.allclose(torch.as_tensor(res["instance_loss"]), g["instance_loss"], atol=1e-6), name
+        assert torch.equal(res["inst_preds"], g["inst_preds"]) and torch.equal(res["inst_labels"], g["inst_labels"]), name
+
+
+def test_clam_training_oracle_matches_reference_gradients_with_known_dropout_masks():
+    """Oracle (mask application points restated from model_clam.py:50-52, 84-85) vs the reference module run with the same
+    masks injected through forward hooks: outputs, loss and every gradient."""
+    import torch.nn.functional as F
+    from hipt_abmil_atec23_b200 import clam_engine
+    from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+    for name, g in _train_gold()["train"].items():
+        torch.manual_seed(g["model_seed"])
+        mod = CLAM_SB(size_arg=g["size_arg"], dropout=g["dropout"], n_classes=g["n_classes"], subtyping=g["subtyping"])
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+        bag = torch.randn(g["n"], 192, generator=torch.Generator().manual_seed(g["bag_seed"]))
+        L1, D = sd["attention_net.0.weight"].shape[0], sd["classifiers.weight"].shape[1] // 2
+        masks = clam_engine.dropout_masks(g["n"], L1, D, g["dropout"], g["mask_seed"]) if g["dropout"] > 0 else None
+        lab = torch.tensor([g["label"]])
+        logits, _, _, a_raw, res = O.clam_sb_forward_train(sd, bag, masks, lab, g["instance_eval"], 8, g["subtyping"], g["n_classes"])
+        loss = F.cross_entropy(logits, lab)
+        total = 0.7 * loss + 0.3 * res["instance_loss"] if g["instance_eval"] else loss
+        total.backward()
+        assert torch.allclose(logits, g["logits"], atol=1e-5) and torch.allclose(a_raw, g["a_raw"], atol=1e-5), name
+        assert torch.allclose(total.detach(), g["loss"], atol=1e-5), name
+        for k, ref in g["grads"].items():
+            got = sd[k].grad
+            if ref is None:
+                assert got is None or float(got.abs().max()) == 0.0, (name, k)
+            else:
+                assert torch.allclose(got, ref, atol=1e-5, rtol=1e-4), (name, k, float((got - ref).abs().max()))
