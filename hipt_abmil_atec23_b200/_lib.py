@@ -59,6 +59,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_void_p)]),
     "hb_vit_plan_destroy": (None, [C.c_void_p]),
     "hb_vit_plan_set_depth_limit": (C.c_int, [C.c_void_p, C.c_int]),
+    "hb_vit_plan_set_cls_attention": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hb_vit_plan_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "hb_vit256_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                     C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

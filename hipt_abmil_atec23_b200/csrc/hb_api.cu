@@ -173,6 +173,7 @@ struct hb_vit_plan {
     float* stats1;     // [n_part][rows][2] partial (sum, sum of squares) of the rows before norm1
     float* stats2;     // same before norm2
     size_t hid_bytes;
+    float* cls_attn;   // optional [n_seq, heads, seq_len] fp32: softmax row of the CLS query in the last block (heatmaps)
     std::vector<const void*> w;
     std::vector<GemmArgs> g_qkv, g_proj, g_fc1, g_fc2;
 };
@@ -344,6 +345,7 @@ int hb_vit_plan_create(const hb_vit_config* cfg, const void* const* weights_host
     if (!p) return set_error("hb_vit_plan_create: out of host memory");
     p->cfg = *cfg;
     p->depth_limit = cfg->depth;
+    p->cls_attn = nullptr;
     {
         const char* e = getenv("HB_VIT_FULL_LAST_BLOCK");   // debug: compute every token in the last block too
         p->cls_only_last = !(e && e[0] == '1');
@@ -394,6 +396,13 @@ int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit) {
     return 0;
 }
 
+int hb_vit_plan_set_cls_attention(hb_vit_plan* plan, float* cls_attn) {
+    if (!plan) return set_error("null plan");
+    if (cls_attn && !plan->cls_only_last) return set_error("hb_vit_plan_set_cls_attention: the plan runs the full last block (HB_VIT_FULL_LAST_BLOCK)");
+    plan->cls_attn = cls_attn;
+    return 0;
+}
+
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes) {
     if (!plan || !ptr || !bytes) return set_error("null argument");
     const size_t rows = plan->rows;
@@ -427,7 +436,7 @@ static int run_blocks(hb_vit_plan* p, int n_seq, int seq_len, float* cls_f32, vo
         if (cls_tail && i == c.depth - 1) {
             const void* const* w = &p->w[3 + 10 * i];
             { ProfScope ps(kb + HB_PROF_ATTENTION, st);
-              if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st, 1)) return -1; }
+              if (attention_launch(p->qkv, p->att, n_seq, seq_len, c.heads, hd, scale, st, 1, p->cls_attn)) return -1; }
             // compact CLS stream xc [n_seq, D] in the head of the (now dead) qkv buffer; its residual source is the
             // strided CLS rows of xb
             void* xc = p->qkv;

@@ -127,9 +127,11 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[HD / 16][4], uin
 template <int HD>
 __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         __nv_bfloat16* __restrict__ out, int seq_len, int heads,
-                                                        float scale_log2, int cls_only) {
+                                                        float scale_log2, int cls_only, float* __restrict__ cls_probs) {
     // cls_only: only query row 0 of each sequence is computed and written to a COMPACT [n_seq, D] output — all that
     // the last transformer block needs, because forward() returns x[:, 0] (vision_transformer.py:252-253).
+    // cls_probs (cls_only mode, may be NULL): [n_seq, heads, seq_len] fp32, the softmax row of query 0 — what the heatmap
+    // code reads from get_last_selfattention as attention[:, :, 0, :] (hipt_4k.py:145-147, 155-157).
     extern __shared__ __align__(128) uint8_t smem_attn[];
     constexpr int CH = HD / 8;                              // 16 B chunks per row
     const int s_pad = (seq_len + 15) & ~15;
@@ -197,6 +199,31 @@ __global__ void __launch_bounds__(288, 2) attention_kernel(const __nv_bfloat16* 
 #pragma unroll
                 for (int d = 0; d < HD / 8; ++d)
                     *reinterpret_cast<uint32_t*>(orow + d * 8) = pack_bf16x2(o[d][0] * inv0, o[d][1] * inv0);
+            }
+            if (cls_probs != nullptr) {
+                // second pass over the keys for query 0 only: p_k = exp2(s_k * scale - m) / l with the final (m, l)
+                float* prow = cls_probs + (static_cast<size_t>(seq) * heads + h) * seq_len;
+                const float mrow = __shfl_sync(0xffffffffu, m[0], 0);
+                const int t2 = (lane & 3) * 2;
+                for (int key0 = 0; key0 < s_pad; key0 += 16) {
+                    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int kk = 0; kk < HD / 16; ++kk) {
+                        const int key = key0 + (lane & 7) + ((lane >> 4) << 3);
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4(sK + swz_off<HD>(key, kk * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+                        mma_bf16_16816(c0, qf[kk], b0, b1);
+                        mma_bf16_16816(c1, qf[kk], b2, b3);
+                    }
+                    if ((lane >> 2) == 0) {
+                        const float v[4] = {c0[0], c0[1], c1[0], c1[1]};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int key = key0 + (e >> 1) * 8 + t2 + (e & 1);
+                            if (key < seq_len) prow[key] = exp2f(v[e] * scale_log2 - mrow) * inv0;
+                        }
+                    }
+                }
             }
             continue;
         }
@@ -663,7 +690,7 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
                      cudaStream_t stream, int cls_only, float* cls_probs) {
     if (n_seq <= 0) return 0;
     if (seq_len <= 0 || heads <= 0) return set_error("hb_attention: bad shape");
-    (void)cls_probs;
+    if (cls_probs && !cls_only) return set_error("hb_attention: the CLS-row probabilities come from the CLS-only launch");
     if (seq_len == ATC_S && head_dim == 64 && !attention_force_legacy() && !cls_only)
         return attention_force_v1() ? attention_tc_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream)
                                     : attention_tc2_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream);
@@ -681,12 +708,12 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
         auto k = attention_kernel<64>;
         if (set_max_dynamic_smem(reinterpret_cast<const void*>(k), 200 * 1024)) return -1;
         k<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
-                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only);
+                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only, cls_probs);
     } else if (head_dim == 32) {
         auto k = attention_kernel<32>;
         if (set_max_dynamic_smem(reinterpret_cast<const void*>(k), 200 * 1024)) return -1;
         k<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
-                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only);
+                                              static_cast<__nv_bfloat16*>(out_bf16), seq_len, heads, scale_log2, cls_only, cls_probs);
     } else {
         return set_error("hb_attention: head_dim %d not supported (64 or 32)", head_dim);
     }

@@ -1,25 +1,27 @@
 // hb_attention_tc.cu — tcgen05 / TMEM attention for the ViT-256 shape (257 tokens, head_dim 64): softmax(q k^T * scale) v of
 // Attention.forward (HIPT_4K/vision_transformer.py:119-128) without the [B, heads, 257, 257] matrix.
 //
-// One persistent CTA per SM walks (sequence, head) items.  An item is THREE query tiles — queries 0..127, 128..255 and a
-// tail tile whose only real row is query 256 — and every tile is TWO independent units, one per key half (keys 0..127,
-// keys 128..255 plus key 256).  A unit owns 128 TMEM columns and goes through
+// One persistent CTA per SM walks (sequence, head) items.  An item is two 128-query tiles plus query 256; every tile is TWO
+// independent units, one per key half (keys 0..127, keys 128..255 plus key 256).  A unit owns 128 TMEM columns and goes through
 //     S = Q K_half^T            tcgen05.mma, A and B from shared memory, 128 x 128 fp32 in the unit's 128 columns
 //     softmax warpgroup         thread = query row: tcgen05.ld all 128 scores, row max, exp2, row sum; P is rounded to bf16
 //                               and written BACK to tensor memory (tcgen05.st) over the unit's columns 0..63
 //     O = P V_half              tcgen05.mma with the A operand read from TMEM, V read MN-major in place, into columns 64..127
-// with its own (max, sum); the two halves are merged in the tile epilogue (out = (O_a w_a + O_b w_b), w from the two maxima
-// and sums), so no unit ever waits for another one's statistics and nothing is rescaled in flight.  Key 256 does not fit a
-// 128-key half: its score is a 64-term dot product in the row's thread, it joins half B's statistics, and p_256 v_256 is
-// added in the epilogue.  Four units are resident (4 x 128 = all 512 TMEM columns): two softmax warpgroups each alternate
-// between their two unit buffers, so the S of a warpgroup's NEXT tile is computed while it is still busy with the current
-// one and the MUFU pipe always has a second warp to run.
-//   warp 0        TMA producer: K / V [272 x 64] per item (two stages) and one Q tile per warpgroup slot; the tail tile
-//                 loads the 16-row box holding query 256 at row 32 * ((item / 2) % 4) of the slot, so that successive tail
-//                 tiles of a warpgroup land on different warps (= different scheduler partitions)
-//   warps 1, 2    MMA issuers of warpgroups 0 and 1 (whole warp walks the protocol, one elected lane issues)
-//   warps 4-7     softmax warpgroup 0 (tiles 0, 2, 4, ... of the CTA's tile sequence), warps 8-11 warpgroup 1
-// Softmax statistics stay fp32; P is rounded to bf16 relative to its half's maximum.
+// with its own (max, sum).  The two halves are merged by a separate EPILOGUE warpgroup (out = O_a w_a + O_b w_b, weights from
+// the two maxima and sums), so a softmax warpgroup goes from one unit straight to the next — it never waits for a P V product,
+// nothing is rescaled in flight — and the S of its next tile is issued as soon as the epilogue has drained the unit.
+// Key 256 does not fit a 128-key half: its score against every query is a 64-term dot product on the CUDA cores, it joins
+// half B's statistics, and p_256 v_256 is added in the epilogue.  Query 256 has no tile either: one row on the CUDA cores
+// (two keys per thread, warp-shuffle softmax, a 4-way split P V).  Both run in the EPILOGUE warpgroup at the START of an
+// item, while the softmax warpgroups are busy with its first units: a few hundred issue slots per scheduler partition that
+// are off the softmax critical path, and K / V are released as soon as the item's last P V product has completed.
+//   warp 0        TMA producer: K / V [272 x 64] per item (two stages), one Q tile per softmax warpgroup, the 16-row box that
+//                 starts at query 256
+//   warps 1, 2    MMA issuers of softmax warpgroups 0 and 1 (whole warp walks the protocol, one elected lane issues)
+//   warps 4-7     softmax warpgroup 0 (queries 0..127 of every item), warps 8-11 warpgroup 1 (queries 128..255)
+//   warps 12-15   epilogue warpgroup: drains O_a / O_b of both tiles, merges, stores rows straight to global memory; query 256
+// Four units are resident (4 x 128 = all 512 TMEM columns).  Softmax statistics stay fp32; P is rounded to bf16 relative to
+// its half's maximum.
 #include "hb_ptx.cuh"
 #include "hb_internal.h"
 
@@ -28,18 +30,21 @@ namespace hb {
 #ifdef HB_EXP_TRACE
 // timing experiment only (tools/build_exp.sh NAME -DHB_EXP_TRACE, tools/exp_at2_trace.py): clock64 stamps of CTA 0
 __device__ long long g_at2_trace[4 * 64 * 16];
-#define AT2_TRACE(role, it, k) do { if (blockIdx.x == 0 && (it) < 64 && lane == 0 && (warp < 4 || (warp & 3) == 0)) g_at2_trace[((role) * 64 + (it)) * 16 + (k)] = clock64(); } while (0)
-#define AT2_TRACE_UNIT(k) do { if (blockIdx.x == 0 && tr_j < 64 && (threadIdx.x & 127) == 0) g_at2_trace[(tr_w * 64 + tr_j) * 16 + (k)] = clock64(); } while (0)
+#define AT2_TRACE(role, it, k) do { if (blockIdx.x == 0 && (it) < 64 && (threadIdx.x & 127) == 0) g_at2_trace[((role) * 64 + (it)) * 16 + (k)] = clock64(); } while (0)
 #else
 #define AT2_TRACE(role, it, k) do { } while (0)
-#define AT2_TRACE_UNIT(k) do { } while (0)
 #endif
 
-constexpr int AT2_THREADS = 384;
+constexpr int AT2_THREADS = 512;
 constexpr int AT2_S = 257;
 constexpr int AT2_KV_BYTES = 272 * 128;                 // [272 keys][64 bf16], 128-byte swizzled rows
 constexpr int AT2_TILE_BYTES = 128 * 128;               // one 128-row tile of 128-byte rows
-constexpr int AT2_SMEM = 4 * AT2_KV_BYTES + 4 * AT2_TILE_BYTES + 512 + 1024;
+constexpr int AT2_Q256_BYTES = 16 * 128;                // the 16-row box that starts at query 256 (row 0 is unswizzled)
+constexpr int AT2_STATS_FLOATS = 128 * 8;               // per warpgroup: [128 rows][m_a, l_a, m_b, l_b, p_256, pad]
+constexpr int AT2_ROW_FLOATS = 272 + 4 * 64 + 16 + 64;   // query 256: p[272], partial O [4][64], reduction scratch;
+                                                                   // copies of v_256 (2 stages x 64 bf16)
+constexpr int AT2_SMEM = 4 * AT2_KV_BYTES + 2 * AT2_TILE_BYTES + 2 * AT2_Q256_BYTES + 2 * AT2_STATS_FLOATS * 4 +
+                         AT2_ROW_FLOATS * 4 + 512 + 1024;
 constexpr int AT2_TMEM_COLS = 512;
 
 __device__ __forceinline__ void at2_ld32(uint32_t taddr, uint32_t* v) {
@@ -62,15 +67,48 @@ __device__ __forceinline__ float at2_ex2(float x) {
 __device__ __forceinline__ float at2_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float at2_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// ---- mma.sync helpers for the two odd ones out (key 256 and query 256), which have no 128-wide tile of their own
+__device__ __forceinline__ uint32_t at2_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+__device__ __forceinline__ void at2_ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void at2_ldsm4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void at2_mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// q_r . k_256 for the 32 rows [row0, row0 + 32) of a swizzled Q tile, one warp: two m16 tiles x four k16 steps against a
+// B fragment whose only non-zero column is k_256 (an unswizzled 128-byte row).  Lane l returns the score of row row0 + l.
+__device__ __forceinline__ float at2_warp_dot_k256(uint32_t q_tile, int row0, const uint32_t* k256_words, int lane) {
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t b0 = lane < 4 ? k256_words[kk * 8 + lane] : 0u;          // B[k = 2 (l % 4) .., n = l / 4]: column 0 only
+        const uint32_t b1 = lane < 4 ? k256_words[kk * 8 + 4 + lane] : 0u;
+        uint32_t a[4], a2[4];
+        at2_ldsm4(q_tile + at2_swz(row0 + (lane & 15), kk * 2 + (lane >> 4)), a[0], a[1], a[2], a[3]);
+        at2_ldsm4(q_tile + at2_swz(row0 + 16 + (lane & 15), kk * 2 + (lane >> 4)), a2[0], a2[1], a2[2], a2[3]);
+        at2_mma16816(c0, a, b0, b1);
+        at2_mma16816(c1, a2, b0, b1);
+    }
+    // column 0 of the C fragments lives in lanes 4 i: rows i (c[0]) and i + 8 (c[2]) of each m16 tile
+    const int src = (lane & 7) * 4;
+    const float v00 = __shfl_sync(0xffffffffu, c0[0], src), v01 = __shfl_sync(0xffffffffu, c0[2], src);
+    const float v10 = __shfl_sync(0xffffffffu, c1[0], src), v11 = __shfl_sync(0xffffffffu, c1[2], src);
+    return (lane & 16) ? ((lane & 8) ? v11 : v10) : ((lane & 8) ? v01 : v00);
+}
+
 // One unit of a softmax thread: its row of S (128 scores in the unit's TMEM columns) -> P (bf16, back into columns 0..63).
 // `extra` is the score against key 256 (half B) or -inf (half A).  Returns the row's maximum (raw score units) and sum.
 __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, float scale_log2, float& m_out, float& l_out,
-                                                 float& p_extra, int tr_w = 0, int tr_j = 99, int tr_k = 0) {
+                                                 float& p_extra) {
     uint32_t sv[128];
 #pragma unroll
     for (int c = 0; c < 4; ++c) at2_ld32(t_unit + c * 32, sv + c * 32);
     tmem_ld_wait();
-    AT2_TRACE_UNIT(tr_k);
     float m0 = extra, m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
     m0 = fmaxf(m0, __uint_as_float(sv[0]));
 #pragma unroll
@@ -80,7 +118,6 @@ __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, f
     }
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     const float neg_m = -m * scale_log2;
-    AT2_TRACE_UNIT(tr_k + 1);
     const f32x2_t c2 = f2_pack(scale_log2, scale_log2), n2 = f2_pack(neg_m, neg_m);
     f32x2_t sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
@@ -99,7 +136,6 @@ __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, f
     }
     float s0, s1;
     f2_unpack(sum2, s0, s1);
-    AT2_TRACE_UNIT(tr_k + 2);
     p_extra = at2_ex2(fmaf(extra, scale_log2, neg_m));  // exp2(-inf) = 0 for half A
     m_out = m;
     l_out = s0 + s1 + p_extra;
@@ -108,33 +144,38 @@ __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, f
 
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map16,
-                     const __grid_constant__ CUtensorMap map_out, __nv_bfloat16* __restrict__ out, int n_items, int heads,
-                     float scale_log2) {
+                     __nv_bfloat16* __restrict__ out, int n_items, int heads, float scale_log2) {
     extern __shared__ uint8_t smem_raw_at2[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at2) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;                                   // [2 stages][34816]
     uint8_t* sV = sK + 2 * AT2_KV_BYTES;                  // [2 stages][34816]
-    uint8_t* sQ = sV + 2 * AT2_KV_BYTES;                  // [2 warpgroup slots][16384]
-    uint8_t* sO = sQ + 2 * AT2_TILE_BYTES;                // [2 warpgroups][16384]  output staging for the TMA store
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * AT2_TILE_BYTES);
-    uint64_t* kv_full = bars;            // [2 stages]   TMA bytes of K and V
-    uint64_t* kv_empty = bars + 2;       // [2 stages]   3 tiles x (1 MMA commit + 128 softmax threads)
-    uint64_t* q_full = bars + 4;         // [2 slots]
-    uint64_t* q_empty = bars + 6;        // [2 slots]    1 MMA commit (both S MMAs done) + 128 softmax threads (key-256 dot)
+    uint8_t* sQ = sV + 2 * AT2_KV_BYTES;                  // [2 softmax warpgroups][16384]
+    uint8_t* sQ256 = sQ + 2 * AT2_TILE_BYTES;             // [2 stages][2048]
+    float* sStats = reinterpret_cast<float*>(sQ256 + 2 * AT2_Q256_BYTES);       // [2 warpgroups][128][8]
+    float* sRow = sStats + 2 * AT2_STATS_FLOATS;          // query 256 scratch
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + AT2_ROW_FLOATS);
+    uint64_t* kv_full = bars;            // [2 stages]   TMA bytes of K, V and the query-256 box
+    uint64_t* kv_empty = bars + 2;       // [2 stages]   2 MMA commits (the item's last P V) + 256 softmax threads (key 256) + 128 epilogue threads (query 256)
+    uint64_t* q_full = bars + 4;         // [2 warpgroups]
+    uint64_t* q_empty = bars + 6;        // [2]          1 MMA commit (both S MMAs done) + 128 softmax threads (key-256 dot)
     uint64_t* s_full = bars + 8;         // [4 units]    S of the unit is in TMEM
     uint64_t* p_full = bars + 12;        // [4 units]    128 softmax threads: P is in TMEM
     uint64_t* o_full = bars + 16;        // [4 units]    O of the unit is in TMEM
-    uint64_t* u_free = bars + 20;        // [4 units]    128 softmax threads: O has been read, the unit's columns are free
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* u_free = bars + 20;        // [4 units]    128 epilogue threads: O has been read, the unit's columns are free
+    uint64_t* st_full = bars + 24;       // [2 warpgroups]  128 softmax threads: the tile's row statistics are in shared memory
+    uint64_t* st_empty = bars + 26;      // [2]          128 epilogue threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+    uint4* sV256 = reinterpret_cast<uint4*>(sRow + 272 + 4 * 64 + 16);   // [2 stages][8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = heads * 64;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); tma_prefetch_desc(&map_out); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 3 * 129);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2 + 256 + 128);
             mbar_init(&q_full[i], 1);  mbar_init(&q_empty[i], 129);
+            mbar_init(&st_full[i], 128); mbar_init(&st_empty[i], 128);
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); mbar_init(&u_free[i], 128);
@@ -149,64 +190,55 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
 
     int my_items = 0;
     if (static_cast<int>(blockIdx.x) < n_items) my_items = (n_items - 1 - blockIdx.x) / gridDim.x + 1;
-    const int n_tiles = 3 * my_items;                    // tile n = 3 * it + t is handled by warpgroup n & 1
 
-    // register budget: the producer / MMA warpgroup (warps 0-3) gives its registers to the two softmax warpgroups, whose
-    // threads hold a full 128-score row (128 x 56 + 256 x 224 = 64,512 of the SM's 65,536 registers); the setmaxnreg sits
-    // inside each role's branch so that the compiler sees the budget of that role only
+    // register budget (64 K registers per SM): 128 x 48 (producer / MMA warpgroup) + 256 x 168 (softmax: a full 128-score
+    // row per thread) + 128 x 120 (epilogue: O_a whole + O_b by halves) = 64,512.  setmaxnreg sits inside each role's
+    // branch so that the compiler sees that role's budget only.
     if (warp == 0) {
-        setmaxnreg_dec<56>();
         // ------------------------------------------------------------------------------------------ TMA producer
+        setmaxnreg_dec<48>();
         if (lane == 0) {
-            for (int n = 0; n < n_tiles; ++n) {
-                const int it = n / 3, t = n - 3 * it;
+            for (int it = 0; it < my_items; ++it) {
                 const int item = blockIdx.x + it * gridDim.x;
                 const int seq = item / heads, h = item - seq * heads;
                 const int row0 = seq * AT2_S;
-                if (t == 0) {                                           // K and V of the item, stage it & 1
-                    const int st = it & 1;
-                    mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT2_KV_BYTES);
-                    uint8_t* k = sK + st * AT2_KV_BYTES;
-                    uint8_t* v = sV + st * AT2_KV_BYTES;
-                    tma_load_2d(k, &map128, &kv_full[st], D + h * 64, row0);
-                    tma_load_2d(k + AT2_TILE_BYTES, &map128, &kv_full[st], D + h * 64, row0 + 128);
-                    tma_load_2d(k + 2 * AT2_TILE_BYTES, &map16, &kv_full[st], D + h * 64, row0 + 256);
-                    tma_load_2d(v, &map128, &kv_full[st], 2 * D + h * 64, row0);
-                    tma_load_2d(v + AT2_TILE_BYTES, &map128, &kv_full[st], 2 * D + h * 64, row0 + 128);
-                    tma_load_2d(v + 2 * AT2_TILE_BYTES, &map16, &kv_full[st], 2 * D + h * 64, row0 + 256);
-                }
-                const int w = n & 1, j = n >> 1;                        // warpgroup slot, index in its tile sequence
-                mbar_wait(&q_empty[w], (j & 1) ^ 1);
-                uint8_t* q = sQ + w * AT2_TILE_BYTES;
-                if (t < 2) {
+                const int st = it & 1;
+                mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * AT2_KV_BYTES + AT2_Q256_BYTES);
+                uint8_t* k = sK + st * AT2_KV_BYTES;
+                uint8_t* v = sV + st * AT2_KV_BYTES;
+                tma_load_2d(k, &map128, &kv_full[st], D + h * 64, row0);
+                tma_load_2d(k + AT2_TILE_BYTES, &map128, &kv_full[st], D + h * 64, row0 + 128);
+                tma_load_2d(k + 2 * AT2_TILE_BYTES, &map16, &kv_full[st], D + h * 64, row0 + 256);
+                tma_load_2d(v, &map128, &kv_full[st], 2 * D + h * 64, row0);
+                tma_load_2d(v + AT2_TILE_BYTES, &map128, &kv_full[st], 2 * D + h * 64, row0 + 128);
+                tma_load_2d(v + 2 * AT2_TILE_BYTES, &map16, &kv_full[st], 2 * D + h * 64, row0 + 256);
+                tma_load_2d(sQ256 + st * AT2_Q256_BYTES, &map16, &kv_full[st], h * 64, row0 + 256);
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    mbar_wait(&q_empty[w], (it & 1) ^ 1);
                     mbar_arrive_expect_tx(&q_full[w], AT2_TILE_BYTES);
-                    tma_load_2d(q, &map128, &q_full[w], h * 64, row0 + t * 128);
-                } else {                                                // tail tile: query 256 at row 32 * ((it / 2) % 4)
-                    mbar_arrive_expect_tx(&q_full[w], 16 * 128);
-                    tma_load_2d(q + ((it >> 1) & 3) * 32 * 128, &map16, &q_full[w], h * 64, row0 + 256);
+                    tma_load_2d(sQ + w * AT2_TILE_BYTES, &map128, &q_full[w], h * 64, row0 + w * 128);
                 }
             }
         }
     } else if (warp == 1 || warp == 2) {
         // ------------------------------------------------------------------------------------------ MMA issuers
-        setmaxnreg_dec<56>();
+        setmaxnreg_dec<48>();
         const int w = warp - 1;
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
         constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
         const uint32_t t_a = tmem_base + (2 * w) * 128, t_b = t_a + 128;       // the warpgroup's two unit buffers
         const uint64_t dq = umma_desc_k128(smem_u32(sQ + w * AT2_TILE_BYTES));
-        const int my_tiles = (n_tiles - w + 1) >> 1;
 
-        auto issue_s = [&](int j) {                     // S of both halves of the warpgroup's tile j
-            const int n = 2 * j + w, it = n / 3, st = it & 1;
+        auto issue_s = [&](int it) {                    // S of both key halves of the warpgroup's tile of item `it`
+            const int st = it & 1;
             mbar_wait(&kv_full[st], (it >> 1) & 1);
-            mbar_wait(&q_full[w], j & 1);
+            mbar_wait(&q_full[w], it & 1);
             const uint64_t dk = umma_desc_k128(smem_u32(sK + st * AT2_KV_BYTES));
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                if (j > 0) mbar_wait(&u_free[2 * w + half], (j - 1) & 1);
-                AT2_TRACE(2 + w, j, 4 + 2 * half);
+                if (it > 0) mbar_wait(&u_free[2 * w + half], (it - 1) & 1);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -216,18 +248,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                     if (half) umma_commit(&q_empty[w]);
                 }
                 __syncwarp();
-                AT2_TRACE(2 + w, j, 5 + 2 * half);
             }
         };
 
-        if (my_tiles > 0) issue_s(0);
-        for (int j = 0; j < my_tiles; ++j) {
-            const int n = 2 * j + w, it = n / 3, st = it & 1;
+        if (my_items > 0) issue_s(0);
+        for (int it = 0; it < my_items; ++it) {
+            const int st = it & 1;
             const uint32_t v_base = smem_u32(sV + st * AT2_KV_BYTES);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                mbar_wait(&p_full[2 * w + half], j & 1);
-                AT2_TRACE(2 + w, j, 2 * half);
+                mbar_wait(&p_full[2 * w + half], it & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t t_u = half ? t_b : t_a;
@@ -240,115 +270,199 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                     if (half) umma_commit(&kv_empty[st]);
                 }
                 __syncwarp();
-                AT2_TRACE(2 + w, j, 1 + 2 * half);
             }
-            if (j + 1 < my_tiles) issue_s(j + 1);
+            if (it + 1 < my_items) issue_s(it + 1);
         }
     } else if (warp == 3) {
-        setmaxnreg_dec<56>();                                 // idle warp of the first warpgroup (the instruction is warpgroup-wide)
-#ifdef HB_EXP_TRACE
-        // observer: completion times of warpgroup 0's MMAs (s_full / o_full of its two units), role 2 slots 8..11
-        if (lane == 0) {
-            const int my_tiles0 = (n_tiles + 1) >> 1;
-            for (int j = 0; j < my_tiles0; ++j) {
-                mbar_wait(&s_full[0], j & 1); AT2_TRACE(2, j, 8);
-                mbar_wait(&s_full[1], j & 1); AT2_TRACE(2, j, 9);
-                mbar_wait(&o_full[0], j & 1); AT2_TRACE(2, j, 10);
-                mbar_wait(&o_full[1], j & 1); AT2_TRACE(2, j, 11);
-            }
-        }
-#endif
-    } else {
+        setmaxnreg_dec<48>();                                 // idle warp of the first warpgroup (the instruction is warpgroup-wide)
+    } else if (warp < 12) {
         // ------------------------------------------------------------------------------------------ softmax warpgroups
-        setmaxnreg_inc<224>();
-        const int w = (warp - 4) >> 2;
+        setmaxnreg_inc<168>();
+        const int w = (warp - 4) >> 2;                        // warpgroup = query tile of every item
         const int quad = warp & 3;
         const int r = quad * 32 + lane;                       // query row inside the tile = TMEM lane
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (2 * w) * 128;
-        const int sw = r & 7;
-        const bool leader = (quad == 0 && lane == 0);
-        const uint8_t* q_row = sQ + w * AT2_TILE_BYTES + r * 128;
-        uint8_t* o_row = sO + w * AT2_TILE_BYTES + r * 128;
-        const int my_tiles = (n_tiles - w + 1) >> 1;
-        for (int j = 0; j < my_tiles; ++j) {
-            const int n = 2 * j + w, it = n / 3, t = n - 3 * it, st = it & 1;
-            const int item = blockIdx.x + it * gridDim.x;
-            const int seq = item / heads, h = item - seq * heads;
-            const bool tail = (t == 2);
-            const bool active = !tail || quad == ((it >> 1) & 3);       // warp-uniform: the tail tile has one real row
-
-            // ---- score against key 256: q_r . k_256 (row 256 of K is row 0 of its own swizzle atom: unswizzled)
-            AT2_TRACE(w, j, 0);
+        float* my_stats = sStats + w * AT2_STATS_FLOATS + r * 8;
+        for (int it = 0; it < my_items; ++it) {
+            AT2_TRACE(w, it, 0);
+            // ---- score of every row against key 256 (row 256 of K is row 0 of its own swizzle atom: unswizzled)
+            const int st = it & 1;
             mbar_wait(&kv_full[st], (it >> 1) & 1);
-            mbar_wait(&q_full[w], j & 1);
-            AT2_TRACE(w, j, 1);
-            float s256 = 0.f;
-            if (active) {
-                const uint4* k256 = reinterpret_cast<const uint4*>(sK + st * AT2_KV_BYTES + 2 * AT2_TILE_BYTES);
-                f32x2_t acc = f2_pack(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 qv = *reinterpret_cast<const uint4*>(q_row + ((c ^ sw) << 4));
-                    const uint4 kv = k256[c];
-                    acc = f2_fma(f2_pack(at2_lo(qv.x), at2_hi(qv.x)), f2_pack(at2_lo(kv.x), at2_hi(kv.x)), acc);
-                    acc = f2_fma(f2_pack(at2_lo(qv.y), at2_hi(qv.y)), f2_pack(at2_lo(kv.y), at2_hi(kv.y)), acc);
-                    acc = f2_fma(f2_pack(at2_lo(qv.z), at2_hi(qv.z)), f2_pack(at2_lo(kv.z), at2_hi(kv.z)), acc);
-                    acc = f2_fma(f2_pack(at2_lo(qv.w), at2_hi(qv.w)), f2_pack(at2_lo(kv.w), at2_hi(kv.w)), acc);
-                }
-                float a0, a1;
-                f2_unpack(acc, a0, a1);
-                s256 = a0 + a1;
-            }
+            mbar_wait(&q_full[w], it & 1);
+            const float s256 = at2_warp_dot_k256(smem_u32(sQ + w * AT2_TILE_BYTES), quad * 32,
+                                                 reinterpret_cast<const uint32_t*>(sK + st * AT2_KV_BYTES + 2 * AT2_TILE_BYTES), lane);
             mbar_arrive(&q_empty[w]);
-
+            mbar_arrive(&kv_empty[st]);
+            AT2_TRACE(w, it, 1);
             // ---- the two units: S -> P, each with its own statistics
-            float m_a = 0.f, l_a = 1.f, m_b = 0.f, l_b = 1.f, p256 = 0.f, unused;
-            mbar_wait(&s_full[2 * w], j & 1);
-            AT2_TRACE(w, j, 2);
+            float m_a, l_a, m_b, l_b, p256, unused;
+            mbar_wait(&s_full[2 * w], it & 1);
+            AT2_TRACE(w, it, 2);
             tc_fence_after();
-#ifdef HB_EXP_TRACE
-            if (active) at2_softmax_unit(t_row, -INFINITY, scale_log2, m_a, l_a, unused, w, j, 11);
-#else
-            if (active) at2_softmax_unit(t_row, -INFINITY, scale_log2, m_a, l_a, unused);
-#endif
+            at2_softmax_unit(t_row, -INFINITY, scale_log2, m_a, l_a, unused);
             tc_fence_before();
             mbar_arrive(&p_full[2 * w]);
-            AT2_TRACE(w, j, 3);
-            mbar_wait(&s_full[2 * w + 1], j & 1);
-            AT2_TRACE(w, j, 4);
+            AT2_TRACE(w, it, 3);
+            mbar_wait(&s_full[2 * w + 1], it & 1);
+            AT2_TRACE(w, it, 4);
             tc_fence_after();
-            if (active) at2_softmax_unit(t_row + 128, s256, scale_log2, m_b, l_b, p256);
+            at2_softmax_unit(t_row + 128, s256, scale_log2, m_b, l_b, p256);
             tc_fence_before();
             mbar_arrive(&p_full[2 * w + 1]);
-            AT2_TRACE(w, j, 5);
+            AT2_TRACE(w, it, 5);
 
-            // ---- merge weights of the two halves
-            const float m = fmaxf(m_a, m_b);
-            const float e_a = at2_ex2((m_a - m) * scale_log2), e_b = at2_ex2((m_b - m) * scale_log2);
-            const float inv = 1.0f / fmaf(l_a, e_a, l_b * e_b);
-            const float w_a = e_a * inv, w_b = e_b * inv, w_256 = p256 * w_b;
-
-            // ---- epilogue: O_a w_a + O_b w_b + p_256 w_b v_256 (O_b in two halves of 32 columns to bound the registers)
-            uint32_t oa[64];
-            uint4 res[8];
-            mbar_wait(&o_full[2 * w], j & 1);
-            AT2_TRACE(w, j, 6);
-            tc_fence_after();
-            if (active) { at2_ld32(t_row + 64, oa); at2_ld32(t_row + 96, oa + 32); tmem_ld_wait(); }
-            tc_fence_before();
-            mbar_arrive(&u_free[2 * w]);
-            AT2_TRACE(w, j, 7);
-            mbar_wait(&o_full[2 * w + 1], j & 1);
-            AT2_TRACE(w, j, 8);
-            tc_fence_after();
-            if (active) {
-                const uint4* v256 = reinterpret_cast<const uint4*>(sV + st * AT2_KV_BYTES + 2 * AT2_TILE_BYTES);
+            // ---- hand the row statistics to the epilogue warpgroup
+            mbar_wait(&st_empty[w], (it & 1) ^ 1);
+            *reinterpret_cast<float4*>(my_stats) = make_float4(m_a, l_a, m_b, l_b);
+            my_stats[4] = p256;
+            mbar_arrive(&st_full[w]);
+            AT2_TRACE(w, it, 6);
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ epilogue warpgroup
+        setmaxnreg_dec<120>();                                // the kernel launches with 128 registers per thread
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                       // row of the tile this thread finishes; thread id for query 256
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        float* sPart = sRow + 272;                            // [4][64]
+        float* sRed = sPart + 4 * 64;                         // [8]
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int seq = item / heads, h = item - seq * heads;
+            const int st = it & 1;
+            AT2_TRACE(3, it, 0);
+            mbar_wait(&kv_full[st], (it >> 1) & 1);           // acquire the TMA writes of K, V and the query-256 box
+            AT2_TRACE(3, it, 1);
+            const uint8_t* kbase = sK + st * AT2_KV_BYTES;
+            const uint8_t* vbase = sV + st * AT2_KV_BYTES;
+            // ---- query 256 on mma.sync, spread over the four warps: warp `quad` takes keys [64 quad, 64 quad + 64), warp 3
+            //      also key 256.  Only row 0 of the m16 fragments is real (lanes 0-3); v_256 is copied aside for the merges.
+            {
+                if (r < 8) sV256[st * 8 + r] = reinterpret_cast<const uint4*>(vbase + 2 * AT2_TILE_BYTES)[r];   // two copies: a slow
+                                                              // warp may still be merging the previous item
+                const uint32_t* q256 = reinterpret_cast<const uint32_t*>(sQ256 + st * AT2_Q256_BYTES);
+                const uint32_t k_addr = smem_u32(kbase), v_addr = smem_u32(vbase);
+                const int n_groups = (quad == 3) ? 5 : 4;     // 16-key groups; the fifth holds key 256 (+ 15 masked rows)
+                const int key0 = quad * 64;
+                const int t2 = (lane & 3) * 2;
+                uint32_t qf[4][4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    qf[kk][0] = lane < 4 ? q256[kk * 8 + lane] : 0u;
+                    qf[kk][2] = lane < 4 ? q256[kk * 8 + 4 + lane] : 0u;
+                    qf[kk][1] = 0u; qf[kk][3] = 0u;
+                }
+                float sc[10][2];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    if (g < n_groups) {
+                        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            uint32_t b0, b1, b2, b3;
+                            at2_ldsm4(k_addr + at2_swz(key0 + g * 16 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+                            at2_mma16816(c0, qf[kk], b0, b1);
+                            at2_mma16816(c1, qf[kk], b2, b3);
+                        }
+                        sc[2 * g][0] = c0[0] * scale_log2; sc[2 * g][1] = c0[1] * scale_log2;
+                        sc[2 * g + 1][0] = c1[0] * scale_log2; sc[2 * g + 1][1] = c1[1] * scale_log2;
+                        if (g == 4) {                         // keys 256..271: only key 256 exists
+                            if (t2 != 0) sc[8][0] = -INFINITY;
+                            sc[8][1] = -INFINITY; sc[9][0] = -INFINITY; sc[9][1] = -INFINITY;
+                        }
+                    } else {
+                        sc[2 * g][0] = sc[2 * g][1] = sc[2 * g + 1][0] = sc[2 * g + 1][1] = -INFINITY;
+                    }
+                    mx = fmaxf(mx, fmaxf(fmaxf(sc[2 * g][0], sc[2 * g][1]), fmaxf(sc[2 * g + 1][0], sc[2 * g + 1][1])));
+                }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                if (lane == 0) sRed[quad] = mx;
+                AT2_TRACE(3, it, 2);
+                named_bar_sync(4, 128);                       // also publishes sV256
+                AT2_TRACE(3, it, 3);
+                mx = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    sc[j][0] = at2_ex2(sc[j][0] - mx); sc[j][1] = at2_ex2(sc[j][1] - mx);
+                    sum += sc[j][0] + sc[j][1];
+                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                AT2_TRACE(3, it, 4);
+                float o[8][4];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) { o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f; }
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    if (g < n_groups) {
+                        uint32_t pa[4];
+                        pa[0] = pack_bf16x2(sc[2 * g][0], sc[2 * g][1]); pa[1] = 0u;
+                        pa[2] = pack_bf16x2(sc[2 * g + 1][0], sc[2 * g + 1][1]); pa[3] = 0u;
+#pragma unroll
+                        for (int dd = 0; dd < 4; ++dd) {
+                            uint32_t b0, b1, b2, b3;
+                            at2_ldsm4_t(v_addr + at2_swz(key0 + g * 16 + (lane & 15), dd * 2 + (lane >> 4)), b0, b1, b2, b3);
+                            at2_mma16816(o[2 * dd], pa, b0, b1);
+                            at2_mma16816(o[2 * dd + 1], pa, b2, b3);
+                        }
+                    }
+                }
+                if (lane < 4) {
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) { sPart[quad * 64 + d * 8 + t2] = o[d][0]; sPart[quad * 64 + d * 8 + t2 + 1] = o[d][1]; }
+                }
+                if (lane == 0) sRed[4 + quad] = sum;
+                mbar_arrive(&kv_empty[st]);                   // this warpgroup is done with K, V and the query-256 box of the item
+                AT2_TRACE(3, it, 5);
+                named_bar_sync(4, 128);
+                AT2_TRACE(3, it, 6);
+                if (quad == 0) {
+                    const float inv = 1.0f / (sRed[4] + sRed[5] + sRed[6] + sRed[7]);
+                    const float x0 = (sPart[2 * lane] + sPart[64 + 2 * lane] + sPart[128 + 2 * lane] + sPart[192 + 2 * lane]) * inv;
+                    const float x1 = (sPart[2 * lane + 1] + sPart[64 + 2 * lane + 1] + sPart[128 + 2 * lane + 1] + sPart[192 + 2 * lane + 1]) * inv;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(seq) * AT2_S + 256) * D + h * 64);
+                    dst[lane] = pack_bf16x2(x0, x1);
+                }
+                named_bar_sync(4, 128);                       // sPart / sRed are rewritten by the next item
+                AT2_TRACE(3, it, 7);
+            }
+            const uint4* v256 = sV256 + st * 8;
+#pragma unroll 1
+            for (int w = 0; w < 2; ++w) {
+                const uint32_t t_row = t_lane + (2 * w) * 128;
+                // ---- O_a as soon as it exists (the softmax warpgroup is still busy with half B): frees the unit early
+                uint32_t oa[64];
+                mbar_wait(&o_full[2 * w], it & 1);
+                tc_fence_after();
+                at2_ld32(t_row + 64, oa); at2_ld32(t_row + 96, oa + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&u_free[2 * w]);
+                AT2_TRACE(2, it, 2 * w);
+                // ---- merge weights of the two halves from the row statistics
+                mbar_wait(&st_full[w], it & 1);
+                const float* stats = sStats + w * AT2_STATS_FLOATS + r * 8;
+                const float4 s4 = *reinterpret_cast<const float4*>(stats);
+                const float p256 = stats[4];
+                mbar_arrive(&st_empty[w]);
+                const float m = fmaxf(s4.x, s4.z);
+                const float e_a = at2_ex2((s4.x - m) * scale_log2), e_b = at2_ex2((s4.z - m) * scale_log2);
+                const float inv = 1.0f / fmaf(s4.y, e_a, s4.w * e_b);
+                const float w_a = e_a * inv, w_b = e_b * inv, w_256 = p256 * w_b;
                 const f32x2_t wa2 = f2_pack(w_a, w_a), wb2 = f2_pack(w_b, w_b), w2 = f2_pack(w_256, w_256);
+                // ---- O_b by halves: out = O_a w_a + O_b w_b + p_256 w_b v_256, rows straight to global memory
+                mbar_wait(&o_full[2 * w + 1], it & 1);
+                tc_fence_after();
+                uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seq) * AT2_S + w * 128 + r) * D + h * 64);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t ob[32];
                     at2_ld32(t_row + 128 + 64 + hf * 32, ob);
                     tmem_ld_wait();
+                    if (hf == 1) { tc_fence_before(); mbar_arrive(&u_free[2 * w + 1]); }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint4 vv = v256[hf * 4 + q];
@@ -364,35 +478,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                             f2_unpack(acc, x0, x1);
                             o4[e] = pack_bf16x2(x0, x1);
                         }
-                        res[hf * 4 + q] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                        dst[hf * 4 + q] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
                     }
                 }
+                AT2_TRACE(2, it, 2 * w + 1);
             }
-            tc_fence_before();
-            mbar_arrive(&u_free[2 * w + 1]);
-            AT2_TRACE(w, j, 9);
-            mbar_arrive(&kv_empty[st]);
 
-            if (!tail) {
-                // the TMA store of the warpgroup's previous full tile must have drained the staging buffer
-                if (leader) tma_store_wait_read<0>();
-                named_bar_sync(4 + w, 128);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(o_row + ((q ^ sw) << 4)) = res[q];
-                fence_proxy_async_smem();
-                named_bar_sync(4 + w, 128);
-                AT2_TRACE(w, j, 10);
-                if (leader) {
-                    tma_store_2d(&map_out, sO + w * AT2_TILE_BYTES, h * 64, seq * AT2_S + t * 128);
-                    tma_store_commit();
-                }
-            } else if (active && lane == 0) {
-                uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(seq) * AT2_S + 256) * D + h * 64);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) dst[q] = res[q];
-            }
         }
-        if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -400,27 +492,26 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
     if (warp == 2) tmem_dealloc(tmem_base, AT2_TMEM_COLS);
 }
 
-int attention_tc2_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int heads, float scale, cudaStream_t stream) {
-    const int D = heads * 64;
-    const uint64_t rows = static_cast<uint64_t>(n_seq) * AT2_S;
-    CUtensorMap map128, map16, map_out;
-    if (encode_tmap_2d(&map128, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 128, 64)) return -1;
-    if (encode_tmap_2d(&map16, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 16, 64)) return -1;
-    if (encode_tmap_2d(&map_out, TMAP_BF16, out_bf16, rows, D, static_cast<uint64_t>(D) * 2, 128, 64)) return -1;
-    if (set_max_dynamic_smem(reinterpret_cast<const void*>(attention_tc2_kernel), AT2_SMEM)) return -1;
-    const int n_items = n_seq * heads;
-    const int grid = n_items < num_sms() ? n_items : num_sms();
-    attention_tc2_kernel<<<grid, AT2_THREADS, AT2_SMEM, stream>>>(map128, map16, map_out, static_cast<__nv_bfloat16*>(out_bf16),
-                                                                  n_items, heads, scale * 1.4426950408889634f);
-    count_launch();
-    HB_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
 #ifdef HB_EXP_TRACE
 extern "C" int hb_exp_read_at2_trace(long long* out) {
     return cudaMemcpyFromSymbol(out, g_at2_trace, sizeof(long long) * 4 * 64 * 16) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+int attention_tc2_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int heads, float scale, cudaStream_t stream) {
+    const int D = heads * 64;
+    const uint64_t rows = static_cast<uint64_t>(n_seq) * AT2_S;
+    CUtensorMap map128, map16;
+    if (encode_tmap_2d(&map128, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 128, 64)) return -1;
+    if (encode_tmap_2d(&map16, TMAP_BF16, qkv_bf16, rows, 3 * D, static_cast<uint64_t>(3) * D * 2, 16, 64)) return -1;
+    if (set_max_dynamic_smem(reinterpret_cast<const void*>(attention_tc2_kernel), AT2_SMEM)) return -1;
+    const int n_items = n_seq * heads;
+    const int grid = n_items < num_sms() ? n_items : num_sms();
+    attention_tc2_kernel<<<grid, AT2_THREADS, AT2_SMEM, stream>>>(map128, map16, static_cast<__nv_bfloat16*>(out_bf16), n_items,
+                                                                  heads, scale * 1.4426950408889634f);
+    count_launch();
+    HB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 }  // namespace hb

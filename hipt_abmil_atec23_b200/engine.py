@@ -66,6 +66,10 @@ class VitEngine:
             self.max_seqs = max_seqs or VIT4K_MAX_REGIONS
         self.max_rows = self.max_seqs * 257
         self._module = module
+        # one workspace per (module, device): concurrent callers (threads of nn.DataParallel sharing a device, user threads)
+        # take turns; launches go to the caller's current stream, and the next caller's stream waits for the previous one
+        self._run_lock = threading.RLock()
+        self._last_stream = None
         self._pos_cache = {}
         self._embed_cache = {}
         self._pack(module)
@@ -176,9 +180,22 @@ class VitEngine:
         return ent
 
     # ------------------------------------------------------------------------------------------------ forwards
-    def forward_patches(self, image, patch_begin=0, n_patches=None, mean=None, std=None, want_f32=True, out_bf16=None):
+    def _order_streams(self):
+        """The workspace is shared: work queued on another stream by the previous caller must finish first."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._last_stream is not None and self._last_stream != cur:
+            cur.wait_stream(self._last_stream)
+        self._last_stream = cur
+
+    def _set_cls_attention(self, buf):
+        _lib.check(self.lib.hb_vit_plan_set_cls_attention(self.plan, _lib.ptr(buf)))
+
+    def forward_patches(self, image, patch_begin=0, n_patches=None, mean=None, std=None, want_f32=True, out_bf16=None,
+                        cls_attn=None):
         """ViT-256 over patches of `image` (region [3,H,W], region batch [R,3,H,W] or patch batch [B,3,256,256]; fp32
-        normalised, or uint8 with mean/std).  Returns (cls_f32 [n, dim] or None, cls_bf16 [n, dim])."""
+        normalised, or uint8 with mean/std).  Returns (cls_f32 [n, dim] or None, cls_bf16 [n, dim]).
+        cls_attn: optional fp32 [n, heads, 257] CUDA tensor that receives the softmax row of the CLS query of the last block
+        (get_last_selfattention(...)[:, :, 0, :], vision_transformer.py:255-262) from the fused attention launch."""
         assert self.kind == "vit256"
         _lib.require_cuda(image, "image")
         ps, cs, rp, gc, total, ppi, istride = _lib.image_layout(image)
@@ -194,13 +211,19 @@ class VitEngine:
         else:
             ew, eb = self.embed_weights(None if is_f32 else mean, None if is_f32 else std)
         pos = self.pos_table(16, 16)
-        with torch.cuda.device(self.device):
+        with self._run_lock, torch.cuda.device(self.device):
+            self._order_streams()
             cls_f32 = torch.empty((n, self.dim), dtype=torch.float32, device=self.device) if want_f32 else None
             cls_bf16 = out_bf16 if out_bf16 is not None else torch.empty((n, self.dim), dtype=torch.bfloat16,
                                                                          device=self.device)
+            if cls_attn is not None:
+                assert cls_attn.is_cuda and cls_attn.dtype == torch.float32 and cls_attn.is_contiguous()
+                assert tuple(cls_attn.shape) == (n, self.heads, 257)
             done = 0
             while done < n:                         # minibatches of the plan capacity (hipt_4k.py:68-70)
                 cur = min(self.max_seqs, n - done)
+                if cls_attn is not None:
+                    self._set_cls_attention(cls_attn[done:])
                 if fused:
                     _lib.check(self.lib.hb_vit256_forward_u8(
                         self.plan, _lib.ptr(image), cs, rp, gc, ppi // gc, istride, total // ppi, patch_begin + done, cur,
@@ -213,9 +236,11 @@ class VitEngine:
                     _lib.ptr(eb), _lib.ptr(pos), _lib.ptr(cls_f32[done:] if cls_f32 is not None else None),
                     _lib.ptr(cls_bf16[done:]), _lib.stream_ptr()))
                 done += cur
+            if cls_attn is not None:
+                self._set_cls_attention(None)
         return cls_f32, cls_bf16
 
-    def forward_grid(self, cls256_bf16, n_regions, w0, h0, out=None):
+    def forward_grid(self, cls256_bf16, n_regions, w0, h0, out=None, cls_attn=None):
         """ViT-4K over n_regions grids of w0*h0 ViT-256 CLS tokens: [n_regions*w0*h0, in_dim] bf16 -> [n_regions, dim]
         (written into `out` [>= n_regions, dim] fp32 when given: the slide-set pass pools straight out of that buffer)."""
         assert self.kind == "vit4k"
@@ -225,19 +250,27 @@ class VitEngine:
         assert cls256_bf16.shape[0] >= n_regions * T and cls256_bf16.shape[1] == self.in_dim
         pos = self.pos_table(w0, h0)
         cap = max(1, self.max_rows // (T + 1))
-        with torch.cuda.device(self.device):
+        with self._run_lock, torch.cuda.device(self.device):
+            self._order_streams()
             if out is None:
                 out = torch.empty((n_regions, self.dim), dtype=torch.float32, device=self.device)
             else:
                 assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape[1] == self.dim
                 assert out.shape[0] >= n_regions
+            if cls_attn is not None:                  # [n_regions, heads, T + 1] fp32: CLS-query softmax row of the last block
+                assert cls_attn.is_cuda and cls_attn.dtype == torch.float32 and cls_attn.is_contiguous()
+                assert tuple(cls_attn.shape) == (n_regions, self.heads, T + 1)
             done = 0
             while done < n_regions:
                 cur = min(cap, n_regions - done)
+                if cls_attn is not None:
+                    self._set_cls_attention(cls_attn[done:])
                 _lib.check(self.lib.hb_vit4k_forward(
                     self.plan, _lib.ptr(cls256_bf16[done * T:]), cur, T, self.in_dim, _lib.ptr(self.phi_w),
                     _lib.ptr(self.phi_b), _lib.ptr(pos), _lib.ptr(out[done:]), _lib.stream_ptr()))
                 done += cur
+            if cls_attn is not None:
+                self._set_cls_attention(None)
         return out[:n_regions]
 
     # ------------------------------------------------------------------------------- attention maps (heatmap helpers)
@@ -249,12 +282,16 @@ class VitEngine:
         its rows (this is the visualisation path, SURVEY.md §8f rank 4, not the extraction hot path)."""
         import torch.nn.functional as F
         blk = self._module.blocks[-1]
-        if self.depth > 1:
-            self.set_depth_limit(self.depth - 1)
-        try:
-            run_prefix()
-        finally:
-            self.set_depth_limit(0)
+        with self._run_lock:                          # the depth limit is plan state: no other forward may interleave
+            if self.depth > 1:
+                self.set_depth_limit(self.depth - 1)
+            try:
+                run_prefix()
+            finally:
+                self.set_depth_limit(0)
+            return self._last_block_attention(blk, n_seq, seq_len, F)
+
+    def _last_block_attention(self, blk, n_seq, seq_len, F):
         if self.depth == 1:
             raise NotImplementedError("attention-map export needs at least two blocks")
         x = self.buffer(1, n_seq * seq_len, self.dim, torch.bfloat16).float().view(n_seq, seq_len, self.dim)

@@ -116,9 +116,45 @@ class HIPT_4K(nn.Module):
         out = self.model4k._engine(cls_bf16.device).forward_grid(cls_bf16, R, w_256, h_256)
         return (out, cls_bf16) if return_cls256 else out
 
-    # ------------------------------------------------------------------------------ out of the hot path
-    def _get_region_attention_scores(self, *a, **k):
-        raise NotImplementedError("ViT attention heatmaps are outside the accelerated hot path (SURVEY.md §8f rank 4)")
+    # ------------------------------------------------------------------------------ hierarchical attention maps
+    @torch.no_grad()
+    def region_cls_attention(self, x):
+        """CLS-query attention of the LAST block of both ViTs for one normalised region x [1,3,W,H]:
+        (attention_256 [w*h, heads, 256], attention_4k [heads, w*h], w_256, h_256) — exactly the slices
+        `get_last_selfattention(...)[:, :, 0, 1:]` that the reference's heatmap code reads (hipt_4k.py:145-147, 155-157),
+        emitted by the fused CLS-only attention launch of the forward pass itself: one model pass, no [B,6,257,257] matrix."""
+        img, w_256, h_256 = self.prepare_img_tensor(x)
+        img = img.to(self.device256, non_blocking=True)[0].float()
+        eng256 = self.model256._engine(img.device)
+        T = w_256 * h_256
+        a256 = torch.empty((T, eng256.heads, 257), dtype=torch.float32, device=img.device)
+        _, cls_bf16 = eng256.forward_patches(img, want_f32=False, cls_attn=a256)
+        if torch.device(self.device4k) != cls_bf16.device:
+            cls_bf16 = cls_bf16.to(self.device4k, non_blocking=True)
+        eng4k = self.model4k._engine(cls_bf16.device)
+        a4k = torch.empty((1, eng4k.heads, T + 1), dtype=torch.float32, device=cls_bf16.device)
+        eng4k.forward_grid(cls_bf16, 1, w_256, h_256, cls_attn=a4k)
+        return a256[:, :, 1:], a4k[0, :, 1:], w_256, h_256
+
+    @torch.no_grad()
+    def _get_region_attention_scores(self, region, scale=1):
+        """Interface of hipt_4k.py:121-164: region = PIL image (or HxWx3 uint8 array); returns
+        (patches [n, 256/scale, 256/scale, 3] uint8, attention_256 [n, heads, 256/scale, 256/scale],
+         attention_4k [heads, W/scale, H/scale]) as numpy arrays."""
+        x = eval_transforms()(region).unsqueeze(dim=0)
+        a256, a4k, w_256, h_256 = self.region_cls_attention(x)
+        nh = a256.shape[1]
+        attention_256 = a256.reshape(w_256 * h_256, nh, 16, 16)
+        attention_256 = nn.functional.interpolate(attention_256, scale_factor=int(16 / scale), mode="nearest").cpu().numpy()
+        attention_4k = a4k.reshape(a4k.shape[0], w_256, h_256)
+        attention_4k = nn.functional.interpolate(attention_4k.unsqueeze(0), scale_factor=int(256 / scale), mode="nearest")[0].cpu().numpy()
+        batch_256, _, _ = self.prepare_img_tensor(x)
+        batch_256 = batch_256.unfold(2, 256, 256).unfold(3, 256, 256)
+        batch_256 = batch_256.permute(0, 2, 3, 1, 4, 5).reshape(-1, 3, 256, 256)          # 'b c p1 p2 w h -> (b p1 p2) c w h'
+        if scale != 1:
+            batch_256 = nn.functional.interpolate(batch_256, scale_factor=(1 / scale), mode="nearest")
+        return tensorbatch2im(batch_256), attention_256, attention_4k
 
     def get_region_attention_heatmaps(self, *a, **k):
-        raise NotImplementedError("ViT attention heatmaps are outside the accelerated hot path (SURVEY.md §8f rank 4)")
+        raise NotImplementedError("drawing the blended heatmap images (matplotlib / PIL, hipt_4k.py:167-306) is outside the "
+                                  "accelerated hot path; _get_region_attention_scores provides their inputs")

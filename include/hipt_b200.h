@@ -155,6 +155,11 @@ void hb_vit_plan_destroy(hb_vit_plan* plan);
  * (1 = bf16 residual stream, 2 = qkv bf16, 3 = attention out bf16, 4 = MLP hidden bf16) */
 int hb_vit_plan_set_depth_limit(hb_vit_plan* plan, int depth_limit);
 int hb_vit_plan_buffer(hb_vit_plan* plan, int which, void** ptr, size_t* bytes);
+/* Attention-map export for the hierarchical heatmaps (HIPT_4K/hipt_4k.py:121-164 reads only attention[:, :, 0, 1:] of
+ * get_last_selfattention, vision_transformer.py:255-262 / vision_transformer4k.py:248-255): while cls_attn is non-NULL the
+ * forward drivers also write the softmax row of the CLS query of the LAST block, [n_seq, heads, seq_len] fp32 (device), from
+ * the fused CLS-only attention launch — no [B, heads, 257, 257] matrix, no second model pass.  NULL switches it off. */
+int hb_vit_plan_set_cls_attention(hb_vit_plan* plan, float* cls_attn);
 
 /* ViT-256 over n_patches 256x256 patches of one or more region images (HIPT_4K.forward steps 2-3, hipt_4k.py:64-70).
  * grid_cols > 0: the input is n_images-many region images, image_stride BYTES apart, each a grid of

@@ -223,6 +223,35 @@ def test_last_selfattention_maps(hipt):
     assert (att4 - ref4).abs().max().item() < 2e-3, (att4 - ref4).abs().max().item()
 
 
+def test_region_cls_attention_from_the_fused_kernel(hipt):
+    """f4: HIPT_4K._get_region_attention_scores (hipt_4k.py:121-164) from the CLS-row probabilities the fused CLS-only
+    attention launch writes during the ordinary forward pass — against the oracle's full attention maps (row 0, keys 1..),
+    and against the same module's get_last_selfattention; the features of that pass are the ordinary forward's."""
+    px = torch.randint(0, 256, (1, 3, 512, 768), dtype=torch.uint8, generator=torch.Generator().manual_seed(33))
+    x = O.eval_transforms_u8(px)
+    a256, a4k, w, h = hipt.region_cls_attention(x.to(DEV))
+    assert (w, h) == (2, 3) and a256.shape == (6, 6, 256) and a4k.shape == (6, 6)
+    sd = {k: v.detach().cpu() for k, v in hipt.model256.state_dict().items()}
+    sd4 = {k: v.detach().cpu() for k, v in hipt.model4k.state_dict().items()}
+    patches = O.unfold_region(x)
+    ref256 = O.last_selfattention(sd, O.vit256_tokens(sd, patches), 6)[:, :, 0, 1:]
+    assert (a256.cpu() - ref256).abs().max().item() < 2e-3, (a256.cpu() - ref256).abs().max().item()
+    cls = O.vit256_forward(sd, patches)
+    grid = cls.reshape(w, h, 384).transpose(0, 1).transpose(0, 2).unsqueeze(0)
+    ref4k = O.last_selfattention(sd4, O.vit4k_tokens(sd4, grid), 6)[0, :, 0, 1:]
+    assert (a4k.cpu() - ref4k).abs().max().item() < 3e-3, (a4k.cpu() - ref4k).abs().max().item()
+    full = hipt.model256.get_last_selfattention(patches.to(DEV))[:, :, 0, 1:]
+    assert (a256 - full).abs().max().item() < 2e-3
+    # the reference-shaped entry point: numpy arrays with nearest-neighbour upsampling
+    import numpy as np
+    img = px[0].permute(1, 2, 0).numpy()
+    b, att256, att4k = hipt._get_region_attention_scores(img, scale=4)
+    assert b.shape == (6, 64, 64, 3) and b.dtype == np.uint8
+    assert att256.shape == (6, 6, 64, 64) and att4k.shape == (6, 2 * 64, 3 * 64)
+    assert np.allclose(att256[:, :, ::4, ::4], a256.reshape(6, 6, 16, 16).cpu().numpy(), atol=1e-6)
+    assert np.allclose(att4k[:, ::64, ::64], a4k.reshape(6, 2, 3).cpu().numpy(), atol=1e-6)
+
+
 def test_batch_gt_1_rejected_like_reference(hipt):
     with pytest.raises(RuntimeError):
         hipt(torch.zeros(2, 3, 256, 256, device=DEV))

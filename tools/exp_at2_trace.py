@@ -1,5 +1,6 @@
-"""Dump the in-kernel event trace (HB_EXP_TRACE build) of CTA 0 of the tcgen05 attention kernel: cycles relative to the
-first stamp, per warpgroup tile.  HB_LIB_PATH=hipt_abmil_atec23_b200/lib/exp_NAME.so python tools/exp_at2_trace.py [n_seq]"""
+"""Dump the in-kernel event trace (HB_EXP_TRACE build) of CTA 0 of the tcgen05 attention kernel: cycles per phase of the
+softmax warpgroups (warp 4 / 8) and the epilogue warpgroup (warp 12).
+HB_LIB_PATH=hipt_abmil_atec23_b200/lib/exp_NAME.so python tools/exp_at2_trace.py [n_seq]"""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -16,18 +17,18 @@ lib = L.load()
 assert lib.hb_exp_read_at2_trace(buf) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(4, 64, 16)
 t0 = t[0, 0, 0]
-names = ["start", "kvq", "sA", "pA", "sB", "pB", "oA", "ldA", "oB", "ldB", "bar", "x"]
+names = ["kvq+dot", "sA", "unitA", "sB", "unitB", "stats"]
 for w in (0, 1):
-    print(f"--- softmax warpgroup {w}: per tile, start then deltas between successive stamps [{' '.join(names[1:11])}]")
+    print(f"--- softmax warpgroup {w} (one warp): item start, then deltas [{' '.join(names)}], item total")
     for j in range(2, 14):
         r = t[w, j]
-        d = [int(r[k] - r[k - 1]) for k in range(1, 11)]
-        print(f"tile {j:2d} start {int(r[0] - t0):8d} | " + " ".join(f"{x:6d}" for x in d) + f" | tile total {int(t[w, j + 1, 0] - r[0]):6d}")
-    print(f"    unit A inner: [ld done, max done, exp done] relative to the sA stamp")
-    for j in range(2, 8):
-        r = t[w, j]
-        print(f"tile {j:2d} " + " ".join(f"{int(r[k] - r[2]):6d}" for k in (11, 12, 13)) + f"   (pA {int(r[3]-r[2])})")
-    print(f"--- MMA warp {w}: [wait pA, issue PV A, wait pB, issue PV B, wait freeA, issue S A', wait freeB, issue S B'] absolute; then observed completion [S A, S B, O A, O B] (warpgroup 0 only)")
-    for j in range(2, 10):
-        r = t[2 + w, j]
-        print(f"tile {j:2d} " + " ".join(f"{int(r[k] - t0):8d}" for k in range(8)) + " | " + " ".join(f"{int(r[k] - t0):8d}" for k in range(8, 12)))
+        d = [int(r[k] - r[k - 1]) for k in range(1, 7)]
+        print(f"item {j:2d} start {int(r[0] - t0):8d} | " + " ".join(f"{x:6d}" for x in d) + f" | total {int(t[w, j + 1, 0] - r[0]):6d}")
+print("--- epilogue warpgroup (warp 12): absolute [O_a tile0 drained, tile0 stored, O_a tile1 drained, tile1 stored]")
+for j in range(2, 14):
+    r = t[2, j]
+    print(f"item {j:2d} " + " ".join(f"{int(r[k] - t0):8d}" for k in range(4)) + f" | item period {int(t[2, j + 1, 0] - r[0]):6d}")
+print("--- epilogue warpgroup, query-256 block (warp 12): deltas [kv wait, scores, bar1, exp+sum, P V, bar2, out+bar3]")
+for j in range(2, 14):
+    r = t[3, j]
+    print(f"item {j:2d} start {int(r[0] - t0):8d} | " + " ".join(f"{int(r[k] - r[k - 1]):6d}" for k in range(1, 8)))
