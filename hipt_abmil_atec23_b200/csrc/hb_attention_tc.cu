@@ -282,7 +282,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
         const int quad = warp & 3;
         const int r = quad * 32 + lane;                       // query row inside the tile = TMEM lane
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (2 * w) * 128;
-        float* my_stats = sStats + w * AT2_STATS_FLOATS + r * 8;
+        // The hand-off of the row statistics uses shared-space st / ld: they and the mbarrier operations travel the same
+        // in-order path.  Generic-address accesses (ST.E / LD.E) immediately followed by the arrive were observed to be
+        // overtaken by it about once in 10^5 items (the last word of the record, p_256, arrived stale).
+        const uint32_t my_stats = smem_u32(sStats + w * AT2_STATS_FLOATS + r * 8);
         for (int it = 0; it < my_items; ++it) {
             AT2_TRACE(w, it, 0);
             // ---- score of every row against key 256 (row 256 of K is row 0 of its own swizzle atom: unswizzled)
@@ -313,8 +316,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
 
             // ---- hand the row statistics to the epilogue warpgroup
             mbar_wait(&st_empty[w], (it & 1) ^ 1);
-            *reinterpret_cast<float4*>(my_stats) = make_float4(m_a, l_a, m_b, l_b);
-            my_stats[4] = p256;
+            sts_f4(my_stats, make_float4(m_a, l_a, m_b, l_b));
+            sts_f1(my_stats + 16, p256);
             mbar_arrive(&st_full[w]);
             AT2_TRACE(w, it, 6);
         }
@@ -444,9 +447,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
                 AT2_TRACE(2, it, 2 * w);
                 // ---- merge weights of the two halves from the row statistics
                 mbar_wait(&st_full[w], it & 1);
-                const float* stats = sStats + w * AT2_STATS_FLOATS + r * 8;
-                const float4 s4 = *reinterpret_cast<const float4*>(stats);
-                const float p256 = stats[4];
+                const uint32_t stats = smem_u32(sStats + w * AT2_STATS_FLOATS + r * 8);
+                const float4 s4 = lds_f4(stats);
+                const float p256 = __uint_as_float(lds_u1(stats + 16));
                 mbar_arrive(&st_empty[w]);
                 const float m = fmaxf(s4.x, s4.z);
                 const float e_a = at2_ex2((s4.x - m) * scale_log2), e_b = at2_ex2((s4.z - m) * scale_log2);

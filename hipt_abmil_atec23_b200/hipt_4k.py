@@ -59,6 +59,8 @@ class HIPT_4K(nn.Module):
     def _cls256(self, x, mean=None, std=None, want_f32=True):
         """ViT-256 CLS tokens of every 256x256 patch of one region view [3, W, H] on device256."""
         eng = self.model256._engine(x.device)
+        if x.stride(-1) != 1:                     # e.g. a channels-last view: the kernels read rows of unit stride
+            x = x.contiguous()
         return eng.forward_patches(x, mean=mean, std=std, want_f32=want_f32)
 
     @torch.no_grad()
@@ -124,7 +126,7 @@ class HIPT_4K(nn.Module):
         `get_last_selfattention(...)[:, :, 0, 1:]` that the reference's heatmap code reads (hipt_4k.py:145-147, 155-157),
         emitted by the fused CLS-only attention launch of the forward pass itself: one model pass, no [B,6,257,257] matrix."""
         img, w_256, h_256 = self.prepare_img_tensor(x)
-        img = img.to(self.device256, non_blocking=True)[0].float()
+        img = img.to(self.device256, non_blocking=True)[0].float().contiguous()
         eng256 = self.model256._engine(img.device)
         T = w_256 * h_256
         a256 = torch.empty((T, eng256.heads, 257), dtype=torch.float32, device=img.device)

@@ -57,7 +57,7 @@ class _ToNormalizedTensor:
         arr = np.asarray(img)
         if arr.ndim == 2:
             arr = arr[:, :, None]
-        t = torch.from_numpy(np.ascontiguousarray(arr)).permute(2, 0, 1)
+        t = torch.from_numpy(np.ascontiguousarray(arr)).permute(2, 0, 1).contiguous()   # CHW, as torchvision's ToTensor
         t = t.float().div(255.0) if t.dtype == torch.uint8 else t.float()
         return (t - self.mean) / self.std
 
