@@ -42,6 +42,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Consumer release of a buffer this thread has only READ (ld.shared) and whose values it has not consumed yet: the arrive
+// alone is not enough.  ptxas lowers mbarrier.arrive(.release) to a bare SYNCS.ARRIVE, which was observed to take effect while
+// earlier LDS of the same thread were still queued (shared-memory pipe backed up by every warp of the CTA loading at once):
+// the producer refilled the buffer and the late loads returned the NEXT item's rows.  The fence makes the loads perform first.
+__device__ __forceinline__ void mbar_arrive_after_reads(uint64_t* bar) {
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");

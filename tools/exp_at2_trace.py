@@ -28,7 +28,3 @@ print("--- epilogue warpgroup (warp 12): absolute [O_a tile0 drained, tile0 stor
 for j in range(2, 14):
     r = t[2, j]
     print(f"item {j:2d} " + " ".join(f"{int(r[k] - t0):8d}" for k in range(4)) + f" | item period {int(t[2, j + 1, 0] - r[0]):6d}")
-print("--- epilogue warpgroup, query-256 block (warp 12): deltas [kv wait, scores, bar1, exp+sum, P V, bar2, out+bar3]")
-for j in range(2, 14):
-    r = t[3, j]
-    print(f"item {j:2d} start {int(r[0] - t0):8d} | " + " ".join(f"{int(r[k] - r[k - 1]):6d}" for k in range(1, 8)))
