@@ -469,6 +469,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_sections:
         line["vit256_config2"] = vit256_config2(hipt, dev, peaks)
         line["clam_config4"] = clam_config4(dev, peaks)
+        line["ingest_jpeg"] = ingest_jpeg(hipt, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         state = cpu_reference_state()
         secs, info = [], {}
@@ -507,6 +508,72 @@ def vit256_config2(hipt, dev, peaks):
     return {"batch": 256, "ms": ms, "patches_per_s": 256 / ms * 1e3, "tflops_executed": flops / ms / 1e9,
             "frac_of_bf16_sustained": flops / ms / 1e9 / peaks["tflops_sustained"],
             "note": "one launch sequence over 256 patches (half the two-region launch the slide path uses)"}
+
+
+def ingest_jpeg(hipt, dev, regions=8, tile=256, quality=90):
+    """the slide pipeline fed from COMPRESSED regions (grids of 256 x 256 JPEG tiles, the storage
+    layout of the pyramidal TIFF / SVS files the reference reads through OpenSlide) — nvJPEG batched GPU decode into the
+    staging ring (hb_jpeg_decode_tiles), next group overlapped with the current ViT-256 pass — beside the decode alone and
+    the CPU decoder of the reference's loader (PIL / libjpeg, one core).  Tiles are encoded here with PIL from smooth
+    synthetic regions (noise does not compress); skipped when PIL is not importable."""
+    import io
+    import time
+    try:
+        from PIL import Image
+        import numpy as np
+    except Exception as ex:                                  # pragma: no cover
+        return {"skipped": f"PIL is not importable ({ex})"}
+    from hipt_abmil_atec23_b200.ingest import JpegRegionDecoder
+    from hipt_abmil_atec23_b200.pipeline import SlidePipeline
+    S = 4096
+    g = torch.Generator().manual_seed(77)
+    grids = []
+    for _ in range(2):                                       # two distinct regions, reused
+        img = torch.zeros(3, S, S)
+        for sc in (16, 64, 256):
+            img += torch.nn.functional.interpolate(torch.rand((1, 3, S // sc, S // sc), generator=g), size=(S, S), mode="bilinear")[0]
+        px = ((img / 3.0 + 0.02 * torch.randn((3, S, S), generator=g)).clamp(0, 1) * 255).round().to(torch.uint8).permute(1, 2, 0).numpy()
+        grid = []
+        for y in range(0, S, tile):
+            for x in range(0, S, tile):
+                buf = io.BytesIO()
+                Image.fromarray(px[y:y + tile, x:x + tile]).save(buf, format="JPEG", quality=quality, subsampling=0)
+                grid.append(buf.getvalue())
+        grids.append(grid)
+    per = len(grids[0])
+    tiles = [b for i in range(regions) for b in grids[i % 2]]
+    t0 = time.time()
+    for b in grids[0][:32]:
+        np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))
+    cpu_s = (time.time() - t0) * per / 32
+    dec = JpegRegionDecoder(dev, max_batch=2 * per)
+    out = torch.empty((2, 3, S, S), dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        dec.decode(tiles[:2 * per], S, S, out=out, tile=(tile, tile))
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for r0 in range(0, regions, 2):
+        dec.decode(tiles[r0 * per:(r0 + 2) * per], S, S, out=out, tile=(tile, tile))
+    torch.cuda.synchronize()
+    dec_rps = regions / (time.time() - t0)
+    from hipt_abmil_atec23_b200.model_clam import CLAM_SB
+    folds = []
+    for f in range(5):
+        torch.manual_seed(10 + f)
+        folds.append(CLAM_SB(size_arg="hipt_smaller", dropout=0.0, n_classes=2).eval().to(dev))
+    pipe = SlidePipeline(hipt, folds)
+    for _ in range(2):
+        pipe.run_jpeg(tiles, S, S, tile=(tile, tile))
+    t0 = time.time()
+    r = pipe.run_jpeg(tiles, S, S, tile=(tile, tile))
+    wall = time.time() - t0
+    return {"regions": regions, "tile": tile, "tiles_per_region": per, "quality": quality, "subsampling": "4:4:4", "backend": dec.backend,
+            "jpeg_MB_per_region": sum(map(len, grids[0])) / 1e6, "decode_only_regions_per_s": dec_rps,
+            "decode_only_decoded_GBps": dec_rps * 3 * S * S / 1e9, "pipeline_from_jpeg_regions_per_s": regions / wall,
+            "h2d_MB_per_region": sum(map(len, tiles)) / regions / 1e6, "finite": bool(torch.isfinite(r["features"]).all()),
+            "cpu_pil_decode_s_per_region_one_core": cpu_s,
+            "note": "decode and ViT share the SMs, so the JPEG-fed pipeline runs at about 1 / (1 / decode + 1 / model); the "
+                    "uint8-fed e2e line above is the headline"}
 
 
 def clam_config4(dev, peaks):

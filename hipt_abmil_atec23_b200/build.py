@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhipt_b200.so")
-SOURCES = ["hb_api.cu", "hb_gemm.cu", "hb_mlp.cu", "hb_rowops.cu", "hb_attention.cu", "hb_attention_tc.cu", "hb_clam.cu", "hb_embed.cu"]
+SOURCES = ["hb_api.cu", "hb_gemm.cu", "hb_mlp.cu", "hb_rowops.cu", "hb_attention.cu", "hb_attention_tc.cu", "hb_clam.cu", "hb_embed.cu", "hb_ingest.cu"]
 HEADERS = ["hb_ptx.cuh", "hb_internal.h", os.path.join("..", "..", "include", "hipt_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + out)
         objs.append(obj)
-    res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs,
+    res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-ldl"],
                          cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

@@ -806,24 +806,31 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
     return launch_gemm_cg<BN, EPI, 1, 0>(g, stream);
 }
 
+// Instantiated variants: 192-wide tiles for every epilogue (all model widths — 192, 384, 576, 768, 1152 — are multiples of
+// 192), 256-wide tiles for the plain / GELU / LayerNorm-folded epilogues of the N >= 1024 GEMMs (fc1).  A 128-wide tile was
+// never picked by any model shape and is gone; the residual and token epilogues never ran 256 wide.
 template <int BN>
 static int launch_gemm_bn(const GemmArgs& g, cudaStream_t stream) {
     switch (g.epi) {
         case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(g, stream);
         case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(g, stream);
-        case EPI_BIAS_RESADD_F32: return launch_gemm_t<BN, EPI_BIAS_RESADD_F32>(g, stream);
-        case EPI_TOKENS_F32: return launch_gemm_t<BN, EPI_TOKENS_F32>(g, stream);
-        case EPI_TOKENS_GELU_F32: return launch_gemm_t<BN, EPI_TOKENS_GELU_F32>(g, stream);
         case EPI_BIAS_GELU_FAST_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_FAST_BF16>(g, stream);
         case EPI_LNFOLD_BF16: return launch_gemm_t<BN, EPI_LNFOLD_BF16>(g, stream);
         case EPI_LNFOLD_GELU_BF16: return launch_gemm_t<BN, EPI_LNFOLD_GELU_BF16>(g, stream);
         case EPI_LNFOLD_GELU2_BF16: return launch_gemm_t<BN, EPI_LNFOLD_GELU2_BF16>(g, stream);
-        case EPI_RESID_BF16: return launch_gemm_t<BN, EPI_RESID_BF16>(g, stream);
-        case EPI_RESID_STATS_F32:
-            if constexpr (BN == 256) return set_error("hb_gemm: the residual epilogue runs 128/192-wide tiles only");
-            else return launch_gemm_t<BN, EPI_RESID_STATS_F32>(g, stream);
+        default: break;
     }
-    return set_error("hb_gemm: unknown epilogue %d", g.epi);
+    if constexpr (BN == 192) {
+        switch (g.epi) {
+            case EPI_BIAS_RESADD_F32: return launch_gemm_t<BN, EPI_BIAS_RESADD_F32>(g, stream);
+            case EPI_TOKENS_F32: return launch_gemm_t<BN, EPI_TOKENS_F32>(g, stream);
+            case EPI_TOKENS_GELU_F32: return launch_gemm_t<BN, EPI_TOKENS_GELU_F32>(g, stream);
+            case EPI_RESID_BF16: return launch_gemm_t<BN, EPI_RESID_BF16>(g, stream);
+            case EPI_RESID_STATS_F32: return launch_gemm_t<BN, EPI_RESID_STATS_F32>(g, stream);
+            default: break;
+        }
+    }
+    return set_error("hb_gemm: epilogue %d is not available with %d-wide tiles", g.epi, BN);
 }
 
 static bool gemm_use_cta_pairs() {      // HB_GEMM_CG=1 forces the single-CTA kernel (debug / comparison)
@@ -835,11 +842,10 @@ static bool gemm_use_cta_pairs() {      // HB_GEMM_CG=1 forces the single-CTA ke
 int gemm_pick_bn(int N) {
     {   // experiment hook: HB_GEMM_BN forces the tile width when it divides N
         const char* e = getenv("HB_GEMM_BN");
-        if (e) { const int v = atoi(e); if ((v == 128 || v == 192 || v == 256) && N % v == 0) return v; }
+        if (e) { const int v = atoi(e); if ((v == 192 || v == 256) && N % v == 0) return v; }
     }
     if (N % 256 == 0 && N >= 1024) return 256;
     if (N % 192 == 0) return 192;
-    if (N % 128 == 0) return 128;
     return 0;
 }
 
@@ -848,9 +854,10 @@ int gemm_prepare(GemmArgs& g, const void* A, const void* W, const float* bias, i
     if (M <= 0 || N <= 0 || K <= 0) return set_error("hb_gemm: bad shape M=%d N=%d K=%d", M, N, K);
     if (K % GEMM_BK != 0) return set_error("hb_gemm: K=%d must be a multiple of %d", K, GEMM_BK);
     int bn = gemm_pick_bn(N);
-    if (bn == 256 && epi == EPI_RESID_STATS_F32) bn = 128;      // residual ring + staging leave room for 128/192 only
-    if (bn == 256 && epi == EPI_RESID_BF16) bn = 128;           // 64-column statistics planes: keep the chunking simple
-    if (bn == 0) return set_error("hb_gemm: N=%d must be a multiple of 128 or 192", N);
+    const bool wide_ok = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_FAST_BF16 ||
+                          epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16 || epi == EPI_LNFOLD_GELU2_BF16);
+    if (bn == 256 && !wide_ok) bn = (N % 192 == 0) ? 192 : 0;   // residual / token epilogues run 192-wide tiles only
+    if (bn == 0) return set_error("hb_gemm: N=%d must be a multiple of 192 (or of 256 from 1024 up for the plain, GELU and LayerNorm-folded epilogues)", N);
     if (bias == nullptr) return set_error("hb_gemm: bias is required");
     g.bn = bn; g.epi = epi; g.M = M; g.N = N; g.K = K; g.bias = bias;
     g.tok_table = tok_table; g.tok_out = nullptr; g.tokens_per_seq = tokens_per_seq;
@@ -908,7 +915,6 @@ extern "C" int hb_exp_read_trace(long long* out) {
 
 int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
     switch (g.bn) {
-        case 128: return launch_gemm_bn<128>(g, stream);
         case 192: return launch_gemm_bn<192>(g, stream);
         case 256: return launch_gemm_bn<256>(g, stream);
     }

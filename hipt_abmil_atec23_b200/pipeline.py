@@ -4,7 +4,8 @@ This is the call a user of the accelerated path makes for one slide (the referen
 the file system: extract_features_fp.py:159-171 -> .h5/.pt -> eval.py / create_heatmaps.py:34-57).  `run_device` takes
 regions already resident in HBM; `run_host` takes pinned host memory and overlaps the host->device copy of the next group of regions
 (one ViT-256 launch = two 4096 x 4096 regions) with the ViT-256 pass of the current one on a second stream (two staging
-buffers).
+buffers); `run_jpeg` takes the JPEG bytes of the region tiles and decodes the next group on the GPU (nvJPEG, ingest.py)
+into the same staging buffers while the current group runs.
 """
 import torch
 
@@ -21,6 +22,7 @@ class SlidePipeline:
         self._stage = None
         self._copy_stream = None
         self._offs = {}
+        self._decoder = None
 
     # ------------------------------------------------------------------------------------------------ device input
     @torch.no_grad()
@@ -45,12 +47,42 @@ class SlidePipeline:
         Bytes moved per call: R * 3 * H * W in, R * 192 * 4 + small out."""
         assert not regions_u8_pinned.is_cuda and regions_u8_pinned.dtype == torch.uint8
         R, _, W, H = regions_u8_pinned.shape
+
+        def fill(stage, r0, n):
+            stage[:n].copy_(regions_u8_pinned[r0:r0 + n], non_blocking=True)
+        return self._run_staged(R, W, H, fill)
+
+    @torch.no_grad()
+    def run_jpeg(self, tiles, rows, cols, tile=None, backend="auto"):
+        """Same as run_host for regions of `rows` x `cols` pixels (multiples of 256) stored as JPEG: `tiles` is the flat
+        list of byte strings, region-major then row-major over each region's grid of tile = (tile_h, tile_w) tiles (None:
+        one bitstream per region).  The compressed bytes are what crosses PCIe; nvJPEG decodes group g + 1 into the
+        second staging buffer while ViT-256 runs group g.  Bytes moved per call: sum(len(t)) in."""
+        from .ingest import JpegRegionDecoder
+        th, tw = (rows, cols) if tile is None else tile
+        per = (rows // th) * (cols // tw)
+        assert len(tiles) % per == 0
+        R = len(tiles) // per
+        eng = self.hipt.model256._engine(self.device)
+        k = max(1, eng.max_seqs // ((rows // 256) * (cols // 256)))
+        if self._decoder is None or self._decoder.max_batch < k * per:
+            self._decoder = JpegRegionDecoder(self.device, max_batch=k * per, backend=backend)
+        tiles = [bytes(t) if not isinstance(t, bytes) else t for t in tiles]      # alive until the final synchronize
+
+        def fill(stage, r0, n):
+            self._decoder.decode(tiles[r0 * per:(r0 + n) * per], rows, cols, out=stage, tile=(th, tw))
+        out = self._run_staged(R, rows, cols, fill)
+        self._decoder.release()
+        return out
+
+    def _run_staged(self, R, W, H, fill):
+        """Groups of k regions through two staging buffers: fill(stage_buffer, first_region, n) runs on the copy stream."""
         dev = self.device
         T = (W // 256) * (H // 256)
         with torch.cuda.device(dev):
             eng = self.hipt.model256._engine(dev)
             k = max(1, eng.max_seqs // T)                       # regions per ViT-256 launch (two 4096x4096 regions)
-            shape = (2, k) + tuple(regions_u8_pinned.shape[1:])
+            shape = (2, k, 3, W, H)
             if self._stage is None or tuple(self._stage.shape) != shape:
                 self._stage = torch.empty(shape, dtype=torch.uint8, device=dev)
                 self._copy_stream = torch.cuda.Stream(device=dev)
@@ -66,7 +98,7 @@ class SlidePipeline:
                         self._copy_stream.wait_event(consumed[b])
                     elif g == 0:                                   # g == 1: staging buffer 1 has no consumer yet in this call
                         self._copy_stream.wait_stream(main)        # orders against the previous call's use of the buffers
-                    self._stage[b, :n].copy_(regions_u8_pinned[r0:r0 + n], non_blocking=True)
+                    fill(self._stage[b], r0, n)
                     copied[b].record(self._copy_stream)
                 main.wait_event(copied[b])
                 eng.forward_patches(self._stage[b, :n], mean=self.mean, std=self.std, want_f32=False,

@@ -257,6 +257,27 @@ int hb_adam_step(void* const* params, const void* const* grads, void* const* exp
                  const int* numel, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                  void* stream);
 
+/* Region ingest: JPEG-compressed region tiles -> planar uint8 regions in device memory, the
+ * [n, 3, height, width] layout hb_vit256_forward_u8 reads.  Replaces Whole_Slide_Bag_FP.__getitem__
+ * (datasets/dataset_h5.py:194-207: OpenSlide read_region -> PIL -> ToTensor/Normalize on the CPU) + collate_features
+ * (utils/utils.py:58-61) + the fp32 host -> device copy (HIPT_4K/hipt_4k.py:69) for tiles that are stored as JPEG.
+ * The decoder is nvJPEG's batched decode (library code, loaded with dlopen at the first call; it allocates its own scratch
+ * device memory — the one exception to "callers pass every buffer").  backend: -1 = GPU-assisted Huffman, falling back to
+ * the library default; otherwise an nvjpegBackend_t value.
+ * hb_jpeg_decode_tiles: a region is stored the way pyramidal TIFF / SVS files store it — as a grid of independently
+ * compressed tile_h x tile_w JPEG tiles (tile = region is the degenerate case).  jpeg_host: n = n_regions * (height / tile_h)
+ * * (width / tile_w) pointers to HOST bitstreams, region-major then row-major over the tile grid (keep them alive until the
+ * stream has been synchronised); image i lands in its sub-rectangle of the three planes of its region (nvJPEG writes with
+ * the region's row pitch).  Large batches of small tiles are what nvJPEG's GPU Huffman stage is built for: n <= max_batch. */
+typedef struct hb_jpeg_decoder hb_jpeg_decoder;
+int hb_jpeg_decoder_create(hb_jpeg_decoder** out, int max_batch, int backend);
+const char* hb_jpeg_decoder_backend(const hb_jpeg_decoder* decoder);
+void hb_jpeg_decoder_destroy(hb_jpeg_decoder* decoder);
+int hb_jpeg_probe(hb_jpeg_decoder* decoder, const unsigned char* jpeg, size_t length, int* width, int* height,
+                  int* components, int* subsampling);
+int hb_jpeg_decode_tiles(hb_jpeg_decoder* decoder, const unsigned char* const* jpeg_host, const size_t* lengths, int n,
+                         void* regions_u8, int height, int width, int tile_h, int tile_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

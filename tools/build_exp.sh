@@ -5,9 +5,9 @@ set -e
 NAME=$1; shift
 cd "$(dirname "$0")/../hipt_abmil_atec23_b200/csrc"
 mkdir -p ../lib
-for f in hb_api hb_gemm hb_mlp hb_rowops hb_attention hb_attention_tc hb_clam hb_embed; do
+for f in hb_api hb_gemm hb_mlp hb_rowops hb_attention hb_attention_tc hb_clam hb_embed hb_ingest; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -diag-suppress 128 -c $f.cu -o /tmp/exp_${NAME}_$f.o &
 done
 wait
-nvcc -shared -o ../lib/exp_${NAME}.so /tmp/exp_${NAME}_hb_*.o -lcuda
+nvcc -shared -o ../lib/exp_${NAME}.so /tmp/exp_${NAME}_hb_*.o -lcuda -ldl
 echo built ../lib/exp_${NAME}.so
