@@ -648,6 +648,27 @@ def clam_config4(dev, peaks):
     out["lean_train_step_1000_instances"] = {"ms": e0.elapsed_time(e1) / 100, "steps_per_s": 100e3 / e0.elapsed_time(e1),
                                              "note": "clam_engine.TrainStep: the same step as 6 launches, cross-entropy fused "
                                                      "into the backward, no autograd"}
+    # T independent trials (own weights, Adam state, bag, dropout seed, lr) per fused step, at the
+    # reference's training dropout 0.85 — six launches for all of them (hb_clam_sb_train_step_trials)
+    for T in (5, 8):
+        models = []
+        for t in range(T):
+            torch.manual_seed(300 + t)
+            models.append(CLAM_SB(size_arg="hipt_smaller", dropout=0.85, n_classes=2).to(dev).train())
+        tb = clam_engine.TrialBatchStep(models, lr=[2e-4 * (1 + t) for t in range(T)], weight_decay=1e-5, max_instances=1000)
+        bags = [torch.randn((1000, 192), generator=torch.Generator().manual_seed(50 + t)).to(dev) for t in range(T)]
+        labels = torch.tensor([t & 1 for t in range(T)], device=dev)
+        for _ in range(5):
+            tb.step(bags, labels)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            tb.step(bags, labels)
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"trial_batch_step_{T}_trials_1000_instances"] = {
+            "ms": e0.elapsed_time(e1) / 100, "trial_steps_per_s": T * 100e3 / e0.elapsed_time(e1), "dropout": 0.85,
+            "note": f"clam_engine.TrialBatchStep: {T} independent trials advance one train_loop step each in six launches"}
     return out
 
 

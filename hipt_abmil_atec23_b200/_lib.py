@@ -87,6 +87,13 @@ SIGNATURES = {
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_uint64,
                                             C.c_void_p]),
     "hb_clam_dropout_masks": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_clam_trials_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hb_clam_sb_train_step_trials": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_float,
+                                               C.c_float, C.c_float, C.c_float, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                               C.c_void_p]),
     "hb_jpeg_decoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "hb_jpeg_decoder_backend": (C.c_char_p, [C.c_void_p]),
     "hb_jpeg_decoder_destroy": (None, [C.c_void_p]),

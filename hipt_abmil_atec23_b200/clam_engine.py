@@ -306,6 +306,86 @@ class TrainStep:
         return self.loss
 
 
+class TrialBatchStep:
+    """up to 8 independent training trials of one CLAM_SB head size advance one step of train_loop
+    each (utils/core_utils.py:409-425: model(bag) -> CrossEntropyLoss -> backward -> Adam step) in SIX launches in total
+    (hb_clam_sb_train_step_trials) — the reference runs such trials as separate Ray Tune processes sharing a GPU
+    (main.py:40-52), ~60 launches per trial and step.  Trial t has its own model, Adam state (lr, weight decay, betas shared),
+    dropout seed and bag; semantics per trial are those of TrainStep + FusedAdam (same kernels' arithmetic).
+
+    models: CLAM_SB modules of one size_arg / n_classes / dropout on one CUDA device, all 10 tensors trainable.
+    step(bags, labels): bags = list of [n_t, 192] fp32 CUDA tensors (one per trial), labels int64 CUDA [T]; returns the
+    losses [T] as a device tensor (no host synchronisation).  Adam state lives in self.exp_avg / self.exp_avg_sq."""
+
+    def __init__(self, models, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, max_instances=20000, seeds=None):
+        self.models = list(models)
+        T = len(self.models)
+        if not 1 <= T <= 8:
+            raise RuntimeError("TrialBatchStep takes 1..8 trials per launch")
+        if not all(supports_fused_backward(m) for m in self.models):
+            raise RuntimeError("TrialBatchStep covers the HIPT head sizes (192-d features, L1 <= 128)")
+        self.params = [_param_list(m) for m in self.models]
+        if not all(p.requires_grad for ps in self.params for p in ps):
+            raise RuntimeError("TrialBatchStep updates all 10 CLAM_SB tensors of every trial")
+        shapes = [tuple(p.shape) for p in self.params[0]]
+        if any([tuple(p.shape) for p in ps] != shapes for ps in self.params):
+            raise RuntimeError("the trials of one launch share one head size and class count")
+        self.drop_p = dropout_p(self.models[0])
+        if any(dropout_p(m) != self.drop_p for m in self.models):
+            raise RuntimeError("the trials of one launch share one dropout probability")
+        self.T = T
+        self.dev = self.params[0][0].device
+        self.L0, self.L1 = 192, shapes[0][0]
+        self.D, self.C = shapes[2][0], shapes[8][0]
+        as_list = lambda v: [float(x) for x in v] if isinstance(v, (list, tuple)) else [float(v)] * T
+        self.lr, self.wd = as_list(lr), as_list(weight_decay)
+        self.betas, self.eps = betas, float(eps)
+        self.seeds = [int(s) for s in (seeds if seeds is not None else range(T))]
+        self.n_steps = [0] * T
+        self.maxn = int(max_instances)
+        self.lib = _lib.load()
+        dev = self.dev
+        self.grads = [[torch.zeros_like(p) for p in ps] for ps in self.params]
+        self.exp_avg = [[torch.zeros_like(p) for p in ps] for ps in self.params]
+        self.exp_avg_sq = [[torch.zeros_like(p) for p in ps] for ps in self.params]
+        flat = lambda groups: (C.c_void_p * (10 * T))(*[t.data_ptr() for g in groups for t in g])
+        self.warr, self.garr, self.marr, self.varr = flat(self.params), flat(self.grads), flat(self.exp_avg), flat(self.exp_avg_sq)
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        self.a_raw, self.m_out, self.logits, self.loss = f32(T * self.maxn), f32(T, self.L1), f32(T, self.C), f32(T)
+        self.ws = torch.empty(max(self.lib.hb_clam_trials_workspace_bytes(self.maxn, T, self.L1), 16), dtype=torch.uint8, device=dev)
+        self.last_seeds = None
+
+    @torch.no_grad()
+    def step(self, bags, labels):
+        T = self.T
+        assert len(bags) == T and labels.numel() == T and labels.dtype == torch.int64 and labels.is_cuda
+        lens = [int(b.shape[0]) for b in bags]
+        if min(lens) < 1 or max(lens) > self.maxn:
+            raise RuntimeError(f"bag sizes {lens} outside 1..{self.maxn}")
+        feats = bags[0] if T == 1 else torch.cat([b.float() for b in bags], dim=0)
+        if feats.dtype != torch.float32 or not feats.is_contiguous():
+            feats = feats.float().contiguous()
+        offs_h = [0]
+        for n in lens:
+            offs_h.append(offs_h[-1] + n)
+        offs_host = (C.c_int32 * (T + 1))(*offs_h)
+        offs_dev = torch.tensor(offs_h, dtype=torch.int32).to(self.dev, non_blocking=True)
+        training = self.models[0].training
+        seeds = []
+        for t in range(T):
+            self.n_steps[t] += 1
+            seeds.append((self.seeds[t] + 0x9E3779B97F4A7C15 * self.n_steps[t]) & 0x3FFFFFFFFFFFFFFF)   # TrainStep's schedule
+        self.last_seeds = seeds
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.hb_clam_sb_train_step_trials(
+                _lib.ptr(feats), _lib.ptr(offs_dev), offs_host, T, self.warr, self.garr, self.marr, self.varr, _lib.ptr(labels),
+                (C.c_float * T)(*self.lr), (C.c_float * T)(*self.wd), (C.c_int * T)(*self.n_steps), float(self.betas[0]),
+                float(self.betas[1]), self.eps, self.drop_p if training else 0.0, (C.c_uint64 * T)(*seeds), _lib.ptr(self.a_raw),
+                _lib.ptr(self.m_out), _lib.ptr(self.logits), _lib.ptr(self.loss), self.L0, self.L1, self.D, self.C,
+                _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr()))
+        return self.loss
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr, betas, eps, weight_decay) semantics with every fp32 CUDA tensor of a group updated by
     ONE hb_adam_step launch (the reference's get_optim builds optim.Adam(lr=args.lr, weight_decay=args.reg),

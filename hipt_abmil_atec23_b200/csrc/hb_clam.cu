@@ -67,6 +67,8 @@ __host__ __device__ __forceinline__ float clam_keep(const ClamDrop& dr, uint32_t
     const uint32_t h = clam_mix32(clam_mix32(instance * 0x9E3779B1u + dr.seed_lo) ^ (unit * 0x7FEB352Du + dr.seed_hi));
     return h >= dr.thresh_lo ? dr.scale : 0.0f;
 }
+// one dropout state per model: the paired (multi-trial training) launch gives every trial its own seed
+struct ClamDrops { ClamDrop d[8]; };
 static ClamDrop clam_drop_make(float p, unsigned long long seed) {
     ClamDrop d = {};
     if (p <= 0.f) return d;
@@ -352,7 +354,9 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
                                                                      int D_rt, const int32_t* __restrict__ prefix,
                                                                      const int32_t* __restrict__ work, int work_cap,
                                                                      float* __restrict__ a_raw, float* __restrict__ partials,
-                                                                     const ClamDrop dr) {
+                                                                     const __grid_constant__ ClamDrops drs, int paired) {
+    // paired: model m is evaluated on bag m only (n_bags == n_models) and a_raw is written without the model stride —
+    // the multi-trial training step, where every trial has its own weights, bag and dropout seed
     const int L1 = L1T ? L1T : L1_rt, D = L1T ? L1T / 2 : D_rt;    // the HIPT heads have D = L1 / 2 (model_clam.py:81)
     extern __shared__ __align__(16) float smem_clam[];
     const int ldh = L1 + 4;
@@ -392,7 +396,9 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
     const int inst = tid & 63, half = tid >> 6;
     const bool valid = half == 0 && inst < n_valid;
     for (int mi = 0; mi < n_models; ++mi) {
+        if (paired && mi != bag) continue;
         const ClamModel& w = models.m[mi];
+        const ClamDrop& dr = drs.d[paired ? mi : 0];
         // gate weights and every small vector of this fold: issued before the first Linear so that their latency hides
         // under it (the staging of W1 inside clam_fc1_192 waits on the same cp.async group)
         for (int idx = tid; idx < D * L1 / 4; idx += nthreads) {
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
         __syncthreads();
         float A = sV[L1 + 3 * D];
         for (int q = 0; q < n_gt; ++q) A += sA[q * CL_CH + inst];
-        if (valid) a_raw[static_cast<size_t>(mi) * total_instances + start + i0 + inst] = A;
+        if (valid) a_raw[(paired ? 0 : static_cast<size_t>(mi) * total_instances) + start + i0 + inst] = A;
 
         // ---- chunk-local softmax partial
         const float mx = block_reduce_max_128(valid ? A : -INFINITY, red);
@@ -763,12 +769,14 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
                                                            int C, int work_cap, int CH, const int32_t* __restrict__ prefix,
                                                            const float* __restrict__ partials,
                                                            float* __restrict__ m_out, float* __restrict__ logits,
-                                                           float* __restrict__ y_prob, long long* __restrict__ y_hat) {
+                                                           float* __restrict__ y_prob, long long* __restrict__ y_hat,
+                                                           int paired) {
     extern __shared__ float sM[];                             // [L1] + [C] + [128] scratch + [8]
     float* sL = sM + L1;
     float* sP = sL + C;                                       // [128] per-group partial sums of M
     float* red = sP + 128;
-    const int bag = blockIdx.x, mi = blockIdx.y, tid = threadIdx.x;
+    const int bag = blockIdx.x, mi = paired ? blockIdx.x : blockIdx.y, tid = threadIdx.x;
+    const int oi = paired ? bag : mi * n_bags + bag;          // paired (multi-trial): model m pools bag m only, compact outputs
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
     const int n_chunks = (len + CH - 1) / CH;
     const size_t rec = L1 + 2;
@@ -794,7 +802,7 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
             for (int g = 0; g < G; ++g) v += sP[g * L1 + tid];
             v *= inv;
             sM[tid] = v;
-            if (m_out) m_out[static_cast<size_t>(mi * n_bags + bag) * L1 + tid] = v;
+            if (m_out) m_out[static_cast<size_t>(oi) * L1 + tid] = v;
         }
     } else {
         for (int j = tid; j < L1; j += blockDim.x) {
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
             for (int c = 0; c < n_chunks; ++c) acc = fmaf(base[c * rec + 2 + j], expf(base[c * rec] - gmax), acc);
             acc *= inv;
             sM[j] = acc;
-            if (m_out) m_out[static_cast<size_t>(mi * n_bags + bag) * L1 + j] = acc;
+            if (m_out) m_out[static_cast<size_t>(oi) * L1 + j] = acc;
         }
     }
     __syncthreads();
@@ -812,7 +820,7 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
         float acc = __ldg(bcls + c);
         for (int j = 0; j < L1; ++j) acc = fmaf(__ldg(Wcls + static_cast<size_t>(c) * L1 + j), sM[j], acc);
         sL[c] = acc;
-        if (logits) logits[static_cast<size_t>(mi * n_bags + bag) * C + c] = acc;
+        if (logits) logits[static_cast<size_t>(oi) * C + c] = acc;
     }
     __syncthreads();
     if (tid == 0) {
@@ -821,8 +829,8 @@ __global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __rest
         for (int c = 1; c < C; ++c) if (sL[c] > mx) { mx = sL[c]; arg = c; }
         float s = 0.f;
         for (int c = 0; c < C; ++c) s += expf(sL[c] - mx);
-        if (y_prob) for (int c = 0; c < C; ++c) y_prob[static_cast<size_t>(mi * n_bags + bag) * C + c] = expf(sL[c] - mx) / s;
-        if (y_hat) y_hat[mi * n_bags + bag] = arg;
+        if (y_prob) for (int c = 0; c < C; ++c) y_prob[static_cast<size_t>(oi) * C + c] = expf(sL[c] - mx) / s;
+        if (y_hat) y_hat[oi] = arg;
     }
 }
 
@@ -845,9 +853,16 @@ size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1) {
 int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
                         int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
                         float* a_raw, float* m_out, float* logits, float* y_prob, long long* y_hat, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream, float dropout_p, unsigned long long dropout_seed) {
+                        size_t workspace_bytes, cudaStream_t stream, float dropout_p, unsigned long long dropout_seed,
+                        const unsigned long long* paired_seeds) {
     if (n_bags <= 0) return 0;
-    const ClamDrop dr = clam_drop_make(dropout_p, dropout_seed);
+    // paired_seeds != NULL: the multi-trial training forward — model m on bag m only, its own dropout seed
+    const int paired = paired_seeds != nullptr;
+    if (paired && n_bags != n_models) return set_error("hb_clam: the paired launch needs one bag per model");
+    ClamDrops drs;
+    memset(&drs, 0, sizeof(drs));
+    drs.d[0] = clam_drop_make(dropout_p, dropout_seed);
+    if (paired) for (int m = 0; m < n_models && m < 8; ++m) drs.d[m] = clam_drop_make(dropout_p, paired_seeds[m]);
     const bool dropping = dropout_p > 0.f;
     if (dropping && !clam_is192(L0, L1, D))
         return set_error("hb_clam: training-mode dropout is implemented for the HIPT heads (192-d features, L1 <= 128)");
@@ -881,7 +896,8 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + off_part);
     static int tc_env = -1;
     if (tc_env < 0) { const char* e = getenv("HB_CLAM_TC"); tc_env = (e && e[0] == '0') ? 0 : 1; }
-    if (tc_env && !dropping && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
+    if (paired && !clam_is192(L0, L1, D)) return set_error("hb_clam: the paired launch is implemented for the HIPT heads (192-d features)");
+    if (tc_env && !dropping && !paired && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
         // tensor-core path: 128-instance chunks (fewer (bag, chunk) items than the bound computed for CH above)
         clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, TC_M, prefix, work, work_cap);
         count_launch();
@@ -909,7 +925,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         ProfScope ps2(11, stream);
         clam_combine_kernel<<<grid2, 128, (L1 + C + 128 + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                                         work_cap, TC_M, prefix, partials, m_out,
-                                                                                        logits, y_prob, y_hat);
+                                                                                        logits, y_prob, y_hat, 0);
         count_launch();
         HB_CUDA_OK(cudaGetLastError());
         return 0;
@@ -933,7 +949,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 220 * 1024)) return -1;
         ProfScope ps(10, stream);
         kern<<<work_cap, threads, smem, stream>>>(feats, bag_offsets, models, n_models, n_bags, total_instances, L1, D,
-                                                  prefix, work, work_cap, a_raw, partials, dr);
+                                                  prefix, work, work_cap, a_raw, partials, drs, paired);
         count_launch();
         HB_CUDA_OK(cudaGetLastError());
     } else if (max_chunks > 0) {
@@ -947,11 +963,11 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         count_launch();
     HB_CUDA_OK(cudaGetLastError());
     }
-    dim3 grid2(n_bags, n_models);
+    dim3 grid2(n_bags, paired ? 1 : n_models);
     ProfScope ps2(11, stream);
     clam_combine_kernel<<<grid2, 128, (L1 + C + 128 + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                                     work_cap, CH, prefix, partials, m_out,
-                                                                                    logits, y_prob, y_hat);
+                                                                                    logits, y_prob, y_hat, paired);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -972,12 +988,12 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
 // =====================================================================================================================
 struct ClamGrads { float* p[10]; };
 
-__global__ void __launch_bounds__(256) clam_bwd_prep_kernel(const float* __restrict__ a_raw, int N, const float* __restrict__ M,
-                                                            const float* __restrict__ dlogits, const float* __restrict__ dM_ext,
-                                                            const float* __restrict__ Wcls, const __grid_constant__ ClamGrads g,
-                                                            int L1, int D, int C, float* __restrict__ ctx,
-                                                            const float* __restrict__ logits, const long long* __restrict__ label,
-                                                            float* __restrict__ loss_out) {
+__device__ __forceinline__ void clam_bwd_prep_body(const float* __restrict__ a_raw, int N, const float* __restrict__ M,
+                                                   const float* __restrict__ dlogits, const float* __restrict__ dM_ext,
+                                                   const float* __restrict__ Wcls, const ClamGrads& g,
+                                                   int L1, int D, int C, float* __restrict__ ctx,
+                                                   const float* __restrict__ logits, const long long* __restrict__ label,
+                                                   float* __restrict__ loss_out) {
     __shared__ float red[8];
     __shared__ float s_dl[64];
     const int tid = threadIdx.x;
@@ -1018,12 +1034,34 @@ __global__ void __launch_bounds__(256) clam_bwd_prep_kernel(const float* __restr
         for (int idx = tid; idx < sizes[k]; idx += 256) g.p[k][idx] = 0.f;
 }
 
+// One training trial of the fused multi-trial step (hb_clam_sb_train_step_trials): its bag, weights, gradient buffers,
+// forward outputs and dropout state.  Eight of them fit the 4 KB kernel-parameter space.
+struct BwdTrial {
+    const float* feats; const float* a_raw; const float* M; const float* logits; const long long* label; float* loss; float* ctx;
+    int N;
+    ClamModel w; ClamGrads g; ClamDrop dr;
+};
+struct BwdTrials { BwdTrial t[8]; };
+
+__global__ void __launch_bounds__(256) clam_bwd_prep_kernel(const float* __restrict__ a_raw, int N, const float* __restrict__ M,
+                                                            const float* __restrict__ dlogits, const float* __restrict__ dM_ext,
+                                                            const float* __restrict__ Wcls, const __grid_constant__ ClamGrads g,
+                                                            int L1, int D, int C, float* __restrict__ ctx,
+                                                            const float* __restrict__ logits, const long long* __restrict__ label,
+                                                            float* __restrict__ loss_out) {
+    clam_bwd_prep_body(a_raw, N, M, dlogits, dM_ext, Wcls, g, L1, D, C, ctx, logits, label, loss_out);
+}
+// one CTA per trial: cross-entropy of the trial's logits against its label, softmax statistics, classifier gradients
+__global__ void __launch_bounds__(256) clam_bwd_prep_trials_kernel(const __grid_constant__ BwdTrials tr, int L1, int D, int C) {
+    const BwdTrial& t = tr.t[blockIdx.x];
+    clam_bwd_prep_body(t.a_raw, t.N, t.M, nullptr, nullptr, t.w.p[8], t.g, L1, D, C, t.ctx, t.logits, t.label, t.loss);
+}
+
 template <int TN, int L1T>
-__global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restrict__ feats, int N,
-                                                          const __grid_constant__ ClamModel w, const float* __restrict__ a_raw,
-                                                          const float* __restrict__ dA_ext, const float* __restrict__ ctx,
-                                                          const __grid_constant__ ClamGrads g, int L1_rt, int D_rt, int ch,
-                                                          const ClamDrop dr) {
+__device__ __forceinline__ void clam_bwd192_body(const float* __restrict__ feats, int N, const ClamModel& w,
+                                                 const float* __restrict__ a_raw, const float* __restrict__ dA_ext,
+                                                 const float* __restrict__ ctx, const ClamGrads& g, int L1_rt, int D_rt, int ch,
+                                                 const ClamDrop& dr, int chunk) {
     const int L1 = L1T ? L1T : L1_rt, D = L1T ? L1T / 2 : D_rt;
     extern __shared__ __align__(16) float smem_clam[];
     const int ldh = L1 + 4, ldp = 2 * D + 1;
@@ -1037,7 +1075,7 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
     float* sV = sDA + 2 * ch;                             // b1 [L1] | ba [D] | bb [D] | Wc [D] | bc [1] | pad | dM [L1]
     float* sDZ = sW;
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int i0 = blockIdx.x * ch;
+    const int i0 = chunk * ch;
     const int n_valid = min(ch, N - i0);
     const int nsmall = L1 + 3 * D + 1;
     float* sDM = sV + ((nsmall + 3) & ~3);
@@ -1181,6 +1219,22 @@ __global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restric
     }
 }
 
+template <int TN, int L1T>
+__global__ void __launch_bounds__(256) clam_bwd192_kernel(const float* __restrict__ feats, int N,
+                                                          const __grid_constant__ ClamModel w, const float* __restrict__ a_raw,
+                                                          const float* __restrict__ dA_ext, const float* __restrict__ ctx,
+                                                          const __grid_constant__ ClamGrads g, int L1_rt, int D_rt, int ch,
+                                                          const ClamDrop dr) {
+    clam_bwd192_body<TN, L1T>(feats, N, w, a_raw, dA_ext, ctx, g, L1_rt, D_rt, ch, dr, blockIdx.x);
+}
+// grid (chunks of the longest bag, trials): every trial's recomputing backward in one launch
+template <int TN, int L1T>
+__global__ void __launch_bounds__(256) clam_bwd192_trials_kernel(const __grid_constant__ BwdTrials tr, int L1_rt, int D_rt, int ch) {
+    const BwdTrial& t = tr.t[blockIdx.y];
+    if (static_cast<int>(blockIdx.x) * ch >= t.N) return;
+    clam_bwd192_body<TN, L1T>(t.feats, t.N, t.w, t.a_raw, nullptr, t.ctx, t.g, L1_rt, D_rt, ch, t.dr, blockIdx.x);
+}
+
 int clam_backward_launch(const float* feats, int N, const void* const* weights_host, const float* a_raw, const float* M,
                          const float* dlogits, const float* dM_ext, const float* dA_ext, void* const* grads_host, int L0,
                          int L1, int D, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
@@ -1228,6 +1282,144 @@ int clam_backward_launch(const float* feats, int N, const void* const* weights_h
     if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 220 * 1024)) return -1;
     ProfScope ps(13, stream);
     kern<<<(N + ch - 1) / ch, threads, smem, stream>>>(feats, N, w, a_raw, dA_ext, ctx, g, L1, D, ch, dr);
+    count_launch();
+    HB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-trial training step: T independent trials — the reference packs five Ray Tune trials on
+// one GPU as five processes, each running train_loop (utils/core_utils.py:384-426) one bag at a time — advance one step
+// each in SIX launches: work table, paired scores (trial t's weights on trial t's bag), paired combine, one prep CTA per
+// trial (cross-entropy + its gradient), the recomputing backward over a (chunk, trial) grid, and one Adam launch over all
+// 10 T tensors with per-trial learning rate / weight decay / step count.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ADAM_TRIALS = 8;
+struct AdamTrialTensors {
+    float* p[10 * ADAM_TRIALS]; const float* g[10 * ADAM_TRIALS]; float* m[10 * ADAM_TRIALS]; float* v[10 * ADAM_TRIALS];
+    int end[10 * ADAM_TRIALS];
+    float lr_bc1[ADAM_TRIALS], bc2_sqrt[ADAM_TRIALS], wd[ADAM_TRIALS];
+};
+static_assert(sizeof(AdamTrialTensors) <= 4000, "kernel parameter space");
+
+__global__ void __launch_bounds__(256) adam_trials_kernel(const __grid_constant__ AdamTrialTensors t, int n_tensors, int total,
+                                                          float b1, float b2, float eps) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k < n_tensors - 1 && idx >= t.end[k]) ++k;
+        const int off = idx - (k ? t.end[k - 1] : 0);
+        const int tr = k / 10;
+        const float p = t.p[k][off];
+        const float g = t.g[k][off] + t.wd[tr] * p;
+        const float m = b1 * t.m[k][off] + (1.0f - b1) * g;
+        const float v = b2 * t.v[k][off] + (1.0f - b2) * g * g;
+        t.m[k][off] = m;
+        t.v[k][off] = v;
+        t.p[k][off] = p - t.lr_bc1[tr] * m / (sqrtf(v) / t.bc2_sqrt[tr] + eps);
+    }
+}
+
+int clam_train_trials_launch(const float* feats, const int32_t* bag_offsets_dev, const int32_t* bag_offsets_host, int n_trials,
+                             const void* const* weights_host, void* const* grads_host, void* const* exp_avg_host,
+                             void* const* exp_avg_sq_host, const long long* labels_dev, const float* lr, const float* weight_decay,
+                             const int* step, float beta1, float beta2, float eps, float dropout_p,
+                             const unsigned long long* dropout_seeds, float* a_raw, float* m_pooled, float* logits, float* loss,
+                             int L0, int L1, int D, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (n_trials < 1 || n_trials > ADAM_TRIALS) return set_error("hb_clam_sb_train_step_trials: 1..%d trials per launch", ADAM_TRIALS);
+    if (!clam_is192(L0, L1, D)) return set_error("hb_clam_sb_train_step_trials: HIPT heads only (192-d features, L1 <= 128)");
+    if (!feats || !bag_offsets_dev || !bag_offsets_host || !weights_host || !grads_host || !exp_avg_host || !exp_avg_sq_host ||
+        !labels_dev || !lr || !weight_decay || !step || !dropout_seeds || !a_raw || !m_pooled || !logits || !loss || !workspace)
+        return set_error("hb_clam_sb_train_step_trials: null argument");
+    int max_len = 0;
+    for (int t = 0; t < n_trials; ++t) {
+        const int len = bag_offsets_host[t + 1] - bag_offsets_host[t];
+        if (len < 1) return set_error("hb_clam_sb_train_step_trials: trial %d has an empty bag", t);
+        if (step[t] < 1) return set_error("hb_clam_sb_train_step_trials: step counts from 1");
+        max_len = len > max_len ? len : max_len;
+    }
+    const int total = bag_offsets_host[n_trials];
+    // workspace: [forward workspace][n_trials x (4 + L1) floats of backward context]
+    const size_t fwd_ws = (clam_workspace_bytes(max_len, n_trials, n_trials, L1) + 15) & ~static_cast<size_t>(15);
+    const size_t need = fwd_ws + static_cast<size_t>(n_trials) * (4 + L1) * sizeof(float);
+    if (workspace_bytes < need) return set_error("hb_clam_sb_train_step_trials: workspace %zu < %zu bytes", workspace_bytes, need);
+    // ---- forward: launches 1-3
+    if (clam_forward_launch(feats, bag_offsets_dev, n_trials, total, max_len, weights_host, n_trials, L0, L1, D, C, a_raw, m_pooled,
+                            logits, nullptr, nullptr, workspace, fwd_ws, stream, dropout_p, 0ull, dropout_seeds)) return -1;
+    // ---- backward: launches 4-5
+    BwdTrials tr;
+    memset(&tr, 0, sizeof(tr));
+    float* ctx0 = reinterpret_cast<float*>(static_cast<char*>(workspace) + fwd_ws);
+    for (int t = 0; t < n_trials; ++t) {
+        BwdTrial& b = tr.t[t];
+        b.feats = feats + static_cast<size_t>(bag_offsets_host[t]) * 192;
+        b.a_raw = a_raw + bag_offsets_host[t];
+        b.M = m_pooled + static_cast<size_t>(t) * L1;
+        b.logits = logits + static_cast<size_t>(t) * C;
+        b.label = labels_dev + t;
+        b.loss = loss + t;
+        b.ctx = ctx0 + static_cast<size_t>(t) * (4 + L1);
+        b.N = bag_offsets_host[t + 1] - bag_offsets_host[t];
+        b.dr = clam_drop_make(dropout_p, dropout_seeds[t]);
+        for (int k = 0; k < 10; ++k) {
+            b.w.p[k] = static_cast<const float*>(weights_host[t * 10 + k]);
+            b.g.p[k] = static_cast<float*>(grads_host[t * 10 + k]);
+            if (!b.w.p[k] || !b.g.p[k]) return set_error("hb_clam_sb_train_step_trials: weight / gradient pointer %d of trial %d is null", k, t);
+        }
+    }
+    {
+        ProfScope ps(12, stream);
+        clam_bwd_prep_trials_kernel<<<n_trials, 256, 0, stream>>>(tr, L1, D, C);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+    }
+    {
+        const int ldp = 2 * D + 1;
+        const int ch = L1 >= 64 ? 32 : CL_CH;
+        const int threads = L1 >= 64 ? 256 : CL_THREADS;
+        if (D % (threads / ch) != 0 || L1 % (threads / ch) != 0)
+            return set_error("hb_clam_sb_train_step_trials: D=%d and L1=%d must be multiples of %d", D, L1, threads / ch);
+        const size_t smem = (static_cast<size_t>(ch) * CL_XS + clam_sw_floats(L1) + static_cast<size_t>(ch) * (L1 + 4) +
+                             2 * static_cast<size_t>(D) * L1 + 2 * static_cast<size_t>(ch) * ldp + 2 * ch +
+                             ((L1 + 3 * D + 1 + 3) & ~3) + L1 + 8) * sizeof(float);
+        auto kern = (L1 <= 16) ? clam_bwd192_trials_kernel<4, 0> : clam_bwd192_trials_kernel<8, 0>;
+        if (D * 2 == L1) {
+            if (L1 == 8) kern = clam_bwd192_trials_kernel<4, 8>;
+            else if (L1 == 16) kern = clam_bwd192_trials_kernel<4, 16>;
+            else if (L1 == 32) kern = clam_bwd192_trials_kernel<8, 32>;
+            else if (L1 == 64) kern = clam_bwd192_trials_kernel<8, 64>;
+            else if (L1 == 128) kern = clam_bwd192_trials_kernel<8, 128>;
+        }
+        if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 220 * 1024)) return -1;
+        ProfScope ps(13, stream);
+        kern<<<dim3((max_len + ch - 1) / ch, n_trials), threads, smem, stream>>>(tr, L1, D, ch);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+    }
+    // ---- Adam: launch 6
+    AdamTrialTensors at;
+    memset(&at, 0, sizeof(at));
+    const int numel[10] = {L1 * 192, L1, D * L1, D, D * L1, D, D, 1, C * L1, C};
+    int tot = 0;
+    for (int t = 0; t < n_trials; ++t) {
+        for (int k = 0; k < 10; ++k) {
+            const int i = t * 10 + k;
+            at.p[i] = static_cast<float*>(const_cast<void*>(weights_host[i]));
+            at.g[i] = static_cast<const float*>(grads_host[i]);
+            at.m[i] = static_cast<float*>(exp_avg_host[i]);
+            at.v[i] = static_cast<float*>(exp_avg_sq_host[i]);
+            if (!at.m[i] || !at.v[i]) return set_error("hb_clam_sb_train_step_trials: Adam state pointer %d of trial %d is null", k, t);
+            tot += numel[k];
+            at.end[i] = tot;
+        }
+        const float bc1 = 1.0f - powf(beta1, static_cast<float>(step[t]));
+        at.lr_bc1[t] = lr[t] / bc1;
+        at.bc2_sqrt[t] = sqrtf(1.0f - powf(beta2, static_cast<float>(step[t])));
+        at.wd[t] = weight_decay[t];
+    }
+    int grid = (tot + 255) / 256;
+    if (grid > 4 * num_sms()) grid = 4 * num_sms();
+    ProfScope ps(14, stream);
+    adam_trials_kernel<<<grid, 256, 0, stream>>>(at, n_trials * 10, tot, beta1, beta2, eps);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1336,6 +1528,22 @@ int hb_clam_sb_backward(const float* feats, int n_instances, const void* const* 
                         void* stream) {
     return hb::clam_backward_launch(feats, n_instances, weights_host, a_raw, m_pooled, dlogits, dm_ext, da_ext, grads_host,
                                     L0, L1, D, C, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+size_t hb_clam_trials_workspace_bytes(int max_bag_len, int n_trials, int L1) {
+    return ((hb::clam_workspace_bytes(max_bag_len, n_trials, n_trials, L1) + 15) & ~static_cast<size_t>(15)) +
+           static_cast<size_t>(n_trials) * (4 + L1) * sizeof(float);
+}
+int hb_clam_sb_train_step_trials(const float* feats, const int32_t* bag_offsets, const int32_t* bag_offsets_host, int n_trials,
+                                 const void* const* weights_host, void* const* grads_host, void* const* exp_avg_host,
+                                 void* const* exp_avg_sq_host, const int64_t* labels, const float* lr, const float* weight_decay,
+                                 const int* step, float beta1, float beta2, float eps, float dropout_p,
+                                 const uint64_t* dropout_seeds, float* a_raw, float* m_pooled, float* logits, float* loss, int L0,
+                                 int L1, int D, int C, void* workspace, size_t workspace_bytes, void* stream) {
+    return hb::clam_train_trials_launch(feats, bag_offsets, bag_offsets_host, n_trials, weights_host, grads_host, exp_avg_host,
+                                        exp_avg_sq_host, reinterpret_cast<const long long*>(labels), lr, weight_decay, step, beta1,
+                                        beta2, eps, dropout_p, reinterpret_cast<const unsigned long long*>(dropout_seeds), a_raw,
+                                        m_pooled, logits, loss, L0, L1, D, C, workspace, workspace_bytes,
+                                        static_cast<cudaStream_t>(stream));
 }
 int hb_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                  const int* numel, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay, int step,

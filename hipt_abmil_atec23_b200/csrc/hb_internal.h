@@ -92,7 +92,8 @@ int cls_rows_launch(const float* cls_token, const float* pos_table, float* x, vo
 int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_bags, int total_instances,
                         int max_bag_len, const void* const* weights_host, int n_models, int L0, int L1, int D, int C,
                         float* a_raw, float* m_out, float* logits, float* y_prob, long long* y_hat, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream, float dropout_p = 0.f, unsigned long long dropout_seed = 0);
+                        size_t workspace_bytes, cudaStream_t stream, float dropout_p = 0.f, unsigned long long dropout_seed = 0,
+                        const unsigned long long* paired_seeds = nullptr);
 size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1);
 
 }  // namespace hb

@@ -250,6 +250,26 @@ int hb_clam_sb_backward_train(const float* feats, int n_instances, const void* c
 int hb_clam_dropout_masks(int n_instances, int L1, int D, float dropout_p, uint64_t dropout_seed, float* m1_host,
                           float* ma_host, float* mb_host);
 
+/* Multi-trial training step.  The reference's hyper-parameter search packs several Ray Tune
+ * trials on one GPU as separate processes (main.py:40-52), each running train_loop (utils/core_utils.py:384-426) one bag at a
+ * time: hundreds of configurations x 5 folds x 3 repeats of a 3.5 k-parameter model, every step pure launch latency.  Here up
+ * to 8 independent trials of one head size advance ONE step each — trial t: its own 10 weight tensors, Adam state, bag,
+ * label, dropout seed, learning rate, weight decay and step count — in six launches in total: paired forward (work table,
+ * scores, combine), cross-entropy + backward (one prep CTA per trial, a (chunk, trial) grid of the recomputing backward),
+ * one Adam launch over all 10 * n_trials tensors.  Same arithmetic as hb_clam_sb_forward_train + hb_clam_sb_backward_train
+ * (logits + label mode) + hb_adam_step per trial.
+ * feats: the trials' bags concatenated [total, 192]; bag_offsets (device) / bag_offsets_host: int32 [n_trials + 1];
+ * weights_host / grads_host / exp_avg_host / exp_avg_sq_host: host arrays of 10 * n_trials device pointers, trial-major,
+ * tensor order of hb_clam_sb_forward; labels: device int64 [n_trials]; lr / weight_decay / step / dropout_seeds: host arrays
+ * [n_trials]; outputs a_raw [total], m_pooled [n_trials, L1], logits [n_trials, C], loss [n_trials] (device). */
+size_t hb_clam_trials_workspace_bytes(int max_bag_len, int n_trials, int L1);
+int hb_clam_sb_train_step_trials(const float* feats, const int32_t* bag_offsets, const int32_t* bag_offsets_host, int n_trials,
+                                 const void* const* weights_host, void* const* grads_host, void* const* exp_avg_host,
+                                 void* const* exp_avg_sq_host, const int64_t* labels, const float* lr, const float* weight_decay,
+                                 const int* step, float beta1, float beta2, float eps, float dropout_p,
+                                 const uint64_t* dropout_seeds, float* a_raw, float* m_pooled, float* logits, float* loss, int L0,
+                                 int L1, int D, int C, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Multi-tensor Adam with L2 weight decay in one launch, torch.optim.Adam semantics (utils/utils.py:100-107 get_optim:
  * optim.Adam(..., lr, weight_decay=reg)): g += wd p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
  * p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps).  Up to 16 fp32 tensors; step counts from 1. */

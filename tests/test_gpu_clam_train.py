@@ -141,3 +141,54 @@ def test_fused_adam_keeps_one_step_count_per_parameter():
     for a, b in zip(p_ref, p_our):
         assert (a.detach() - b.detach().cpu()).abs().max().item() < 1e-6
     assert [int(our.state[p]["step"]) for p in p_our] == [6, 3, 3]
+
+
+@pytest.mark.parametrize("size_arg,n_classes,dropout", [("hipt_smaller", 2, 0.0), ("hipt_smaller", 2, 0.85), ("hipt_small", 5, 0.25),
+                                                       ("hipt_big", 2, 0.5)])
+def test_multi_trial_step_equals_independent_train_steps(size_arg, n_classes, dropout):
+    """f3: five trials (own weights, bags of 50..3000 instances, labels, learning rates, weight decays, dropout seeds) advanced
+    three steps by TrialBatchStep — six launches per step for all of them — against five independent TrainStep + FusedAdam
+    runs (the per-trial path already pinned to the reference module above).  Same kernels' arithmetic; the backward's
+    per-chunk gradient sums meet in atomics, so parameters agree to rounding (1e-5 relative), losses to 1e-5."""
+    T, steps = 5, 3
+    lrs = [2e-4, 1e-3, 5e-4, 2e-3, 1e-4]
+    wds = [1e-5, 0.0, 1e-4, 1e-3, 1e-2]
+    g = torch.Generator().manual_seed(123)
+    lens = [[int(x) for x in torch.randint(50, 3000, (T,), generator=g)] for _ in range(steps)]
+    bags = [[torch.randn((n, 192), generator=g).to(DEV) for n in ls] for ls in lens]
+    labels = [torch.randint(0, n_classes, (T,), generator=g).to(DEV) for _ in range(steps)]
+
+    def make():
+        ms = []
+        for t in range(T):
+            torch.manual_seed(900 + t)
+            ms.append(CLAM_SB(size_arg=size_arg, dropout=dropout, n_classes=n_classes).to(DEV).train())
+        return ms
+    ref_models = make()
+    ref_losses = []
+    singles = [clam_engine.TrainStep(m, clam_engine.FusedAdam(m.parameters(), lr=lrs[t], weight_decay=wds[t]), 3000, seed=40 + t)
+               for t, m in enumerate(ref_models)]
+    for s in range(steps):
+        ref_losses.append([float(singles[t].step(bags[s][t], labels[s][t:t + 1])) for t in range(T)])
+    models = make()
+    batch = clam_engine.TrialBatchStep(models, lr=lrs, weight_decay=wds, max_instances=3000, seeds=[40 + t for t in range(T)])
+    for s in range(steps):
+        n0 = _lib.launch_count()
+        loss = batch.step(bags[s], labels[s])
+        assert _lib.launch_count() - n0 == 6
+        got = loss.cpu().tolist()
+        for t in range(T):
+            assert abs(got[t] - ref_losses[s][t]) <= 1e-5 * max(1.0, abs(ref_losses[s][t])), (s, t, got[t], ref_losses[s][t])
+    for t in range(T):
+        for (name, p), q in zip(models[t].named_parameters(), ref_models[t].parameters()):
+            if not p.requires_grad:
+                continue
+            err = (p - q).abs().max().item()
+            if name.endswith("attention_c.bias"):
+                # dL/d(bc) = sum_i dA_i is zero analytically (softmax is shift-invariant): its computed value is rounding
+                # noise of the atomics' order, and Adam turns noise into steps of +-lr — in the reference as well
+                assert err <= 2 * steps * lrs[t] + 1e-7, (t, name, err)
+                continue
+            assert err <= 1e-5 * max(1.0, q.abs().max().item()), (t, name, err)
+    # the trials really diverged from their common initialisation pattern (different data, lr, seeds)
+    assert not torch.equal(models[0].classifiers.weight, models[1].classifiers.weight)
