@@ -28,6 +28,8 @@
 //                 of query 256 made this warpgroup, not the softmax, set the item period)
 // Four units are resident (4 x 128 = all 512 TMEM columns).  Softmax statistics stay fp32; P is rounded to bf16 relative to
 // its half's maximum.
+#include <stdlib.h>
+
 #include "hb_ptx.cuh"
 #include "hb_internal.h"
 
@@ -146,7 +148,7 @@ __device__ __forceinline__ void at2_softmax_unit(uint32_t t_unit, float extra, f
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map16,
                      const __grid_constant__ CUtensorMap map_out, __nv_bfloat16* __restrict__ out, int n_items, int heads,
-                     float scale_log2) {
+                     float scale_log2, int reverse) {
     extern __shared__ uint8_t smem_raw_at2[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at2) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;                                   // [2 stages][34816]
@@ -203,7 +205,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
         setmaxnreg_dec<56>();
         if (lane == 0) {
             for (int it = 0; it < my_items; ++it) {
-                const int item = blockIdx.x + it * gridDim.x;
+                const int item = reverse ? n_items - 1 - (blockIdx.x + it * gridDim.x) : blockIdx.x + it * gridDim.x;
                 const int seq = item / heads, h = item - seq * heads;
                 const int row0 = seq * AT2_S;
                 const int st = it & 1;
@@ -356,7 +358,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
             sts_f4(my_stats, make_float4(m_a, l_a, m_b, l_b));
             sts_f1(my_stats + 16, p256);
 #ifdef HB_EXP_AT2_DEBUG
-            { const int item = blockIdx.x + it * gridDim.x; if (item < 1536) { float* d = g_at2_dbg + (static_cast<size_t>(item) * 256 + w * 128 + r) * 4; d[0] = s256; d[1] = p256; d[3] = dbg_q0; } }
+            { const int item = reverse ? n_items - 1 - (blockIdx.x + it * gridDim.x) : blockIdx.x + it * gridDim.x; if (item < 1536) { float* d = g_at2_dbg + (static_cast<size_t>(item) * 256 + w * 128 + r) * 4; d[0] = s256; d[1] = p256; d[3] = dbg_q0; } }
 #endif
             mbar_arrive(&st_full[w]);
             AT2_TRACE(w, it, 6);
@@ -369,7 +371,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
         uint8_t* my_out = sOut + quad * 8192;                 // this warp's two staging buffers (tile 0 / tile 1)
         for (int it = 0; it < my_items; ++it) {
-            const int item = blockIdx.x + it * gridDim.x;
+            const int item = reverse ? n_items - 1 - (blockIdx.x + it * gridDim.x) : blockIdx.x + it * gridDim.x;
             const int seq = item / heads, h = item - seq * heads;
             const int st = it & 1;
             mbar_wait(&kv_full[st], (it >> 1) & 1);           // acquire the TMA writes of K and V
@@ -538,8 +540,13 @@ int attention_tc2_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int he
     if (set_max_dynamic_smem(reinterpret_cast<const void*>(attention_tc2_kernel), AT2_SMEM)) return -1;
     const int n_items = n_seq * heads;
     const int grid = n_items < num_sms() ? n_items : num_sms();
+    // Items are walked from the LAST sequence down: the qkv GEMM before this kernel wrote its tiles in ascending row order, so the
+    // rows it wrote last are the ones still in L2, and the proj GEMM after it reads `out` in ascending order — starting with
+    // the rows this kernel writes last (HB_ATT_REVERSE=0 restores the ascending walk for comparison).
+    static int rev = -1;
+    if (rev < 0) { const char* e = getenv("HB_ATT_REVERSE"); rev = (e && e[0] == '0') ? 0 : 1; }
     attention_tc2_kernel<<<grid, AT2_THREADS, AT2_SMEM, stream>>>(map128, map16, map_out, static_cast<__nv_bfloat16*>(out_bf16),
-                                                                  n_items, heads, scale * 1.4426950408889634f);
+                                                                  n_items, heads, scale * 1.4426950408889634f, rev);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;

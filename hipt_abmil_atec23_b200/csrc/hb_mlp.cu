@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_out,
                  const float* __restrict__ c1, const float* __restrict__ d1, const float* __restrict__ b2,
-                 const float* __restrict__ stats_in, float* __restrict__ stats_out, int stats_stride, float eps, int M) {
+                 const float* __restrict__ stats_in, float* __restrict__ stats_out, int stats_stride, float eps, int M,
+                 int reverse) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;
@@ -141,7 +142,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 else mbar_arrive_remote(&w2_full[s], 0);
             };
             for (int tile = pair; tile < n_tiles; tile += n_pairs, ++ti) {
-                const int m0 = tile * 256 + cta_rank * 128;
+                const int m0 = (reverse ? n_tiles - 1 - tile : tile) * 256 + cta_rank * 128;
                 mbar_wait(a_empty, (ti & 1) ^ 1);
 #pragma unroll
                 for (int kb = 0; kb < MLP_KB; ++kb) tma_load_2d_2sm(sA + kb * 16384, &map_a, a_full, kb * 64, m0);
@@ -247,7 +248,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
         uint32_t n = 0, ti = 0, my_chunks = 0;
         for (int tile = pair; tile < n_tiles; tile += n_pairs, ++ti) {
-            const int m0 = tile * 256 + cta_rank * 128;
+            const int m0 = (reverse ? n_tiles - 1 - tile : tile) * 256 + cta_rank * 128;
             const int row = m0 + row_in_tile;
             // LayerNorm factors of this thread's row from the partial sums the producer of xb left behind
             float rstd, nrm;
@@ -416,8 +417,13 @@ int mlp_fused_launch(const void* xb_bf16, const void* w1g_bf16, const float* c1,
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // Tiles are walked from the LAST one down: the proj GEMM before this kernel wrote the residual stream in ascending row order
+    // (its last rows are the ones still in L2), and the next qkv GEMM reads it in ascending order, starting with the rows this
+    // kernel writes last (HB_MLP_REVERSE=0: ascending, for comparison).
+    static int rev = -1;
+    if (rev < 0) { const char* e = getenv("HB_MLP_REVERSE"); rev = (e && e[0] == '0') ? 0 : 1; }
     HB_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, map_a, map_w1, map_w2, map_out, c1, d1, b2, stats_in, stats_out,
-                                  stats_stride, eps, M));
+                                  stats_stride, eps, M, rev));
     count_launch();
     return 0;
 }

@@ -18,7 +18,11 @@ _lock = threading.Lock()
 import os
 
 # default capacities (token sequences per launch)
-VIT256_MAX_PATCHES = int(os.environ.get("HB_VIT256_MAX_PATCHES", "512"))   # 512 = two 4096x4096 regions per launch (514 CTA-pair tiles over 74 SM pairs)
+# Sequences (256 x 256 patches) per ViT-256 launch sequence.  1024 = four 4096x4096 regions = 1,028 CTA-pair tiles = 13.9 waves
+# over the 74 SM pairs (99 % full) and a 1.84 GB workspace.  Measured on one box, 16 regions, serpentine tile order
+# (tools/exp_group_size.py, profiles/r02d_group_size.jsonl): 221 -> 274.5, 294 -> 278.0, 512 -> 285.0, 1024 -> 290.8,
+# 2048 -> 292.9, 4096 -> 293.8 regions/s: fewer launch tails beat the smaller L2 footprint of short groups.
+VIT256_MAX_PATCHES = int(os.environ.get("HB_VIT256_MAX_PATCHES", "1024"))
 VIT4K_MAX_REGIONS = 64
 
 

@@ -9,6 +9,9 @@ The glue that cannot be imported from the reference is restated here and cites i
   * per-slide pooling with every fold  eval.py -> utils/eval_utils.py:62-100 (model(data) per slide, per fold)
 """
 import contextlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 
@@ -20,19 +23,38 @@ _cache = {}
 
 
 def available():
-    return os.path.exists(os.path.join(_REF, "HIPT_4K", "vision_transformer.pyc"))
+    return os.path.exists(os.path.join(_REF, "HIPT_4K", "vision_transformer.refbin"))
+
+
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Imports the reference's byte-compiled modules from oracle/_ref/<package>/<module>.refbin (the bytes of a sourceless
+    .pyc under an extension the GPU-box snapshot keeps); directories are packages."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] not in _TOP:
+            return None
+        rel = os.path.join(_REF, *fullname.split("."))
+        if os.path.isfile(rel + ".refbin"):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, rel + ".refbin")
+            return importlib.util.spec_from_file_location(fullname, rel + ".refbin", loader=loader)
+        if os.path.isdir(rel):
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        return None
 
 
 @contextlib.contextmanager
 def _isolated_imports():
     """The reference's top-level package names (HIPT_4K, models, utils) are also the names of this repository's import
-    shims: import the reference under a private sys.path / sys.modules view and restore the caller's afterwards."""
+    shims: import the reference under a private finder / sys.modules view and restore the caller's afterwards."""
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in _TOP}
-    sys.path.insert(0, _REF)
+    finder = _RefFinder()
+    sys.meta_path.insert(0, finder)
     try:
         yield
     finally:
-        sys.path.remove(_REF)
+        sys.meta_path.remove(finder)
         for k in [k for k in sys.modules if k.split(".")[0] in _TOP]:
             del sys.modules[k]
         sys.modules.update(saved)
