@@ -680,6 +680,109 @@ static int attention_tc_launch(const void* qkv_bf16, void* out_bf16, int n_seq, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CLS-only attention of the last block for head_dim 64 (forward() returns x[:, 0], vision_transformer.py:252-253): one WARP per
+// (sequence, head), no shared memory, no mma.sync.  Lane = key for both products: a lane reads whole 128-byte K / V rows (every
+// byte of K and V of the launch is read exactly once: the kernel is HBM-bound), scores and softmax live in registers, the 64
+// partial outputs per lane are summed across the warp by recursive halving, which leaves dimensions (2 l, 2 l + 1) on lane l.
+// The generic mma.sync kernel ran this row on ONE warp of a 128-thread CTA, 17 HMMA chunks in series (264 us per 1,024 sequences
+// under ncu against 62 us of HBM time; legacy HMMA issues once per 50-75 cycles on this part).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attention_cls64_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                              int n_items, int seq_len, int heads, float scale_log2,
+                                                              float* __restrict__ cls_probs) {
+    const int item = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n_items) return;
+    const int seq = item / heads, h = item - seq * heads;
+    const int D = heads * 64;
+    const size_t row_stride = static_cast<size_t>(3) * D;     // elements between consecutive tokens
+    const __nv_bfloat16* base = qkv + static_cast<size_t>(seq) * seq_len * row_stride + h * 64;
+    constexpr int MAXJ = 9;                                    // keys per lane: seq_len <= 288
+    float s[MAXJ];
+    {
+        f32x2_t q2[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                          // query row 0: the same 128 bytes for every lane
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base) + c);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q2[4 * c + e] = f2_pack(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+        }
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            const int k = lane + 32 * j;
+            s[j] = -INFINITY;
+            if (k < seq_len) {
+                const uint4* krow = reinterpret_cast<const uint4*>(base + static_cast<size_t>(k) * row_stride + D);
+                f32x2_t a0 = f2_pack(0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 v = __ldg(krow + c);
+                    a0 = f2_fma(q2[4 * c + 0], f2_pack(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u)), a0);
+                    a1 = f2_fma(q2[4 * c + 1], f2_pack(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u)), a1);
+                    a0 = f2_fma(q2[4 * c + 2], f2_pack(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u)), a0);
+                    a1 = f2_fma(q2[4 * c + 3], f2_pack(__uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u)), a1);
+                }
+                float x0, x1;
+                f2_unpack(f2_add(a0, a1), x0, x1);
+                s[j] = (x0 + x1) * scale_log2;
+            }
+        }
+    }
+    float m = s[0];
+#pragma unroll
+    for (int j = 1; j < MAXJ; ++j) m = fmaxf(m, s[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) { s[j] = exp2f(s[j] - m); l += s[j]; }     // exp2(-inf) = 0 for the keys past the end
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.0f / l;
+    if (cls_probs != nullptr) {
+        float* prow = cls_probs + static_cast<size_t>(item) * seq_len;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) { const int k = lane + 32 * j; if (k < seq_len) prow[k] = s[j] * inv; }
+    }
+    f32x2_t o2[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) o2[e] = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+        const int k = lane + 32 * j;
+        if (k < seq_len) {
+            const uint4* vrow = reinterpret_cast<const uint4*>(base + static_cast<size_t>(k) * row_stride + 2 * D);
+            const f32x2_t p2 = f2_pack(s[j], s[j]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = __ldg(vrow + c);
+                o2[4 * c + 0] = f2_fma(p2, f2_pack(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u)), o2[4 * c + 0]);
+                o2[4 * c + 1] = f2_fma(p2, f2_pack(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u)), o2[4 * c + 1]);
+                o2[4 * c + 2] = f2_fma(p2, f2_pack(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u)), o2[4 * c + 2]);
+                o2[4 * c + 3] = f2_fma(p2, f2_pack(__uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u)), o2[4 * c + 3]);
+            }
+        }
+    }
+    // sum over the 32 lanes: a lane hands over the half of its elements its partner keeps; element e survives on lane e
+#pragma unroll
+    for (int half = 16, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = lane & bit;
+#pragma unroll
+        for (int e = 0; e < half; ++e) {
+            const f32x2_t keep = up ? o2[e + half] : o2[e], send = up ? o2[e] : o2[e + half];
+            float s0, s1;
+            f2_unpack(send, s0, s1);
+            s0 = __shfl_xor_sync(0xffffffffu, s0, bit);
+            s1 = __shfl_xor_sync(0xffffffffu, s1, bit);
+            o2[e] = f2_add(keep, f2_pack(s0, s1));
+        }
+    }
+    float x0, x1;
+    f2_unpack(o2[0], x0, x1);
+    reinterpret_cast<uint32_t*>(out + static_cast<size_t>(seq) * D + h * 64)[lane] = pack_bf16x2(x0 * inv, x1 * inv);
+}
+
 static bool attention_force_v1() {          // comparison hook: HB_ATTENTION_V1=1 selects the round-1 tcgen05 kernel
     static int v = -1;
     if (v < 0) { const char* e = getenv("HB_ATTENTION_V1"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -694,6 +797,15 @@ int attention_launch(const void* qkv_bf16, void* out_bf16, int n_seq, int seq_le
     if (seq_len == ATC_S && head_dim == 64 && !attention_force_legacy() && !cls_only)
         return attention_force_v1() ? attention_tc_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream)
                                     : attention_tc2_launch(qkv_bf16, out_bf16, n_seq, heads, scale, stream);
+    if (cls_only && head_dim == 64 && seq_len <= 288 && !attention_force_legacy()) {
+        const int n_items = n_seq * heads;
+        attention_cls64_kernel<<<(n_items + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
+                                                                      static_cast<__nv_bfloat16*>(out_bf16), n_items, seq_len, heads,
+                                                                      scale * 1.4426950408889634f, cls_probs);
+        count_launch();
+        HB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const int s_pad = (seq_len + 15) & ~15;
     const size_t smem = static_cast<size_t>(3) * s_pad * head_dim * 2;
     if (smem > 200 * 1024) return set_error("hb_attention: seq_len %d too long for the single-pass kernel", seq_len);
