@@ -495,18 +495,26 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 //
 // kind::tf32 reads fp32 words and ignores the low 13 mantissa bits, i.e. it multiplies hi(x) = x & 0xFFFFE000.  With
 // lo(x) = x - hi(x) (exact in fp32):   x w = hi(x) hi(w) + hi(x) lo(w) + lo(x) hi(w) + O(2^-21 |x w|)
-//   term 1: A = X tile as loaded by TMA,           B = W1        (the hardware truncates both)
-//   term 2: A = the same X tile,                   B = lo(W1)    (precomputed per launch in shared memory)
-//   term 3: A = lo(X) tile (written by 4 warps),   B = W1
+//   terms 1 + 2: A = X tile as loaded by TMA,      B = [W1 ; lo(W1)] stacked along N (the hardware truncates both operands;
+//                                                  lo(W1) is precomputed per launch): ONE pass over A, two accumulator halves
+//                                                  that the epilogue adds — shared-memory bandwidth (TMA writes, operand reads,
+//                                                  LDS) is the busiest unit of this kernel, and A is 3/4 of the operand bytes
+//   term 3:      A = lo(X) (tensor memory),        B = W1, accumulated onto the first half
 // All folds' W1 are stacked along N (N = n_models * L1), so the 98 KB feature tile is read from HBM once AND multiplied once
 // for the whole ensemble.  Persistent CTAs walk the (bag, 128-instance chunk) work table.
-//   warp 0     TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a 2/3-stage ring
+//   warp 0     TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a ring of up to 12 stages
 //   warp 1     MMA issuer (12 MMAs M128 x N x K8 per slice), double-buffered TMEM accumulator
-//   warps 2-9  lo(X): two threads per row (four 16-byte pieces each), swizzled pieces in, same positions out
+//   warps 2-9  lo(X): two threads per row (four 16-byte pieces each) read the slice from shared memory and write lo(x) into
+//              TENSOR memory (tcgen05.st, 32 columns per stage, lane = row): term 3 is an A-from-TMEM MMA.  With lo(X) in
+//              shared memory the ring held 6 x 16 KB of features; at the ~3.7 us HBM latency of this access pattern that is
+//              exactly the 26 GB/s per SM the round-1 kernel ran at (Little's law), so the ring depth, not the pipes, bounded it.
 //   warps 10-13, 14-17  two epilogue warpgroups (even / odd tiles = TMEM buffer 0 / 1): thread = row; per fold: TMEM -> +b1,
 //              ReLU -> gate -> score -> chunk softmax partials
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 576, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 6;
+constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 576, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
+// TMEM: two accumulators of acc_stride columns (2 ntot — the X W1 and X lo(W1) halves — rounded up to 32), then 32 columns of
+// lo(X) per ring stage
+__host__ __device__ inline int clam_tc_acc_stride(int ntot) { return (2 * ntot + 31) & ~31; }
 __host__ __device__ inline bool clam_tc_ok(int L0, int L1, int D, int n_models) {
     return L0 == 192 && (L1 == 16 || L1 == 32) && D * 2 == L1 && n_models * L1 <= 80;
 }
@@ -514,12 +522,14 @@ __host__ __device__ inline bool clam_tc_ok(int L0, int L1, int D, int n_models) 
 __host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int D) {
     const int ntot = n_models * L1;
     return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 +
-           (static_cast<size_t>(n_models) * ((((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3)) + 2 * (8 + 128)) * sizeof(float) + 40 * 8;
+           (static_cast<size_t>(n_models) * ((((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3)) + 2 * (8 + 128)) * sizeof(float) + 48 * 8;
 }
 // as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
 __host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
     const long long room = 232448LL - static_cast<long long>(clam_tc_fixed_bytes(n_models, L1, D));
-    int st = static_cast<int>(room / (2 * TC_SLICE_BYTES));
+    int st = static_cast<int>(room / TC_SLICE_BYTES);
+    const int tmem_st = (512 - 2 * clam_tc_acc_stride(n_models * L1)) / 32;
+    if (st > tmem_st) st = tmem_st;
     return st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
 }
 // floats of per-fold epilogue constants: b1 [L1] | Wa [D][L1] | Wb [D][L1] | ba [D] | bb [D] | Wc [D] | bc
@@ -536,20 +546,20 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
     const int ntot = n_models * L1;
     const int stages = clam_tc_stages(n_models, L1, D);
-    uint8_t* sXr = smem;                                        // [stages][X 16 KB | lo(X) 16 KB]
-    uint8_t* sWh = sXr + stages * 2 * TC_SLICE_BYTES;           // [6 slices][ntot rows][128 B]  W1 (all folds stacked)
-    uint8_t* sWl = sWh + TC_NSL * ntot * 128;                   // same, lo(W1)
-    float* sC = reinterpret_cast<float*>(sWl + TC_NSL * ntot * 128);          // [n_models][fold constants]
+    uint8_t* sXr = smem;                                        // [stages][X 16 KB]
+    uint8_t* sWh = sXr + stages * TC_SLICE_BYTES;               // [6 slices][2 ntot rows][128 B]: W1 of all folds, then lo(W1)
+    uint8_t* sWl = sWh + ntot * 128;                            // the lo rows of slice 0 (slice stride 2 ntot rows)
+    float* sC = reinterpret_cast<float*>(sWh + 2 * TC_NSL * ntot * 128);      // [n_models][fold constants]
     const int fold_floats = clam_tc_fold_floats(L1, D);
     constexpr int SCR = 8 + 128;                                // per epilogue warpgroup: [8] reductions | [4 warps][L1] column partials
     float* sScr = sC + n_models * fold_floats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + 2 * SCR);
-    uint64_t* x_full = bars;              // [6]
-    uint64_t* x_empty = bars + 6;         // [6]  MMA commit
-    uint64_t* lo_full = bars + 12;        // [6]  256 split threads
-    uint64_t* acc_full = bars + 18;       // [2]
-    uint64_t* acc_empty = bars + 20;      // [2]  128 epilogue threads
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* x_full = bars;              // [12]
+    uint64_t* x_empty = bars + 12;        // [12]  MMA commit
+    uint64_t* lo_full = bars + 24;        // [12]  256 split threads
+    uint64_t* acc_full = bars + 36;       // [2]
+    uint64_t* acc_empty = bars + 38;      // [2]  128 epilogue threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_x);
@@ -558,7 +568,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_mbar_init();
     }
-    const uint32_t tmem_cols = (2 * ntot <= 32) ? 32 : (2 * ntot <= 64) ? 64 : (2 * ntot <= 128) ? 128 : 256;
+    const uint32_t tmem_cols = 512;                             // accumulators + the lo(X) ring; one CTA per SM
     if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
     // W1 (every fold) -> shared memory in the K-major SWIZZLE_128B layout of the B operand, hi as is, lo = w - trunc(w);
     // fold constants behind it
@@ -567,7 +577,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         const int m = n / L1, j = n - m * L1;
         const float w = __ldg(models.m[m].p[0] + j * 192 + k);
         const int sl = k >> 5, kk = k & 31;
-        const uint32_t off = sl * ntot * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+        const uint32_t off = sl * 2 * ntot * 128 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
         *reinterpret_cast<float*>(sWh + off) = w;
         *reinterpret_cast<float*>(sWl + off) = w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     }
@@ -588,7 +598,8 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_work = prefix[n_bags];
-    const uint32_t acc_stride = tmem_cols / 2;
+    const uint32_t acc_stride = clam_tc_acc_stride(ntot);
+    const uint32_t t_lo = tmem_base + 2 * acc_stride;           // [stages][32 columns]: lo(X) of the slice in ring stage st
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA producer
@@ -601,13 +612,14 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
                     const uint32_t st = q % stages, use = q / stages;
                     mbar_wait(&x_empty[st], (use & 1) ^ 1);
                     mbar_arrive_expect_tx(&x_full[st], TC_SLICE_BYTES);
-                    tma_load_2d(sXr + st * 2 * TC_SLICE_BYTES, &map_x, &x_full[st], sl * TC_KS, row0);
+                    tma_load_2d(sXr + st * TC_SLICE_BYTES, &map_x, &x_full[st], sl * TC_KS, row0);
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = umma_idesc_tf32(TC_M, ntot);
+        const uint32_t idesc = umma_idesc_tf32(TC_M, ntot);             // lo(X) x W1
+        const uint32_t idesc2 = umma_idesc_tf32(TC_M, 2 * ntot);        // X x [W1 ; lo(W1)]
         uint32_t q = 0, t = 0;
         for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x, ++t) {
             const uint32_t b = t & 1;
@@ -616,17 +628,14 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
             const uint32_t d_tmem = tmem_base + b * acc_stride;
             for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
                 const uint32_t st = q % stages, use = q / stages;
-                const uint64_t dx = umma_desc_k128(smem_u32(sXr + st * 2 * TC_SLICE_BYTES));
-                const uint64_t dl = umma_desc_k128(smem_u32(sXr + st * 2 * TC_SLICE_BYTES + TC_SLICE_BYTES));
-                const uint64_t dwh = umma_desc_k128(smem_u32(sWh + sl * ntot * 128));
-                const uint64_t dwl = umma_desc_k128(smem_u32(sWl + sl * ntot * 128));
+                const uint64_t dx = umma_desc_k128(smem_u32(sXr + st * TC_SLICE_BYTES));
+                const uint64_t dwh = umma_desc_k128(smem_u32(sWh + sl * 2 * ntot * 128));
                 mbar_wait(&x_full[st], use & 1);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        umma_tf32_ss(d_tmem, dx + 2 * kk, dwh + 2 * kk, idesc, (sl | kk) != 0);
-                        umma_tf32_ss(d_tmem, dx + 2 * kk, dwl + 2 * kk, idesc, 1);
+                        umma_tf32_ss(d_tmem, dx + 2 * kk, dwh + 2 * kk, idesc2, (sl | kk) != 0);
                     }
                 }
                 __syncwarp();
@@ -634,7 +643,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_tf32_ss(d_tmem, dl + 2 * kk, dwh + 2 * kk, idesc, 1);
+                    for (int kk = 0; kk < 4; ++kk) umma_tf32_ts(d_tmem, t_lo + st * 32 + 8 * kk, dwh + 2 * kk, idesc, 1);
                     umma_commit(&x_empty[st]);
                     if (sl == TC_NSL - 1) umma_commit(&acc_full[b]);
                 }
@@ -643,26 +652,27 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         }
     } else if (warp < 10) {
         // ------------------------------------------------------------------------------------------ lo(X)
-        const int r = ((warp - 2) & 3) * 32 + lane, half = (warp - 2) >> 2;
+        const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;          // TMEM lane quadrant = warp % 4
+        const uint32_t t_my = t_lo + (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * 16;
         uint32_t q = 0;
         for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
             for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
                 const uint32_t st = q % stages, use = q / stages;
-                const uint32_t xs = smem_u32(sXr + st * 2 * TC_SLICE_BYTES) + r * 128, ls = xs + TC_SLICE_BYTES;
+                const uint32_t xs = smem_u32(sXr + st * TC_SLICE_BYTES) + r * 128;
                 mbar_wait(&x_full[st], use & 1);
+                uint32_t lo[16];
 #pragma unroll
-                for (int c0 = half * 4; c0 < half * 4 + 4; ++c0) {
-                    const int c = c0 ^ (r & 7);                  // lo() is element-wise, so any piece order works: this one
-                                                                 // keeps the 8 rows of a quarter-warp on 8 different pieces
-                    const uint4 v = lds_u4(xs + c * 16);
-                    uint4 o;
-                    o.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
-                    o.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
-                    o.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
-                    o.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
-                    sts_u4(ls + c * 16, o);
+                for (int i = 0; i < 4; ++i) {
+                    const int c = half * 4 + i;                  // 16-byte piece c = K elements 4 c .. 4 c + 3 of the slice
+                    const uint4 v = lds_u4(xs + ((c ^ (r & 7)) << 4));
+                    lo[4 * i + 0] = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+                    lo[4 * i + 1] = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+                    lo[4 * i + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+                    lo[4 * i + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
                 }
-                fence_proxy_async_smem();
+                tmem_st_32x16(t_my + st * 32, lo);
+                tmem_st_wait();
+                tc_fence_before();
                 mbar_arrive(&lo_full[st]);
             }
         }
@@ -689,15 +699,21 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
                 float h[L1];
                 {
                     uint32_t v[L1];
-                    if constexpr (L1 == 16) tmem_ld_32x16(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[16]>(v));
-                    else tmem_ld_32x32(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[32]>(v));
+                    uint32_t v2[L1];                             // the X lo(W1) half of the accumulator
+                    if constexpr (L1 == 16) {
+                        tmem_ld_32x16(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[16]>(v));
+                        tmem_ld_32x16(t_lane + b * acc_stride + ntot + m * L1, *reinterpret_cast<uint32_t(*)[16]>(v2));
+                    } else {
+                        tmem_ld_32x32(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[32]>(v));
+                        tmem_ld_32x32(t_lane + b * acc_stride + ntot + m * L1, *reinterpret_cast<uint32_t(*)[32]>(v2));
+                    }
                     tmem_ld_wait();
                     if (m == n_models - 1) {                     // last TMEM read of the tile: hand the accumulator back
                         tc_fence_before();
                         mbar_arrive(&acc_empty[b]);
                     }
 #pragma unroll
-                    for (int j = 0; j < L1; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + c[j], 0.f);
+                    for (int j = 0; j < L1; ++j) h[j] = fmaxf((__uint_as_float(v[j]) + __uint_as_float(v2[j])) + c[j], 0.f);
                 }
                 const float* Wa = c + L1; const float* Wb = Wa + D * L1;
                 const float* ba = Wb + D * L1; const float* bb = ba + D; const float* Wc = bb + D;
@@ -907,7 +923,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         const int ntot = n_models * L1;
         const int stages = clam_tc_stages(n_models, L1, D);
         if (stages < 2) return set_error("hb_clam: tensor-core path does not fit shared memory (n_models %d, L1 %d)", n_models, L1);
-        const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * 2 * TC_SLICE_BYTES;
+        const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * TC_SLICE_BYTES;
         (void)ntot;
         auto kern = (L1 == 16) ? clam_scores_tc_kernel<16> : clam_scores_tc_kernel<32>;
         if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 232448)) return -1;
