@@ -490,88 +490,133 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Tensor-core scores kernel (192-d features, L1 = 16 or 32, n_models * L1 <= 80): the first Linear of EVERY fold in one
-// tcgen05 GEMM per 128-instance tile, at fp32-level accuracy by operand splitting.
+// Tensor-core scores kernel (192-d features, L1 = 16 / 32 / 64, n_models * L1 <= 80): the first Linear of EVERY fold in one
+// tcgen05 GEMM per 128-instance tile AND both gate Linears (a || b stacked along N) as a second, block-diagonal tcgen05 GEMM
+// whose A operand is h1 in tensor memory — at fp32-level accuracy by operand splitting.
 //
 // kind::tf32 reads fp32 words and ignores the low 13 mantissa bits, i.e. it multiplies hi(x) = x & 0xFFFFE000.  With
 // lo(x) = x - hi(x) (exact in fp32):   x w = hi(x) hi(w) + hi(x) lo(w) + lo(x) hi(w) + O(2^-21 |x w|)
+// First Linear (GEMM 1, per tile: six K-slices of 32 features):
 //   terms 1 + 2: A = X tile as loaded by TMA,      B = [W1 ; lo(W1)] stacked along N (the hardware truncates both operands;
 //                                                  lo(W1) is precomputed per launch): ONE pass over A, two accumulator halves
 //                                                  that the epilogue adds — shared-memory bandwidth (TMA writes, operand reads,
 //                                                  LDS) is the busiest unit of this kernel, and A is 3/4 of the operand bytes
 //   term 3:      A = lo(X) (tensor memory),        B = W1, accumulated onto the first half
+// Gate (GEMM 2, per tile and fold: K = L1, N = 2 D = L1):  the epilogue writes h1 = relu(acc + b1) over the first accumulator
+//   half and lo(h1) over the second (tcgen05.st, thread = row = lane), and the MMA warp issues
+//   G = h1 [Wa;Wb]^T + h1 lo([Wa;Wb])^T + lo(h1) [Wa;Wb]^T   into a ring of G slots (L1 columns each).
+//   Why: with thread = instance every gate weight is warp-uniform, and a uniform shared-memory load still costs one LSU
+//   wavefront per 4 bytes — ncu on the previous kernel (profiles/r02o_clam_tc_5fold_full.csv): 383 shared-load wavefronts per
+//   warp and fold, the LSU pipe at 72 % of its peak, 272 FFMA per instance and fold.  (The same constants read from the constant
+//   bank are slower still: tools/patches/README.md.)  On the tensor core the gate costs 3 L1 / 8 small MMAs per fold and the
+//   epilogue keeps only bias, exp / rcp, the score dot product and the pooling partials.
 // All folds' W1 are stacked along N (N = n_models * L1), so the 98 KB feature tile is read from HBM once AND multiplied once
 // for the whole ensemble.  Persistent CTAs walk the (bag, 128-instance chunk) work table.
-//   warp 0     TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a ring of up to 12 stages
-//   warp 1     MMA issuer (12 MMAs M128 x N x K8 per slice), double-buffered TMEM accumulator
-//   warps 2-9  lo(X): two threads per row (four 16-byte pieces each) read the slice from shared memory and write lo(x) into
-//              TENSOR memory (tcgen05.st, 32 columns per stage, lane = row): term 3 is an A-from-TMEM MMA.  With lo(X) in
-//              shared memory the ring held 6 x 16 KB of features; at the ~3.7 us HBM latency of this access pattern that is
-//              exactly the 26 GB/s per SM the round-1 kernel ran at (Little's law), so the ring depth, not the pipes, bounded it.
-//   warps 10-13, 14-17  two epilogue warpgroups (even / odd tiles = TMEM buffer 0 / 1): thread = row; per fold: TMEM -> +b1,
-//              ReLU -> gate -> score -> chunk softmax partials
+//   warp 0      TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a ring of up to 12 stages
+//   warp 1      MMA issuer: GEMM 1 of tile t, then the gate of tile t - 1 (its h1 was written while GEMM 1 of tile t ran).
+//               The tensor pipe executes in issue order, so GEMM 1 of tile t + 2 may overwrite the accumulator the gate of
+//               tile t read its A operand from without any further hand-shake.
+//   warps 2-3   idle (they only complete the first warpgroup, which gives its registers away)
+//   warps 4-11  lo(X): two threads per row read the slice from shared memory and write lo(x) into TENSOR memory (32 columns
+//               per stage of a second, shorter ring): term 3 is an A-from-TMEM MMA, so the shared-memory ring holds features
+//               only (Little's law: ring bytes / HBM latency is the bandwidth one SM can pull)
+//   warps 12-15, 16-19  two epilogue warpgroups (even / odd tiles = accumulator 0 / 1), thread = row.
+//               Phase A (all folds): TMEM -> +b1, ReLU -> h1 kept in registers for the pooling partials, h1 and lo(h1) -> TMEM.
+//               Phase B (per fold): G slot -> +bias, tanh * sigmoid, score, chunk softmax partials, sum_i e_i h1_i.
+// Registers: 640 threads launch with 96 each; setmaxnreg moves them to 48 (first warpgroup) / 56 (lo) / 160 (epilogue): 61,440 = what the CTA launched with.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 576, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
-// TMEM: two accumulators of acc_stride columns (2 ntot — the X W1 and X lo(W1) halves — rounded up to 32), then 32 columns of
-// lo(X) per ring stage
+constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 640, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
+constexpr int TC_MAX_GSLOTS = 8;
+// TMEM: two accumulators of acc_stride columns (2 ntot — the X W1 and X lo(W1) halves, later h1 and lo(h1) — rounded up to 32),
+// then g_slots gate accumulators of L1 columns, then 32 columns of lo(X) per stage of the lo ring
 __host__ __device__ inline int clam_tc_acc_stride(int ntot) { return (2 * ntot + 31) & ~31; }
-__host__ __device__ inline bool clam_tc_ok(int L0, int L1, int D, int n_models) {
-    return L0 == 192 && (L1 == 16 || L1 == 32) && D * 2 == L1 && n_models * L1 <= 80;
+// gate slots: one ring shared by both epilogue warpgroups, one more slot than a tile has folds (so the gate of tile t + 1 can be
+// issued while the last fold of tile t is still being read) if tensor memory has the room beside three lo(X) stages; at least
+// n_models (a slot is never reused inside a tile: its reader only starts when the whole tile's gate has been committed)
+__host__ __device__ inline int clam_tc_gslots(int n_models, int L1) {
+    const int room = (512 - 2 * clam_tc_acc_stride(n_models * L1) - 3 * 32) / L1;
+    return n_models + 1 < room ? n_models + 1 : room;
 }
-// shared memory besides the X ring: both W operands, fold constants, two epilogue scratch areas, barriers, alignment slack
+__host__ __device__ inline int clam_tc_lo_stages(int n_models, int L1) {
+    const int st = (512 - 2 * clam_tc_acc_stride(n_models * L1) - clam_tc_gslots(n_models, L1) * L1) / 32;
+    return st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+}
+__host__ __device__ inline bool clam_tc_ok(int L0, int L1, int D, int n_models) {
+    return L0 == 192 && (L1 == 16 || L1 == 32 || L1 == 64) && D * 2 == L1 && n_models * L1 <= 80;
+}
+// floats of per-fold epilogue constants: b1 [L1] | ba || bb [L1] | Wc [D] | bc
+__host__ __device__ inline int clam_tc_fold_floats(int L1, int D) { return ((2 * L1 + D + 1) + 3) & ~3; }
+// bytes of one fold's gate operand [Wa ; Wb] (K-major rows of 128 B, K padded to 32 per slice), hi and lo copies
+__host__ __device__ inline int clam_tc_gate_bytes(int L1) { return 2 * ((L1 + 31) / 32) * L1 * 128; }
+// bytes of everything except the X ring
 __host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int D) {
     const int ntot = n_models * L1;
-    return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 +
-           (static_cast<size_t>(n_models) * ((((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3)) + 2 * (8 + 128)) * sizeof(float) + 48 * 8;
+    return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 + static_cast<size_t>(n_models) * clam_tc_gate_bytes(L1) +
+           (static_cast<size_t>(n_models) * clam_tc_fold_floats(L1, D) + 2 * (8 + 4 * L1)) * sizeof(float) + 80 * 8;
 }
 // as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
 __host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
     const long long room = 232448LL - static_cast<long long>(clam_tc_fixed_bytes(n_models, L1, D));
-    int st = static_cast<int>(room / TC_SLICE_BYTES);
-    const int tmem_st = (512 - 2 * clam_tc_acc_stride(n_models * L1)) / 32;
-    if (st > tmem_st) st = tmem_st;
+    const int st = static_cast<int>(room / TC_SLICE_BYTES);
     return st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
 }
-// floats of per-fold epilogue constants: b1 [L1] | Wa [D][L1] | Wb [D][L1] | ba [D] | bb [D] | Wc [D] | bc
-__host__ __device__ inline int clam_tc_fold_floats(int L1, int D) { return ((L1 + 2 * D * L1 + 3 * D + 1) + 3) & ~3; }
 
-template <int L1>
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+    if constexpr (N == 16) tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(v));
+    else {
+#pragma unroll
+        for (int i = 0; i < N; i += 32) tmem_ld_32x32(taddr + i, *reinterpret_cast<uint32_t(*)[32]>(v + i));
+    }
+}
+
+template <int L1, int FMAX>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* __restrict__ bag_offsets,
                       const __grid_constant__ ClamModels models, int n_models, int n_bags, int total_instances,
                       const int32_t* __restrict__ prefix, const int32_t* __restrict__ work, int work_cap,
                       float* __restrict__ a_raw, float* __restrict__ partials) {
     constexpr int D = L1 / 2;
+    constexpr int GKS = (L1 + 31) / 32;                         // 128-byte K slices of the gate operand
+    constexpr int GSL = L1 * 128;                               // bytes of one such slice ([L1 rows][128 B])
     extern __shared__ uint8_t smem_raw_tc[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
     const int ntot = n_models * L1;
     const int stages = clam_tc_stages(n_models, L1, D);
+    const int lo_stages = clam_tc_lo_stages(n_models, L1);
+    const int g_slots = clam_tc_gslots(n_models, L1);
     uint8_t* sXr = smem;                                        // [stages][X 16 KB]
     uint8_t* sWh = sXr + stages * TC_SLICE_BYTES;               // [6 slices][2 ntot rows][128 B]: W1 of all folds, then lo(W1)
     uint8_t* sWl = sWh + ntot * 128;                            // the lo rows of slice 0 (slice stride 2 ntot rows)
-    float* sC = reinterpret_cast<float*>(sWh + 2 * TC_NSL * ntot * 128);      // [n_models][fold constants]
-    const int fold_floats = clam_tc_fold_floats(L1, D);
-    constexpr int SCR = 8 + 128;                                // per epilogue warpgroup: [8] reductions | [4 warps][L1] column partials
+    uint8_t* sG = sWh + 2 * TC_NSL * ntot * 128;                // [n_models][hi, lo][GKS][L1 rows][128 B]: [Wa ; Wb]
+    float* sC = reinterpret_cast<float*>(sG + n_models * clam_tc_gate_bytes(L1));   // [n_models][fold constants]
+    constexpr int fold_floats = ((2 * L1 + D + 1) + 3) & ~3;
+    constexpr int SCR = 8 + 4 * L1;                             // per epilogue warpgroup: [8] reductions | [4 warps][L1] column partials
     float* sScr = sC + n_models * fold_floats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + 2 * SCR);
     uint64_t* x_full = bars;              // [12]
     uint64_t* x_empty = bars + 12;        // [12]  MMA commit
     uint64_t* lo_full = bars + 24;        // [12]  256 split threads
-    uint64_t* acc_full = bars + 36;       // [2]
-    uint64_t* acc_empty = bars + 38;      // [2]  128 epilogue threads
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+    uint64_t* lo_empty = bars + 36;       // [12]  MMA commit
+    uint64_t* acc_full = bars + 48;       // [2]   MMA commit: GEMM 1 of a tile is in the accumulator
+    uint64_t* h_full = bars + 50;         // [2]   128 epilogue threads: h1 / lo(h1) are in tensor memory
+    uint64_t* g_done = bars + 52;         // [2]   MMA commit: the gate pre-activations of every fold of a tile are in their slots
+    uint64_t* g_empty = bars + 54;        // [8]   128 epilogue threads: the slot has been read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 62);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_x);
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&lo_full[i], 256); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < TC_MAX_STAGES; ++i) {
+            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&lo_full[i], 256); mbar_init(&lo_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&h_full[i], 128); mbar_init(&g_done[i], 1); }
+        for (int i = 0; i < TC_MAX_GSLOTS; ++i) mbar_init(&g_empty[i], 128);
         fence_mbar_init();
     }
-    const uint32_t tmem_cols = 512;                             // accumulators + the lo(X) ring; one CTA per SM
+    const uint32_t tmem_cols = 512;                             // accumulators + gate slots + the lo(X) ring; one CTA per SM
     if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
-    // W1 (every fold) -> shared memory in the K-major SWIZZLE_128B layout of the B operand, hi as is, lo = w - trunc(w);
-    // fold constants behind it
+    // W1 (every fold) -> shared memory in the K-major SWIZZLE_128B layout of the B operand, hi as is, lo = w - trunc(w)
     for (int idx = tid; idx < ntot * 192; idx += TC_THREADS) {
         const int n = idx / 192, k = idx - n * 192;
         const int m = n / L1, j = n - m * L1;
@@ -581,16 +626,23 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         *reinterpret_cast<float*>(sWh + off) = w;
         *reinterpret_cast<float*>(sWl + off) = w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     }
+    // gate operand of every fold: row n = gate unit (a: n < D, b: n >= D), K = the L1 hidden units; same layout, hi and lo
+    for (int idx = tid; idx < n_models * L1 * L1; idx += TC_THREADS) {
+        const int m = idx / (L1 * L1), rem = idx - m * L1 * L1, n = rem / L1, k = rem - n * L1;
+        const float w = (n < D) ? __ldg(models.m[m].p[2] + n * L1 + k) : __ldg(models.m[m].p[4] + (n - D) * L1 + k);
+        const int sl = k >> 5, kk = k & 31;
+        const uint32_t off = (m * 2 * GKS + sl) * GSL + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+        *reinterpret_cast<float*>(sG + off) = w;
+        *reinterpret_cast<float*>(sG + off + GKS * GSL) = w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    }
     for (int m = 0; m < n_models; ++m) {
         float* c = sC + m * fold_floats;
         const ClamModel& w = models.m[m];
         for (int i = tid; i < L1; i += TC_THREADS) c[i] = __ldg(w.p[1] + i);
-        for (int i = tid; i < D * L1; i += TC_THREADS) { c[L1 + i] = __ldg(w.p[2] + i); c[L1 + D * L1 + i] = __ldg(w.p[4] + i); }
         for (int i = tid; i < D; i += TC_THREADS) {
-            c[L1 + 2 * D * L1 + i] = __ldg(w.p[3] + i); c[L1 + 2 * D * L1 + D + i] = __ldg(w.p[5] + i);
-            c[L1 + 2 * D * L1 + 2 * D + i] = __ldg(w.p[6] + i);
+            c[L1 + i] = __ldg(w.p[3] + i); c[L1 + D + i] = __ldg(w.p[5] + i); c[2 * L1 + i] = __ldg(w.p[6] + i);
         }
-        if (tid == 0) c[L1 + 2 * D * L1 + 3 * D] = __ldg(w.p[7]);
+        if (tid == 0) c[2 * L1 + D] = __ldg(w.p[7]);
     }
     fence_proxy_async_smem();                                   // generic writes of W -> visible to the tensor core
     tc_fence_before();
@@ -599,67 +651,100 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     const uint32_t tmem_base = *tmem_slot;
     const int n_work = prefix[n_bags];
     const uint32_t acc_stride = clam_tc_acc_stride(ntot);
-    const uint32_t t_lo = tmem_base + 2 * acc_stride;           // [stages][32 columns]: lo(X) of the slice in ring stage st
+    const uint32_t t_g = tmem_base + 2 * acc_stride;            // [g_slots][L1 columns]
+    const uint32_t t_lo = t_g + g_slots * L1;                   // [lo_stages][32 columns]: lo(X) of a K-slice
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            uint32_t q = 0;
-            for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-                const int bag = work[2 * wi], chunk = work[2 * wi + 1];
-                const int row0 = bag_offsets[bag] + chunk * TC_M;
-                for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
-                    const uint32_t st = q % stages, use = q / stages;
-                    mbar_wait(&x_empty[st], (use & 1) ^ 1);
-                    mbar_arrive_expect_tx(&x_full[st], TC_SLICE_BYTES);
-                    tma_load_2d(sXr + st * TC_SLICE_BYTES, &map_x, &x_full[st], sl * TC_KS, row0);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = umma_idesc_tf32(TC_M, ntot);             // lo(X) x W1
-        const uint32_t idesc2 = umma_idesc_tf32(TC_M, 2 * ntot);        // X x [W1 ; lo(W1)]
-        uint32_t q = 0, t = 0;
-        for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x, ++t) {
-            const uint32_t b = t & 1;
-            if (t >= 2) mbar_wait(&acc_empty[b], ((t >> 1) - 1) & 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + b * acc_stride;
-            for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
-                const uint32_t st = q % stages, use = q / stages;
-                const uint64_t dx = umma_desc_k128(smem_u32(sXr + st * TC_SLICE_BYTES));
-                const uint64_t dwh = umma_desc_k128(smem_u32(sWh + sl * 2 * ntot * 128));
-                mbar_wait(&x_full[st], use & 1);
-                tc_fence_after();
-                if (elect_one()) {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        umma_tf32_ss(d_tmem, dx + 2 * kk, dwh + 2 * kk, idesc2, (sl | kk) != 0);
+    if (warp < 4) {
+        setmaxnreg_dec<48>();
+        if (warp == 0) {
+            // -------------------------------------------------------------------------------------- TMA producer
+            if (lane == 0) {
+                uint32_t st = 0, ph = 0;                          // ring position and its phase parity (no divisions)
+                for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+                    const int bag = work[2 * wi], chunk = work[2 * wi + 1];
+                    const int row0 = bag_offsets[bag] + chunk * TC_M;
+                    for (int sl = 0; sl < TC_NSL; ++sl) {
+                        mbar_wait(&x_empty[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&x_full[st], TC_SLICE_BYTES);
+                        tma_load_2d(sXr + st * TC_SLICE_BYTES, &map_x, &x_full[st], sl * TC_KS, row0);
+                        if (++st == static_cast<uint32_t>(stages)) { st = 0; ph ^= 1; }
                     }
                 }
-                __syncwarp();
-                mbar_wait(&lo_full[st], use & 1);
-                tc_fence_after();
-                if (elect_one()) {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_tf32_ts(d_tmem, t_lo + st * 32 + 8 * kk, dwh + 2 * kk, idesc, 1);
-                    umma_commit(&x_empty[st]);
-                    if (sl == TC_NSL - 1) umma_commit(&acc_full[b]);
-                }
-                __syncwarp();
             }
+        } else if (warp == 1) {
+            // -------------------------------------------------------------------------------------- MMA issuer
+            const uint32_t idesc = umma_idesc_tf32(TC_M, ntot);             // lo(X) x W1
+            const uint32_t idesc2 = umma_idesc_tf32(TC_M, 2 * ntot);        // X x [W1 ; lo(W1)]
+            constexpr uint32_t idesc_g = umma_idesc_tf32(TC_M, L1);         // h1 x [Wa ; Wb] of one fold
+            // gate of tile tt (accumulator tt & 1): one slot per fold
+            uint32_t g_pos = 0, g_ph = 0;                        // next gate slot, parity of its current use
+            bool g_wrapped = false;
+            auto issue_gate = [&](uint32_t tt) {
+                const uint32_t b = tt & 1;
+                mbar_wait(&h_full[b], (tt >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_h = tmem_base + b * acc_stride;
+                for (int m = 0; m < n_models; ++m) {
+                    const uint32_t gs = g_pos;
+                    if (g_wrapped) { mbar_wait(&g_empty[gs], g_ph ^ 1); tc_fence_after(); }
+                    if (elect_one()) {
+                        const uint32_t d_g = t_g + gs * L1;
+#pragma unroll
+                        for (int k8 = 0; k8 < L1 / 8; ++k8) {
+                            const uint64_t dgh = umma_desc_k128(smem_u32(sG + (m * 2 * GKS + (k8 >> 2)) * GSL)) + 2 * (k8 & 3);
+                            const uint64_t dgl = umma_desc_k128(smem_u32(sG + (m * 2 * GKS + GKS + (k8 >> 2)) * GSL)) + 2 * (k8 & 3);
+                            umma_tf32_ts(d_g, t_h + m * L1 + 8 * k8, dgh, idesc_g, k8 != 0);
+                            umma_tf32_ts(d_g, t_h + m * L1 + 8 * k8, dgl, idesc_g, 1);
+                            umma_tf32_ts(d_g, t_h + ntot + m * L1 + 8 * k8, dgh, idesc_g, 1);
+                        }
+                        if (m == n_models - 1) umma_commit(&g_done[b]);
+                    }
+                    __syncwarp();
+                    if (++g_pos == static_cast<uint32_t>(g_slots)) { g_pos = 0; g_ph ^= 1; g_wrapped = true; }
+                }
+            };
+            uint32_t t = 0, st = 0, ph = 0, ls = 0, lph = 0;
+            for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x, ++t) {
+                const uint32_t b = t & 1;
+                const uint32_t d_tmem = tmem_base + b * acc_stride;
+                for (int sl = 0; sl < TC_NSL; ++sl) {
+                    const uint64_t dx = umma_desc_k128(smem_u32(sXr + st * TC_SLICE_BYTES));
+                    const uint64_t dwh = umma_desc_k128(smem_u32(sWh + sl * 2 * ntot * 128));
+                    mbar_wait(&x_full[st], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) umma_tf32_ss(d_tmem, dx + 2 * kk, dwh + 2 * kk, idesc2, (sl | kk) != 0);
+                    }
+                    __syncwarp();
+                    mbar_wait(&lo_full[ls], lph);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) umma_tf32_ts(d_tmem, t_lo + ls * 32 + 8 * kk, dwh + 2 * kk, idesc, 1);
+                        umma_commit(&x_empty[st]);
+                        umma_commit(&lo_empty[ls]);
+                        if (sl == TC_NSL - 1) umma_commit(&acc_full[b]);
+                    }
+                    __syncwarp();
+                    if (++st == static_cast<uint32_t>(stages)) { st = 0; ph ^= 1; }
+                    if (++ls == static_cast<uint32_t>(lo_stages)) { ls = 0; lph ^= 1; }
+                }
+                if (t >= 1) issue_gate(t - 1);
+            }
+            if (t >= 1) issue_gate(t - 1);
         }
-    } else if (warp < 10) {
+    } else if (warp < 12) {
         // ------------------------------------------------------------------------------------------ lo(X)
-        const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;          // TMEM lane quadrant = warp % 4
+        setmaxnreg_dec<56>();
+        const int r = (warp & 3) * 32 + lane, half = (warp - 4) >> 2;          // TMEM lane quadrant = warp % 4
         const uint32_t t_my = t_lo + (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * 16;
-        uint32_t q = 0;
+        uint32_t st = 0, ph = 0, ls = 0, lph = 0;
+        bool lo_wrapped = false;
         for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-            for (int sl = 0; sl < TC_NSL; ++sl, ++q) {
-                const uint32_t st = q % stages, use = q / stages;
+            for (int sl = 0; sl < TC_NSL; ++sl) {
                 const uint32_t xs = smem_u32(sXr + st * TC_SLICE_BYTES) + r * 128;
-                mbar_wait(&x_full[st], use & 1);
+                mbar_wait(&x_full[st], ph);
                 uint32_t lo[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -670,21 +755,28 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
                     lo[4 * i + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
                     lo[4 * i + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
                 }
-                tmem_st_32x16(t_my + st * 32, lo);
+                if (lo_wrapped) { mbar_wait(&lo_empty[ls], lph ^ 1); tc_fence_after(); }
+                tmem_st_32x16(t_my + ls * 32, lo);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&lo_full[st]);
+                mbar_arrive(&lo_full[ls]);
+                if (++st == static_cast<uint32_t>(stages)) { st = 0; ph ^= 1; }
+                if (++ls == static_cast<uint32_t>(lo_stages)) { ls = 0; lph ^= 1; lo_wrapped = true; }
             }
         }
     } else {
         // ------------------------------------------------------------------------------------------ epilogue
-        const int eg = (warp - 10) >> 2;                          // epilogue warpgroup = TMEM buffer = tile parity
-        const int et = (tid - 320) & 127;                        // 0..127 inside the warpgroup
+        setmaxnreg_inc<160>();
+        const int eg = (warp - 12) >> 2;                          // epilogue warpgroup = accumulator = tile parity
+        const int et = (tid - 384) & 127;                        // 0..127 inside the warpgroup
         const int r = (warp & 3) * 32 + lane;                    // tile row = TMEM lane (warp % 4 = lane quadrant)
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        float* sRed = sScr + eg * SCR;
-        float* sPart = sRed + 8;
+        const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t sRed = smem_u32(sScr + eg * SCR);
+        const uint32_t sPart = sRed + 8 * 4;
+        const uint32_t sCu = smem_u32(sC);
         const uint32_t bar_id = 2 + eg;
+        uint32_t g_pos = (eg * n_models) % g_slots;              // slot of fold 0 of this warpgroup's next tile (tile t, fold m uses
+                                                                 // slot (t n_models + m) mod g_slots)
         for (uint32_t t = eg; static_cast<long long>(blockIdx.x) + static_cast<long long>(t) * gridDim.x < n_work; t += 2) {
             const int wi = blockIdx.x + t * gridDim.x;
             const uint32_t b = eg;
@@ -692,87 +784,137 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
             const int start = bag_offsets[bag];
             const int n_valid = min(TC_M, bag_offsets[bag + 1] - start - chunk * TC_M);
             const bool valid = r < n_valid;
+            const uint32_t t_acc = tmem_base + lane_off + b * acc_stride;
+            float h[FMAX * L1];
+            // ---- phase A: h1 of every fold -> registers and (with its low part) back into tensor memory
             mbar_wait(&acc_full[b], (t >> 1) & 1);
             tc_fence_after();
-            for (int m = 0; m < n_models; ++m) {
-                const float* c = sC + m * fold_floats;
-                float h[L1];
-                {
-                    uint32_t v[L1];
-                    uint32_t v2[L1];                             // the X lo(W1) half of the accumulator
-                    if constexpr (L1 == 16) {
-                        tmem_ld_32x16(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[16]>(v));
-                        tmem_ld_32x16(t_lane + b * acc_stride + ntot + m * L1, *reinterpret_cast<uint32_t(*)[16]>(v2));
-                    } else {
-                        tmem_ld_32x32(t_lane + b * acc_stride + m * L1, *reinterpret_cast<uint32_t(*)[32]>(v));
-                        tmem_ld_32x32(t_lane + b * acc_stride + ntot + m * L1, *reinterpret_cast<uint32_t(*)[32]>(v2));
-                    }
-                    tmem_ld_wait();
-                    if (m == n_models - 1) {                     // last TMEM read of the tile: hand the accumulator back
-                        tc_fence_before();
-                        mbar_arrive(&acc_empty[b]);
-                    }
 #pragma unroll
-                    for (int j = 0; j < L1; ++j) h[j] = fmaxf((__uint_as_float(v[j]) + __uint_as_float(v2[j])) + c[j], 0.f);
-                }
-                const float* Wa = c + L1; const float* Wb = Wa + D * L1;
-                const float* ba = Wb + D * L1; const float* bb = ba + D; const float* Wc = bb + D;
-                float A = Wc[D];                                 // bc
+            for (int m = 0; m < FMAX; ++m) {
+                if (m < n_models) {
+                    constexpr int CW = L1 < 32 ? L1 : 32;        // columns per pass (register pressure at L1 = 64)
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    float a0 = ba[d], a1 = 0.f, b0 = bb[d], b1v = 0.f;
+                    for (int c0 = 0; c0 < L1; c0 += CW) {
+                        uint32_t v[CW], v2[CW];                  // the X W1 and X lo(W1) halves of the accumulator
+                        tmem_ld_cols<CW>(t_acc + m * L1 + c0, v);
+                        tmem_ld_cols<CW>(t_acc + ntot + m * L1 + c0, v2);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < L1; j += 4) {
-                        const float4 wa = *reinterpret_cast<const float4*>(Wa + d * L1 + j);
-                        const float4 wb = *reinterpret_cast<const float4*>(Wb + d * L1 + j);
-                        a0 = fmaf(wa.x, h[j], a0); a1 = fmaf(wa.y, h[j + 1], a1); a0 = fmaf(wa.z, h[j + 2], a0); a1 = fmaf(wa.w, h[j + 3], a1);
-                        b0 = fmaf(wb.x, h[j], b0); b1v = fmaf(wb.y, h[j + 1], b1v); b0 = fmaf(wb.z, h[j + 2], b0); b1v = fmaf(wb.w, h[j + 3], b1v);
-                    }
-                    // tanh(a) = 1 - 2 / (1 + e^(2a)), sigmoid(b) = 1 / (1 + e^-b): exp2-based, |error| ~1e-6 (bar: 1e-3 on A)
-                    const float ta = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * (a0 + a1)));
-                    const float sb = __fdividef(1.0f, 1.0f + __expf(-(b0 + b1v)));
-                    A = fmaf(Wc[d], ta * sb, A);
-                }
-                if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = A;
-                // chunk-local softmax partial over the 128 rows (one named barrier per epilogue warpgroup)
-                float mx = valid ? A : -INFINITY;
+                        for (int j = 0; j < CW; j += 4) {
+                            const float4 b1 = lds_f4(sCu + (m * fold_floats + c0 + j) * 4);
+                            float* hj = h + m * L1 + c0 + j;
+                            hj[0] = fmaxf((__uint_as_float(v[j + 0]) + __uint_as_float(v2[j + 0])) + b1.x, 0.f);
+                            hj[1] = fmaxf((__uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1])) + b1.y, 0.f);
+                            hj[2] = fmaxf((__uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2])) + b1.z, 0.f);
+                            hj[3] = fmaxf((__uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])) + b1.w, 0.f);
+                        }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                if (lane == 0) sRed[warp & 3] = mx;
-                named_bar_sync(bar_id, 128);
-                mx = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
-                const float e = valid ? expf(A - mx) : 0.f;
-                float sum = e;
+                        for (int j = 0; j < CW; ++j) {
+                            const float hv = h[m * L1 + c0 + j];
+                            v[j] = __float_as_uint(hv);
+                            v2[j] = __float_as_uint(hv - __uint_as_float(v[j] & 0xFFFFE000u));
+                        }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0) sRed[4 + (warp & 3)] = sum;
-                // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles instead of 5 L1): each step
-                // a lane hands over the half of its columns its partner keeps; the surviving column ends up on
-                // lane bits (4..): column = lane >> (5 - log2 L1)
-#pragma unroll
-                for (int j = 0; j < L1; ++j) h[j] *= e;
-#pragma unroll
-                for (int half = L1 / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-                    const bool up = lane & bit;
-#pragma unroll
-                    for (int j = 0; j < half; ++j) {
-                        const float keep = up ? h[j + half] : h[j], send = up ? h[j] : h[j + half];
-                        h[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                        for (int j = 0; j < CW; j += 16) {
+                            tmem_st_32x16(t_acc + m * L1 + c0 + j, v + j);
+                            tmem_st_32x16(t_acc + ntot + m * L1 + c0 + j, v2 + j);
+                        }
                     }
                 }
-                if constexpr (L1 == 16) h[0] += __shfl_xor_sync(0xffffffffu, h[0], 1);      // 16 columns over 32 lanes: pairs share one
-                {
-                    constexpr int SH = (L1 == 16) ? 1 : 0;
-                    if (L1 == 32 || (lane & 1) == 0) sPart[(warp & 3) * L1 + (lane >> SH)] = h[0];
-                }
-                named_bar_sync(bar_id, 128);
-                sum = (sRed[4] + sRed[5]) + (sRed[6] + sRed[7]);
-                float* out = partials + (static_cast<size_t>(m) * work_cap + wi) * (L1 + 2);
-                if (et == 0) { out[0] = mx; out[1] = sum; }
-                if (et < L1) out[2 + et] = (sPart[et] + sPart[L1 + et]) + (sPart[2 * L1 + et] + sPart[3 * L1 + et]);
-                // no trailing barrier: the next fold's first barrier orders these reads before its writes of sRed[4..7] / sPart
-                // (its maxima go to sRed[0..3], which nobody reads after the barrier above)
             }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&h_full[b]);
+            // ---- phase B: per fold, gate pre-activations from the slot -> score, softmax partials, pooling partials
+            mbar_wait(&g_done[b], (t >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int m = 0; m < FMAX; ++m) {
+                if (m < n_models) {
+                    const uint32_t cm = sCu + m * fold_floats * 4;
+                    const uint32_t gs = g_pos;
+                    float A;
+                    {
+                        uint32_t g[L1];
+                        tmem_ld_cols<L1>(t_g + lane_off + gs * L1, g);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        mbar_arrive(&g_empty[gs]);
+                        if (++g_pos == static_cast<uint32_t>(g_slots)) g_pos = 0;
+                        A = __uint_as_float(lds_u1(cm + (2 * L1 + D) * 4));          // bc
+#pragma unroll
+                        for (int d = 0; d < D; d += 4) {
+                            const float4 ba = lds_f4(cm + (L1 + d) * 4), bb = lds_f4(cm + (L1 + D + d) * 4);
+                            const float4 wc = lds_f4(cm + (2 * L1 + d) * 4);
+                            const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+                            const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                // tanh(a) = 1 - 2 / (1 + e^(2a)), sigmoid(b) = 1 / (1 + e^-b): exp2-based, |error| ~1e-6
+                                const float pa = __uint_as_float(g[d + i]) + bav[i], pb = __uint_as_float(g[D + d + i]) + bbv[i];
+                                const float ta = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * pa));
+                                const float sb = __fdividef(1.0f, 1.0f + __expf(-pb));
+                                A = fmaf(wcv[i], ta * sb, A);
+                            }
+                        }
+                    }
+                    if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = A;
+                    // chunk-local softmax partial over the 128 rows (one named barrier per epilogue warpgroup)
+                    float mx = valid ? A : -INFINITY;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    if (lane == 0) sts_f1(sRed + (warp & 3) * 4, mx);
+                    named_bar_sync(bar_id, 128);
+                    {
+                        const float4 m4 = lds_f4(sRed);
+                        mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
+                    }
+                    const float e = valid ? expf(A - mx) : 0.f;
+                    float sum = e;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0) sts_f1(sRed + (4 + (warp & 3)) * 4, sum);
+                    // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles instead of 5 L1): each
+                    // step a lane hands over the half of its columns its partner keeps; the surviving columns end up on
+                    // lane-dependent positions: L1 = 16: column lane >> 1, 32: column lane, 64: columns 2 lane, 2 lane + 1
+                    float* hm = h + m * L1;
+#pragma unroll
+                    for (int j = 0; j < L1; ++j) hm[j] *= e;
+#pragma unroll
+                    for (int half = L1 / 2, bit = 16; half >= 1 && bit >= 1; half >>= 1, bit >>= 1) {
+                        const bool up = lane & bit;
+#pragma unroll
+                        for (int j = 0; j < half; ++j) {
+                            const float keep = up ? hm[j + half] : hm[j], send = up ? hm[j] : hm[j + half];
+                            hm[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                        }
+                    }
+                    if constexpr (L1 == 16) {                    // 16 columns over 32 lanes: pairs share one
+                        hm[0] += __shfl_xor_sync(0xffffffffu, hm[0], 1);
+                        if ((lane & 1) == 0) sts_f1(sPart + ((warp & 3) * L1 + (lane >> 1)) * 4, hm[0]);
+                    } else if constexpr (L1 == 32) {
+                        sts_f1(sPart + ((warp & 3) * L1 + lane) * 4, hm[0]);
+                    } else {
+                        sts_f1(sPart + ((warp & 3) * L1 + 2 * lane) * 4, hm[0]);
+                        sts_f1(sPart + ((warp & 3) * L1 + 2 * lane + 1) * 4, hm[1]);
+                    }
+                    named_bar_sync(bar_id, 128);
+                    {
+                        const float4 s4 = lds_f4(sRed + 16);
+                        sum = (s4.x + s4.y) + (s4.z + s4.w);
+                    }
+                    float* out = partials + (static_cast<size_t>(m) * work_cap + wi) * (L1 + 2);
+                    if (et == 0) { out[0] = mx; out[1] = sum; }
+                    if (et < L1) {
+                        const float p0 = __uint_as_float(lds_u1(sPart + et * 4)), p1 = __uint_as_float(lds_u1(sPart + (L1 + et) * 4));
+                        const float p2 = __uint_as_float(lds_u1(sPart + (2 * L1 + et) * 4)), p3 = __uint_as_float(lds_u1(sPart + (3 * L1 + et) * 4));
+                        out[2 + et] = (p0 + p1) + (p2 + p3);
+                    }
+                    // no trailing barrier: the next fold's first barrier orders these reads before its writes of sRed[4..7] /
+                    // sPart (its maxima go to sRed[0..3], which nobody reads after the barrier above)
+                }
+            }
+            g_pos = (g_pos + n_models) % g_slots;                // the other warpgroup's tile
         }
     }
     tc_fence_before();
@@ -925,7 +1067,8 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         if (stages < 2) return set_error("hb_clam: tensor-core path does not fit shared memory (n_models %d, L1 %d)", n_models, L1);
         const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * TC_SLICE_BYTES;
         (void)ntot;
-        auto kern = (L1 == 16) ? clam_scores_tc_kernel<16> : clam_scores_tc_kernel<32>;
+        auto kern = (L1 == 16) ? clam_scores_tc_kernel<16, 5> : (L1 == 32) ? clam_scores_tc_kernel<32, 2> : clam_scores_tc_kernel<64, 1>;
+        if (clam_tc_lo_stages(n_models, L1) < 2 || clam_tc_gslots(n_models, L1) < n_models) return set_error("hb_clam: tensor-core path does not fit tensor memory");
         if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 232448)) return -1;
         int grid = (total_instances / TC_M) + n_bags;
         if (grid > work_cap) grid = work_cap;
