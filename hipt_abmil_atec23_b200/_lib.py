@@ -161,7 +161,7 @@ def device_check():
 PROF_KINDS = 32
 PROF_NAMES = {0: "im2col", 1: "embed_gemm", 2: "cls_rows", 3: "layernorm", 4: "qkv_gemm", 5: "attention",
               6: "proj_gemm", 7: "fc1_gemm", 8: "fc2_gemm", 9: "final_ln", 10: "clam_scores", 11: "clam_combine",
-              12: "mlp_fused"}
+              12: "mlp_fused", 15: "clam_work_table"}
 
 
 def prof_enable(on=True):

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(1024) clam_work_table_kernel(const int32_t* __
                                                                int work_cap) {
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
+    __shared__ int s_excl[1024];                              // first work item of each bag of the current block of bags
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
@@ -134,10 +135,19 @@ __global__ void __launch_bounds__(1024) clam_work_table_kernel(const int32_t* __
         __syncthreads();
         const int carry = carry_s;
         const int excl = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + inc - cnt;
-        if (b < n_bags) {
-            prefix[b] = excl;
-            for (int c = 0; c < cnt; ++c)
-                if (excl + c < work_cap) { work[2 * (excl + c)] = b; work[2 * (excl + c) + 1] = c; }
+        s_excl[tid] = excl;
+        if (b < n_bags) prefix[b] = excl;
+        __syncthreads();
+        // the block's items are filled by all threads (a thread per item finds its bag by bisection: one thread per BAG writing
+        // its chunks serially costs 157 dependent stores for a 20,000-instance bag and was 11 us of a 150 us forward)
+        const int nb = min(1024, n_bags - b0), end = min(carry + warp_tot[31], work_cap);
+        for (int w = carry + tid; w < end; w += 1024) {
+            int lo = 0, hi = nb;                              // last bag with s_excl <= w (empty bags share their successor's)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_excl[mid] <= w) lo = mid; else hi = mid;
+            }
+            *reinterpret_cast<int2*>(work + 2 * w) = make_int2(b0 + lo, w - s_excl[lo]);
         }
         __syncthreads();
         if (tid == 1023) carry_s = carry + warp_tot[31];
@@ -517,15 +527,16 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 //               The tensor pipe executes in issue order, so GEMM 1 of tile t + 2 may overwrite the accumulator the gate of
 //               tile t read its A operand from without any further hand-shake.
 //   warps 2-3   idle (they only complete the first warpgroup, which gives its registers away)
-//   warps 4-11  lo(X): two threads per row read the slice from shared memory and write lo(x) into TENSOR memory (32 columns
+//   warps 4-7   lo(X): one thread per row reads the slice from shared memory and writes lo(x) into TENSOR memory (32 columns
 //               per stage of a second, shorter ring): term 3 is an A-from-TMEM MMA, so the shared-memory ring holds features
 //               only (Little's law: ring bytes / HBM latency is the bandwidth one SM can pull)
-//   warps 12-15, 16-19  two epilogue warpgroups (even / odd tiles = accumulator 0 / 1), thread = row.
+//   warps 8-11, 12-15  two epilogue warpgroups (even / odd tiles = accumulator 0 / 1), thread = row.
 //               Phase A (all folds): TMEM -> +b1, ReLU -> h1 kept in registers for the pooling partials, h1 and lo(h1) -> TMEM.
 //               Phase B (per fold): G slot -> +bias, tanh * sigmoid, score, chunk softmax partials, sum_i e_i h1_i.
-// Registers: 640 threads launch with 96 each; setmaxnreg moves them to 48 (first warpgroup) / 56 (lo) / 160 (epilogue): 61,440 = what the CTA launched with.
+// Registers: 512 threads launch with 128 each; setmaxnreg moves them to 72 (first warpgroup) / 64 (lo) / 184 (epilogue; h1 of up to
+// five folds = 80 registers stays live across both phases): 64,512 of the 65,536 the CTA launched with.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 640, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
+constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 512, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
 constexpr int TC_MAX_GSLOTS = 8;
 // TMEM: two accumulators of acc_stride columns (2 ntot — the X W1 and X lo(W1) halves, later h1 and lo(h1) — rounded up to 32),
 // then g_slots gate accumulators of L1 columns, then 32 columns of lo(X) per stage of the lo ring
@@ -552,7 +563,7 @@ __host__ __device__ inline int clam_tc_gate_bytes(int L1) { return 2 * ((L1 + 31
 __host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int D) {
     const int ntot = n_models * L1;
     return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 + static_cast<size_t>(n_models) * clam_tc_gate_bytes(L1) +
-           (static_cast<size_t>(n_models) * clam_tc_fold_floats(L1, D) + 2 * (8 + 4 * L1)) * sizeof(float) + 80 * 8;
+           static_cast<size_t>(n_models) * clam_tc_fold_floats(L1, D) * sizeof(float) + 80 * 8;
 }
 // as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
 __host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
@@ -570,10 +581,10 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
     }
 }
 
-template <int L1, int FMAX>
+template <int L1, int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* __restrict__ bag_offsets,
-                      const __grid_constant__ ClamModels models, int n_models, int n_bags, int total_instances,
+                      const __grid_constant__ ClamModels models, int n_bags, int total_instances,
                       const int32_t* __restrict__ prefix, const int32_t* __restrict__ work, int work_cap,
                       float* __restrict__ a_raw, float* __restrict__ partials) {
     constexpr int D = L1 / 2;
@@ -581,7 +592,9 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     constexpr int GSL = L1 * 128;                               // bytes of one such slice ([L1 rows][128 B])
     extern __shared__ uint8_t smem_raw_tc[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
-    const int ntot = n_models * L1;
+    constexpr int n_models = F;                                 // the fold count is a template parameter: every loop over
+                                                                // folds unrolls, h1 of all folds stays in registers
+    constexpr int ntot = n_models * L1;
     const int stages = clam_tc_stages(n_models, L1, D);
     const int lo_stages = clam_tc_lo_stages(n_models, L1);
     const int g_slots = clam_tc_gslots(n_models, L1);
@@ -591,12 +604,10 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     uint8_t* sG = sWh + 2 * TC_NSL * ntot * 128;                // [n_models][hi, lo][GKS][L1 rows][128 B]: [Wa ; Wb]
     float* sC = reinterpret_cast<float*>(sG + n_models * clam_tc_gate_bytes(L1));   // [n_models][fold constants]
     constexpr int fold_floats = ((2 * L1 + D + 1) + 3) & ~3;
-    constexpr int SCR = 8 + 4 * L1;                             // per epilogue warpgroup: [8] reductions | [4 warps][L1] column partials
-    float* sScr = sC + n_models * fold_floats;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + 2 * SCR);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + n_models * fold_floats);
     uint64_t* x_full = bars;              // [12]
     uint64_t* x_empty = bars + 12;        // [12]  MMA commit
-    uint64_t* lo_full = bars + 24;        // [12]  256 split threads
+    uint64_t* lo_full = bars + 24;        // [12]  128 lo(X) threads
     uint64_t* lo_empty = bars + 36;       // [12]  MMA commit
     uint64_t* acc_full = bars + 48;       // [2]   MMA commit: GEMM 1 of a tile is in the accumulator
     uint64_t* h_full = bars + 50;         // [2]   128 epilogue threads: h1 / lo(h1) are in tensor memory
@@ -608,7 +619,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_x);
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < TC_MAX_STAGES; ++i) {
-            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&lo_full[i], 256); mbar_init(&lo_empty[i], 1);
+            mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&lo_full[i], 128); mbar_init(&lo_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&h_full[i], 128); mbar_init(&g_done[i], 1); }
         for (int i = 0; i < TC_MAX_GSLOTS; ++i) mbar_init(&g_empty[i], 128);
@@ -655,7 +666,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     const uint32_t t_lo = t_g + g_slots * L1;                   // [lo_stages][32 columns]: lo(X) of a K-slice
 
     if (warp < 4) {
-        setmaxnreg_dec<48>();
+        setmaxnreg_dec<72>();
         if (warp == 0) {
             // -------------------------------------------------------------------------------------- TMA producer
             if (lane == 0) {
@@ -730,33 +741,35 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
                     if (++st == static_cast<uint32_t>(stages)) { st = 0; ph ^= 1; }
                     if (++ls == static_cast<uint32_t>(lo_stages)) { ls = 0; lph ^= 1; }
                 }
+                // (issuing this gate earlier — between two K-slices, as soon as h1 is in tensor memory — measured SLOWER:
+                // 142 vs 131 us for one fold, 246 vs 243 us for five)
                 if (t >= 1) issue_gate(t - 1);
             }
             if (t >= 1) issue_gate(t - 1);
         }
-    } else if (warp < 12) {
+    } else if (warp < 8) {
         // ------------------------------------------------------------------------------------------ lo(X)
-        setmaxnreg_dec<56>();
-        const int r = (warp & 3) * 32 + lane, half = (warp - 4) >> 2;          // TMEM lane quadrant = warp % 4
-        const uint32_t t_my = t_lo + (static_cast<uint32_t>((warp & 3) * 32) << 16) + half * 16;
+        setmaxnreg_dec<64>();
+        const int r = (warp & 3) * 32 + lane;                    // tile row = TMEM lane (lane quadrant = warp % 4)
+        const uint32_t t_my = t_lo + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         uint32_t st = 0, ph = 0, ls = 0, lph = 0;
         bool lo_wrapped = false;
         for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
             for (int sl = 0; sl < TC_NSL; ++sl) {
                 const uint32_t xs = smem_u32(sXr + st * TC_SLICE_BYTES) + r * 128;
                 mbar_wait(&x_full[st], ph);
-                uint32_t lo[16];
+                uint32_t lo[32];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = half * 4 + i;                  // 16-byte piece c = K elements 4 c .. 4 c + 3 of the slice
+                for (int c = 0; c < 8; ++c) {                    // 16-byte piece c = K elements 4 c .. 4 c + 3 of the slice
                     const uint4 v = lds_u4(xs + ((c ^ (r & 7)) << 4));
-                    lo[4 * i + 0] = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
-                    lo[4 * i + 1] = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
-                    lo[4 * i + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
-                    lo[4 * i + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+                    lo[4 * c + 0] = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+                    lo[4 * c + 1] = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+                    lo[4 * c + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+                    lo[4 * c + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
                 }
                 if (lo_wrapped) { mbar_wait(&lo_empty[ls], lph ^ 1); tc_fence_after(); }
                 tmem_st_32x16(t_my + ls * 32, lo);
+                tmem_st_32x16(t_my + ls * 32 + 16, lo + 16);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&lo_full[ls]);
@@ -766,15 +779,11 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         }
     } else {
         // ------------------------------------------------------------------------------------------ epilogue
-        setmaxnreg_inc<160>();
-        const int eg = (warp - 12) >> 2;                          // epilogue warpgroup = accumulator = tile parity
-        const int et = (tid - 384) & 127;                        // 0..127 inside the warpgroup
+        setmaxnreg_inc<184>();
+        const int eg = (warp - 8) >> 2;                           // epilogue warpgroup = accumulator = tile parity
         const int r = (warp & 3) * 32 + lane;                    // tile row = TMEM lane (warp % 4 = lane quadrant)
         const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t sRed = smem_u32(sScr + eg * SCR);
-        const uint32_t sPart = sRed + 8 * 4;
         const uint32_t sCu = smem_u32(sC);
-        const uint32_t bar_id = 2 + eg;
         uint32_t g_pos = (eg * n_models) % g_slots;              // slot of fold 0 of this warpgroup's next tile (tile t, fold m uses
                                                                  // slot (t n_models + m) mod g_slots)
         for (uint32_t t = eg; static_cast<long long>(blockIdx.x) + static_cast<long long>(t) * gridDim.x < n_work; t += 2) {
@@ -785,133 +794,143 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
             const int n_valid = min(TC_M, bag_offsets[bag + 1] - start - chunk * TC_M);
             const bool valid = r < n_valid;
             const uint32_t t_acc = tmem_base + lane_off + b * acc_stride;
-            float h[FMAX * L1];
-            // ---- phase A: h1 of every fold -> registers and (with its low part) back into tensor memory
+            float h[F * L1];
+            // ---- phase A: h1 of every fold -> registers and (with its low part) back into tensor memory.  Software-pipelined:
+            // the accumulator columns of pass p + 1 are in flight while pass p is computed (inline asm is a compiler barrier,
+            // so the overlap has to be spelled out)
+            constexpr int CW = L1 < 32 ? L1 : 32;                // columns per pass (register pressure at L1 = 64)
+            constexpr int PPF = L1 / CW, NP = F * PPF;           // passes per fold, passes per tile
+            uint32_t vb[2][CW], wb[2][CW];                       // the X W1 and X lo(W1) halves of the accumulator, double-buffered
             mbar_wait(&acc_full[b], (t >> 1) & 1);
             tc_fence_after();
+            tmem_ld_cols<CW>(t_acc, vb[0]);
+            tmem_ld_cols<CW>(t_acc + ntot, wb[0]);
 #pragma unroll
-            for (int m = 0; m < FMAX; ++m) {
-                if (m < n_models) {
-                    constexpr int CW = L1 < 32 ? L1 : 32;        // columns per pass (register pressure at L1 = 64)
+            for (int p = 0; p < NP; ++p) {
+                const int m = p / PPF, c0 = (p % PPF) * CW;
+                uint32_t* v = vb[p & 1];
+                uint32_t* v2 = wb[p & 1];
+                tmem_ld_wait();
+                if (p + 1 < NP) {
+                    const int m1 = (p + 1) / PPF, c1 = ((p + 1) % PPF) * CW;
+                    tmem_ld_cols<CW>(t_acc + m1 * L1 + c1, vb[(p + 1) & 1]);
+                    tmem_ld_cols<CW>(t_acc + ntot + m1 * L1 + c1, wb[(p + 1) & 1]);
+                }
 #pragma unroll
-                    for (int c0 = 0; c0 < L1; c0 += CW) {
-                        uint32_t v[CW], v2[CW];                  // the X W1 and X lo(W1) halves of the accumulator
-                        tmem_ld_cols<CW>(t_acc + m * L1 + c0, v);
-                        tmem_ld_cols<CW>(t_acc + ntot + m * L1 + c0, v2);
-                        tmem_ld_wait();
+                for (int j = 0; j < CW; j += 4) {
+                    const float4 b1 = lds_f4(sCu + (m * fold_floats + c0 + j) * 4);
+                    float* hj = h + m * L1 + c0 + j;
+                    hj[0] = fmaxf((__uint_as_float(v[j + 0]) + __uint_as_float(v2[j + 0])) + b1.x, 0.f);
+                    hj[1] = fmaxf((__uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1])) + b1.y, 0.f);
+                    hj[2] = fmaxf((__uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2])) + b1.z, 0.f);
+                    hj[3] = fmaxf((__uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])) + b1.w, 0.f);
+                }
 #pragma unroll
-                        for (int j = 0; j < CW; j += 4) {
-                            const float4 b1 = lds_f4(sCu + (m * fold_floats + c0 + j) * 4);
-                            float* hj = h + m * L1 + c0 + j;
-                            hj[0] = fmaxf((__uint_as_float(v[j + 0]) + __uint_as_float(v2[j + 0])) + b1.x, 0.f);
-                            hj[1] = fmaxf((__uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1])) + b1.y, 0.f);
-                            hj[2] = fmaxf((__uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2])) + b1.z, 0.f);
-                            hj[3] = fmaxf((__uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])) + b1.w, 0.f);
-                        }
+                for (int j = 0; j < CW; ++j) {
+                    const float hv = h[m * L1 + c0 + j];
+                    v[j] = __float_as_uint(hv);
+                    v2[j] = __float_as_uint(hv - __uint_as_float(v[j] & 0xFFFFE000u));
+                }
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) {
-                            const float hv = h[m * L1 + c0 + j];
-                            v[j] = __float_as_uint(hv);
-                            v2[j] = __float_as_uint(hv - __uint_as_float(v[j] & 0xFFFFE000u));
-                        }
-#pragma unroll
-                        for (int j = 0; j < CW; j += 16) {
-                            tmem_st_32x16(t_acc + m * L1 + c0 + j, v + j);
-                            tmem_st_32x16(t_acc + ntot + m * L1 + c0 + j, v2 + j);
-                        }
-                    }
+                for (int j = 0; j < CW; j += 16) {
+                    tmem_st_32x16(t_acc + m * L1 + c0 + j, v + j);
+                    tmem_st_32x16(t_acc + ntot + m * L1 + c0 + j, v2 + j);
                 }
             }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&h_full[b]);
-            // ---- phase B: per fold, gate pre-activations from the slot -> score, softmax partials, pooling partials
-            mbar_wait(&g_done[b], (t >> 1) & 1);
-            tc_fence_after();
+            // ---- phase B1: per fold, gate pre-activations from the slot -> score (the next fold's slot is in flight meanwhile)
+            float A[F];
+            {
+                constexpr int GB = F > 1 ? 2 : 1;
+                uint32_t gbuf[GB][L1];
+                mbar_wait(&g_done[b], (t >> 1) & 1);
+                tc_fence_after();
+                tmem_ld_cols<L1>(t_g + lane_off + g_pos * L1, gbuf[0]);
 #pragma unroll
-            for (int m = 0; m < FMAX; ++m) {
-                if (m < n_models) {
+                for (int m = 0; m < F; ++m) {
                     const uint32_t cm = sCu + m * fold_floats * 4;
-                    const uint32_t gs = g_pos;
-                    float A;
-                    {
-                        uint32_t g[L1];
-                        tmem_ld_cols<L1>(t_g + lane_off + gs * L1, g);
-                        tmem_ld_wait();
-                        tc_fence_before();
-                        mbar_arrive(&g_empty[gs]);
-                        if (++g_pos == static_cast<uint32_t>(g_slots)) g_pos = 0;
-                        A = __uint_as_float(lds_u1(cm + (2 * L1 + D) * 4));          // bc
+                    const uint32_t* g = gbuf[m % GB];
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&g_empty[g_pos]);
+                    if (++g_pos == static_cast<uint32_t>(g_slots)) g_pos = 0;
+                    if (m + 1 < F) tmem_ld_cols<L1>(t_g + lane_off + g_pos * L1, gbuf[(m + 1) % GB]);
+                    float a = __uint_as_float(lds_u1(cm + (2 * L1 + D) * 4));          // bc
 #pragma unroll
-                        for (int d = 0; d < D; d += 4) {
-                            const float4 ba = lds_f4(cm + (L1 + d) * 4), bb = lds_f4(cm + (L1 + D + d) * 4);
-                            const float4 wc = lds_f4(cm + (2 * L1 + d) * 4);
-                            const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
-                            const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+                    for (int d = 0; d < D; d += 4) {
+                        const float4 ba = lds_f4(cm + (L1 + d) * 4), bb = lds_f4(cm + (L1 + D + d) * 4);
+                        const float4 wc = lds_f4(cm + (2 * L1 + d) * 4);
+                        const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+                        const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                // tanh(a) = 1 - 2 / (1 + e^(2a)), sigmoid(b) = 1 / (1 + e^-b): exp2-based, |error| ~1e-6
-                                const float pa = __uint_as_float(g[d + i]) + bav[i], pb = __uint_as_float(g[D + d + i]) + bbv[i];
-                                const float ta = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * pa));
-                                const float sb = __fdividef(1.0f, 1.0f + __expf(-pb));
-                                A = fmaf(wcv[i], ta * sb, A);
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            // tanh(a) sigmoid(b) = (e^2a - 1) / ((e^2a + 1) (1 + e^-b)): two exp2 and ONE reciprocal per gate
+                            // unit.  Clamps keep the denominator finite: tanh saturates to 1 - 2e-13 at |a| = 15,
+                            // sigmoid(-50) = 2e-22 (bar on A: 1e-3)
+                            const float pa = fminf(fmaxf(__uint_as_float(g[d + i]) + bav[i], -15.f), 15.f);
+                            const float pb = fmaxf(__uint_as_float(g[D + d + i]) + bbv[i], -50.f);
+                            const float e2a = __expf(2.0f * pa), enb = __expf(-pb);
+                            const float tasb = __fdividef(e2a - 1.0f, (e2a + 1.0f) * (1.0f + enb));
+                            a = fmaf(wcv[i], tasb, a);
                         }
                     }
-                    if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = A;
-                    // chunk-local softmax partial over the 128 rows (one named barrier per epilogue warpgroup)
-                    float mx = valid ? A : -INFINITY;
+                    A[m] = a;
+                    if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = a;
+                }
+            }
+            // ---- phase B2: softmax / pooling partials of the WARP's 32 rows for all folds at once (four records per tile and
+            // fold: no barrier, no shared-memory exchange between the warps of the tile — clam_combine_kernel merges
+            // records, it does not care how many).  Every reduction step runs over the folds in its inner loop, so the
+            // shuffles of different folds overlap instead of forming one long dependent chain per fold.
+            float mx[F], e[F], sum[F];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    if (lane == 0) sts_f1(sRed + (warp & 3) * 4, mx);
-                    named_bar_sync(bar_id, 128);
-                    {
-                        const float4 m4 = lds_f4(sRed);
-                        mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
-                    }
-                    const float e = valid ? expf(A - mx) : 0.f;
-                    float sum = e;
+            for (int m = 0; m < F; ++m) mx[m] = valid ? A[m] : -INFINITY;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (lane == 0) sts_f1(sRed + (4 + (warp & 3)) * 4, sum);
-                    // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles instead of 5 L1): each
-                    // step a lane hands over the half of its columns its partner keeps; the surviving columns end up on
-                    // lane-dependent positions: L1 = 16: column lane >> 1, 32: column lane, 64: columns 2 lane, 2 lane + 1
-                    float* hm = h + m * L1;
+            for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                    for (int j = 0; j < L1; ++j) hm[j] *= e;
+                for (int m = 0; m < F; ++m) mx[m] = fmaxf(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], o));
+            }
 #pragma unroll
-                    for (int half = L1 / 2, bit = 16; half >= 1 && bit >= 1; half >>= 1, bit >>= 1) {
-                        const bool up = lane & bit;
+            for (int m = 0; m < F; ++m) { e[m] = valid ? expf(A[m] - mx[m]) : 0.f; sum[m] = e[m]; }
 #pragma unroll
-                        for (int j = 0; j < half; ++j) {
-                            const float keep = up ? hm[j + half] : hm[j], send = up ? hm[j] : hm[j + half];
-                            hm[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-                        }
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int m = 0; m < F; ++m) sum[m] += __shfl_xor_sync(0xffffffffu, sum[m], o);
+            }
+            // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles per fold instead of 5 L1): each
+            // step a lane hands over the half of its columns its partner keeps; the surviving columns end up on
+            // lane-dependent positions: L1 = 16: column lane >> 1, 32: column lane, 64: columns 2 lane, 2 lane + 1
+#pragma unroll
+            for (int m = 0; m < F; ++m) {
+#pragma unroll
+                for (int j = 0; j < L1; ++j) h[m * L1 + j] *= e[m];
+            }
+#pragma unroll
+            for (int half = L1 / 2, bit = 16; half >= 1 && bit >= 1; half >>= 1, bit >>= 1) {
+                const bool up = lane & bit;
+#pragma unroll
+                for (int m = 0; m < F; ++m) {
+#pragma unroll
+                    for (int j = 0; j < half; ++j) {
+                        const float keep = up ? h[m * L1 + j + half] : h[m * L1 + j];
+                        const float send = up ? h[m * L1 + j] : h[m * L1 + j + half];
+                        h[m * L1 + j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
                     }
-                    if constexpr (L1 == 16) {                    // 16 columns over 32 lanes: pairs share one
-                        hm[0] += __shfl_xor_sync(0xffffffffu, hm[0], 1);
-                        if ((lane & 1) == 0) sts_f1(sPart + ((warp & 3) * L1 + (lane >> 1)) * 4, hm[0]);
-                    } else if constexpr (L1 == 32) {
-                        sts_f1(sPart + ((warp & 3) * L1 + lane) * 4, hm[0]);
-                    } else {
-                        sts_f1(sPart + ((warp & 3) * L1 + 2 * lane) * 4, hm[0]);
-                        sts_f1(sPart + ((warp & 3) * L1 + 2 * lane + 1) * 4, hm[1]);
-                    }
-                    named_bar_sync(bar_id, 128);
-                    {
-                        const float4 s4 = lds_f4(sRed + 16);
-                        sum = (s4.x + s4.y) + (s4.z + s4.w);
-                    }
-                    float* out = partials + (static_cast<size_t>(m) * work_cap + wi) * (L1 + 2);
-                    if (et == 0) { out[0] = mx; out[1] = sum; }
-                    if (et < L1) {
-                        const float p0 = __uint_as_float(lds_u1(sPart + et * 4)), p1 = __uint_as_float(lds_u1(sPart + (L1 + et) * 4));
-                        const float p2 = __uint_as_float(lds_u1(sPart + (2 * L1 + et) * 4)), p3 = __uint_as_float(lds_u1(sPart + (3 * L1 + et) * 4));
-                        out[2 + et] = (p0 + p1) + (p2 + p3);
-                    }
-                    // no trailing barrier: the next fold's first barrier orders these reads before its writes of sRed[4..7] /
-                    // sPart (its maxima go to sRed[0..3], which nobody reads after the barrier above)
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < F; ++m) {
+                float* out = partials + ((static_cast<size_t>(m) * work_cap + wi) * 4 + (warp & 3)) * (L1 + 2);
+                if (lane == 0) *reinterpret_cast<float2*>(out) = make_float2(mx[m], sum[m]);
+                if constexpr (L1 == 16) {                        // 16 columns over 32 lanes: pairs share one
+                    const float hv = h[m * L1] + __shfl_xor_sync(0xffffffffu, h[m * L1], 1);
+                    if ((lane & 1) == 0) out[2 + (lane >> 1)] = hv;
+                } else if constexpr (L1 == 32) {
+                    out[2 + lane] = h[m * L1];
+                } else {
+                    *reinterpret_cast<float2*>(out + 2 + 2 * lane) = make_float2(h[m * L1], h[m * L1 + 1]);
                 }
             }
             g_pos = (g_pos + n_models) % g_slots;                // the other warpgroup's tile
@@ -922,37 +941,48 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-__global__ void __launch_bounds__(128) clam_combine_kernel(const int32_t* __restrict__ bag_offsets,
-                                                           const __grid_constant__ ClamModels models, int n_bags, int L1,
-                                                           int C, int work_cap, int CH, const int32_t* __restrict__ prefix,
-                                                           const float* __restrict__ partials,
-                                                           float* __restrict__ m_out, float* __restrict__ logits,
-                                                           float* __restrict__ y_prob, long long* __restrict__ y_hat,
-                                                           int paired) {
-    extern __shared__ float sM[];                             // [L1] + [C] + [128] scratch + [8]
+constexpr int CB_THREADS = 256;
+__global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t* __restrict__ bag_offsets,
+                                                                  const __grid_constant__ ClamModels models, int n_bags, int L1,
+                                                                  int C, int work_cap, int CH, const int32_t* __restrict__ prefix,
+                                                                  const float* __restrict__ partials,
+                                                                  float* __restrict__ m_out, float* __restrict__ logits,
+                                                                  float* __restrict__ y_prob, long long* __restrict__ y_hat,
+                                                                  int paired, int recs_per_chunk) {
+    extern __shared__ float sM[];                             // [L1] + [C] + [CB_THREADS] scratch + [8]
     float* sL = sM + L1;
-    float* sP = sL + C;                                       // [128] per-group partial sums of M
-    float* red = sP + 128;
+    float* sP = sL + C;                                       // [CB_THREADS] per-group partial sums of M
+    float* red = sP + CB_THREADS;
     const int bag = blockIdx.x, mi = paired ? blockIdx.x : blockIdx.y, tid = threadIdx.x;
     const int oi = paired ? bag : mi * n_bags + bag;          // paired (multi-trial): model m pools bag m only, compact outputs
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
-    const int n_chunks = (len + CH - 1) / CH;
+    const int n_chunks = ((len + CH - 1) / CH) * recs_per_chunk;   // partial records of the bag (the tensor-core score kernel
+                                                                   // writes one per warp = four per 128-instance chunk)
     const size_t rec = L1 + 2;
-    const float* base = partials + (static_cast<size_t>(mi) * work_cap + prefix[bag]) * rec;
-    // chunks are spread over the threads (a 20,000-instance bag has 313 of them: a serial walk is latency-bound)
+    const float* __restrict__ base = partials + (static_cast<size_t>(mi) * work_cap + prefix[bag]) * recs_per_chunk * rec;
+    // records are spread over the threads (a 20,000-instance bag has 628 of them: a serial walk is latency-bound)
     float gm = -INFINITY;
-    for (int c = tid; c < n_chunks; c += 128) gm = fmaxf(gm, base[c * rec]);
+    for (int c = tid; c < n_chunks; c += CB_THREADS) gm = fmaxf(gm, base[c * rec]);
     const float gmax = block_reduce_max_128(gm, red);
     float tl = 0.f;
-    for (int c = tid; c < n_chunks; c += 128) tl += base[c * rec + 1] * expf(base[c * rec] - gmax);
+    for (int c = tid; c < n_chunks; c += CB_THREADS) tl += base[c * rec + 1] * expf(base[c * rec] - gmax);
     const float total = block_reduce_sum_128(tl, red);
     const float inv = (n_chunks > 0) ? 1.0f / total : 0.f;
-    if (L1 <= 128) {
-        const int G = 128 / L1;                               // chunk groups walking the chunk list in parallel
+    if (L1 <= CB_THREADS) {
+        const int G = CB_THREADS / L1;                        // record groups walking the list in parallel
         const int cg = tid / L1, j = tid - cg * L1;
         float acc = 0.f;
-        if (cg < G)
-            for (int c = cg; c < n_chunks; c += G) acc = fmaf(base[c * rec + 2 + j], expf(base[c * rec] - gmax), acc);
+        if (cg < G) {
+            int c = cg;
+            for (; c + 3 * G < n_chunks; c += 4 * G) {        // four records in flight per thread
+                const float v0 = base[c * rec + 2 + j], v1 = base[(c + G) * rec + 2 + j];
+                const float v2 = base[(c + 2 * G) * rec + 2 + j], v3 = base[(c + 3 * G) * rec + 2 + j];
+                const float m0 = base[c * rec], m1 = base[(c + G) * rec], m2 = base[(c + 2 * G) * rec], m3 = base[(c + 3 * G) * rec];
+                acc = fmaf(v0, expf(m0 - gmax), acc); acc = fmaf(v1, expf(m1 - gmax), acc);
+                acc = fmaf(v2, expf(m2 - gmax), acc); acc = fmaf(v3, expf(m3 - gmax), acc);
+            }
+            for (; c < n_chunks; c += G) acc = fmaf(base[c * rec + 2 + j], expf(base[c * rec] - gmax), acc);
+        }
         sP[tid] = acc;
         __syncthreads();
         if (tid < L1) {
@@ -1004,7 +1034,8 @@ static size_t clam_ws_layout(size_t cap, int n_bags, int n_models, int L1, size_
     return o + static_cast<size_t>(n_models) * cap * (L1 + 2) * sizeof(float);
 }
 size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1) {
-    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + 31) / 32;
+    // + 3: the tensor-core path writes four records per 128-instance chunk, 4 ceil(n / 128) <= ceil(n / 32) + 3
+    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + 31) / 32 + 3;
     return clam_ws_layout(static_cast<size_t>(n_bags) * (max_chunks ? max_chunks : 1), n_bags, n_models, L1, nullptr, nullptr);
 }
 
@@ -1056,10 +1087,22 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     if (tc_env < 0) { const char* e = getenv("HB_CLAM_TC"); tc_env = (e && e[0] == '0') ? 0 : 1; }
     if (paired && !clam_is192(L0, L1, D)) return set_error("hb_clam: the paired launch is implemented for the HIPT heads (192-d features)");
     if (tc_env && !dropping && !paired && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
-        // tensor-core path: 128-instance chunks (fewer (bag, chunk) items than the bound computed for CH above)
-        clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, TC_M, prefix, work, work_cap);
-        count_launch();
-        HB_CUDA_OK(cudaGetLastError());
+        // tensor-core path: 128-instance chunks, four partial records per chunk (one per epilogue warp)
+        size_t cap_tc = static_cast<size_t>(total_instances) / TC_M + n_bags;
+        const size_t cap_tc2 = static_cast<size_t>(n_bags) * ((max_bag_len + TC_M - 1) / TC_M);
+        if (cap_tc2 < cap_tc) cap_tc = cap_tc2;
+        size_t off_work_tc, off_part_tc;
+        const size_t need_tc = clam_ws_layout(4 * cap_tc, n_bags, n_models, L1, &off_work_tc, &off_part_tc);
+        if (workspace_bytes < need_tc) return set_error("hb_clam: workspace %zu < %zu bytes", workspace_bytes, need_tc);
+        int32_t* work = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + off_work_tc);
+        float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + off_part_tc);
+        const int work_cap = static_cast<int>(cap_tc);
+        {
+            ProfScope ps0(15, stream);
+            clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, TC_M, prefix, work, work_cap);
+            count_launch();
+            HB_CUDA_OK(cudaGetLastError());
+        }
         CUtensorMap map_x;
         if (encode_tmap_2d(&map_x, TMAP_F32, feats, static_cast<uint64_t>(total_instances), 192, 192 * 4, TC_M, TC_KS)) return -1;
         const int ntot = n_models * L1;
@@ -1067,7 +1110,16 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         if (stages < 2) return set_error("hb_clam: tensor-core path does not fit shared memory (n_models %d, L1 %d)", n_models, L1);
         const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * TC_SLICE_BYTES;
         (void)ntot;
-        auto kern = (L1 == 16) ? clam_scores_tc_kernel<16, 5> : (L1 == 32) ? clam_scores_tc_kernel<32, 2> : clam_scores_tc_kernel<64, 1>;
+        decltype(&clam_scores_tc_kernel<16, 1>) kern = nullptr;
+        if (L1 == 16) {
+            decltype(kern) k16[5] = {clam_scores_tc_kernel<16, 1>, clam_scores_tc_kernel<16, 2>, clam_scores_tc_kernel<16, 3>,
+                                     clam_scores_tc_kernel<16, 4>, clam_scores_tc_kernel<16, 5>};
+            kern = k16[n_models - 1];
+        } else if (L1 == 32) {
+            kern = n_models == 1 ? clam_scores_tc_kernel<32, 1> : clam_scores_tc_kernel<32, 2>;
+        } else {
+            kern = clam_scores_tc_kernel<64, 1>;
+        }
         if (clam_tc_lo_stages(n_models, L1) < 2 || clam_tc_gslots(n_models, L1) < n_models) return set_error("hb_clam: tensor-core path does not fit tensor memory");
         if (set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 232448)) return -1;
         int grid = (total_instances / TC_M) + n_bags;
@@ -1075,16 +1127,16 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         if (grid > num_sms()) grid = num_sms();
         {
             ProfScope ps(10, stream);
-            kern<<<grid, TC_THREADS, smem, stream>>>(map_x, bag_offsets, models, n_models, n_bags, total_instances, prefix, work,
+            kern<<<grid, TC_THREADS, smem, stream>>>(map_x, bag_offsets, models, n_bags, total_instances, prefix, work,
                                                      work_cap, a_raw, partials);
             count_launch();
             HB_CUDA_OK(cudaGetLastError());
         }
         dim3 grid2(n_bags, n_models);
         ProfScope ps2(11, stream);
-        clam_combine_kernel<<<grid2, 128, (L1 + C + 128 + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
+        clam_combine_kernel<<<grid2, CB_THREADS, (L1 + C + CB_THREADS + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                                         work_cap, TC_M, prefix, partials, m_out,
-                                                                                        logits, y_prob, y_hat, 0);
+                                                                                        logits, y_prob, y_hat, 0, 4);
         count_launch();
         HB_CUDA_OK(cudaGetLastError());
         return 0;
@@ -1124,9 +1176,9 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     }
     dim3 grid2(n_bags, paired ? 1 : n_models);
     ProfScope ps2(11, stream);
-    clam_combine_kernel<<<grid2, 128, (L1 + C + 128 + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
+    clam_combine_kernel<<<grid2, CB_THREADS, (L1 + C + CB_THREADS + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                                     work_cap, CH, prefix, partials, m_out,
-                                                                                    logits, y_prob, y_hat, paired);
+                                                                                    logits, y_prob, y_hat, paired, 1);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -36,7 +36,16 @@ def run(size, folds, reps=20):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     bytes_alg = total * (192 * 4 + 4 * folds)
-    return {"size": size, "folds": folds, "bags": int(lens.numel()), "instances": total, "ms": ms,
+    # per-kernel times of a second pass (CUDA events around every launch; the headline `ms` above is taken without them)
+    _lib.prof_enable(True)
+    for _ in range(reps): f()
+    torch.cuda.synchronize()
+    kern_us = {k: round(v[0] / v[1] * 1e3, 2) for k, v in _lib.prof_read().items()}
+    _lib.prof_enable(False)
+    score_us = kern_us.get("clam_scores")
+    return {"size": size, "folds": folds, "ms": ms, "kernels_us": kern_us,
+            "score_kernel_GBps": bytes_alg / score_us / 1e3 if score_us else None,
+            "bags": int(lens.numel()), "instances": total,
             "bags_per_s": lens.numel() / ms * 1e3, "instances_per_s": total / ms * 1e3,
             "algorithmic_GBps": bytes_alg / ms / 1e6, "feature_MB": total * 768 / 1e6}
 
