@@ -592,8 +592,9 @@ def clam_config4(dev, peaks):
     feats = torch.randn((total, 192), generator=torch.Generator().manual_seed(5)).to(dev)
     offs_d, mx = offs.to(dev), int(lens.max())
     out = {"bags": 256, "instances": total, "bytes_per_instance": 772, "feature_MB": total * 768 / 1e6}
-    for size in ("hipt_smaller", "hipt_big"):
-        for folds in (1, 5):
+    from hipt_abmil_atec23_b200 import _lib
+    for size, fold_list in (("hipt_smaller", (1, 5)), ("hipt_small", (1, 2)), ("hipt_medium", (1,)), ("hipt_big", (1, 5))):
+        for folds in fold_list:
             models = []
             for f in range(folds):
                 torch.manual_seed(10 + f)
@@ -612,6 +613,19 @@ def clam_config4(dev, peaks):
             gbs = total * (768 + 4 * folds) / ms / 1e6
             key = f"folds{folds}" if size == "hipt_smaller" else f"{size}_folds{folds}"
             out[key] = {"ms": ms, "bags_per_s": 256 / ms * 1e3, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+            # the score kernel alone (CUDA events around each launch in a second pass; `ms` above is the whole forward:
+            # work table + score kernel + combine)
+            _lib.prof_enable(True)
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            pr = _lib.prof_read()
+            _lib.prof_enable(False)
+            if "clam_scores" in pr:
+                us = pr["clam_scores"][0] / pr["clam_scores"][1] * 1e3
+                out[key]["score_kernel_us"] = us
+                out[key]["score_kernel_GBps"] = total * (768 + 4 * folds) / us / 1e3
+                out[key]["score_kernel_frac_of_hbm_peak"] = out[key]["score_kernel_GBps"] / peaks["hbm_gbs"]
     torch.manual_seed(2)
     model = CLAM_SB(size_arg="hipt_smaller", dropout=0.0, n_classes=2).to(dev).train()
     opt = clam_engine.FusedAdam(filter(lambda p: p.requires_grad, model.parameters()), lr=2e-4, weight_decay=1e-5)

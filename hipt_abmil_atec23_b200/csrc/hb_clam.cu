@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(1024) clam_work_table_kernel(const int32_t* __
     __shared__ int carry_s;
     __shared__ int s_excl[1024];                              // first work item of each bag of the current block of bags
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();                                  // the score kernel may stage its weights while this table is built
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (int b0 = 0; b0 < n_bags; b0 += 1024) {
@@ -660,6 +661,8 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                                 // everything above overlapped clam_work_table_kernel
+    pdl_launch_dependents();                                    // clam_combine_kernel: scheduled as this grid's CTAs retire
     const int n_work = prefix[n_bags];
     const uint32_t acc_stride = clam_tc_acc_stride(ntot);
     const uint32_t t_g = tmem_base + 2 * acc_stride;            // [g_slots][L1 columns]
@@ -949,12 +952,13 @@ __global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t*
                                                                   float* __restrict__ m_out, float* __restrict__ logits,
                                                                   float* __restrict__ y_prob, long long* __restrict__ y_hat,
                                                                   int paired, int recs_per_chunk) {
-    extern __shared__ float sM[];                             // [L1] + [C] + [CB_THREADS] scratch + [8]
+    extern __shared__ float sM[];                             // [L1] + [C] + [2 CB_THREADS] scratch + [8]
     float* sL = sM + L1;
-    float* sP = sL + C;                                       // [CB_THREADS] per-group partial sums of M
-    float* red = sP + CB_THREADS;
+    float* sP = sL + C;                                       // [2 CB_THREADS] per-group partial sums of M
+    float* red = sP + 2 * CB_THREADS;
     const int bag = blockIdx.x, mi = paired ? blockIdx.x : blockIdx.y, tid = threadIdx.x;
     const int oi = paired ? bag : mi * n_bags + bag;          // paired (multi-trial): model m pools bag m only, compact outputs
+    pdl_wait();                                               // no-op unless launched as a programmatic dependent
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
     const int n_chunks = ((len + CH - 1) / CH) * recs_per_chunk;   // partial records of the bag (the tensor-core score kernel
                                                                    // writes one per warp = four per 128-instance chunk)
@@ -968,22 +972,36 @@ __global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t*
     for (int c = tid; c < n_chunks; c += CB_THREADS) tl += base[c * rec + 1] * expf(base[c * rec] - gmax);
     const float total = block_reduce_sum_128(tl, red);
     const float inv = (n_chunks > 0) ? 1.0f / total : 0.f;
-    if (L1 <= CB_THREADS) {
-        const int G = CB_THREADS / L1;                        // record groups walking the list in parallel
-        const int cg = tid / L1, j = tid - cg * L1;
-        float acc = 0.f;
+    if ((L1 & 1) == 0 && L1 <= CB_THREADS) {
+        // a thread owns a column PAIR of a group of records; eight records in flight per thread (the walk is latency-bound:
+        // a 20,000-instance bag has 628 records, and each is read exactly once)
+        const int TPR = L1 / 2, G = CB_THREADS / TPR;         // threads per record, record groups walking the list in parallel
+        const int cg = tid / TPR, jp = tid - cg * TPR;
+        float acc0 = 0.f, acc1 = 0.f;
         if (cg < G) {
+            const float* __restrict__ bj = base + 2 + 2 * jp;
             int c = cg;
-            for (; c + 3 * G < n_chunks; c += 4 * G) {        // four records in flight per thread
-                const float v0 = base[c * rec + 2 + j], v1 = base[(c + G) * rec + 2 + j];
-                const float v2 = base[(c + 2 * G) * rec + 2 + j], v3 = base[(c + 3 * G) * rec + 2 + j];
-                const float m0 = base[c * rec], m1 = base[(c + G) * rec], m2 = base[(c + 2 * G) * rec], m3 = base[(c + 3 * G) * rec];
-                acc = fmaf(v0, expf(m0 - gmax), acc); acc = fmaf(v1, expf(m1 - gmax), acc);
-                acc = fmaf(v2, expf(m2 - gmax), acc); acc = fmaf(v3, expf(m3 - gmax), acc);
+            for (; c + 7 * G < n_chunks; c += 8 * G) {
+                float2 v[8];
+                float mr[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = *reinterpret_cast<const float2*>(bj + static_cast<size_t>(c + u * G) * rec);
+                    mr[u] = base[static_cast<size_t>(c + u * G) * rec];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float w = expf(mr[u] - gmax);
+                    acc0 = fmaf(v[u].x, w, acc0); acc1 = fmaf(v[u].y, w, acc1);
+                }
             }
-            for (; c < n_chunks; c += G) acc = fmaf(base[c * rec + 2 + j], expf(base[c * rec] - gmax), acc);
+            for (; c < n_chunks; c += G) {
+                const float2 v = *reinterpret_cast<const float2*>(bj + static_cast<size_t>(c) * rec);
+                const float w = expf(base[static_cast<size_t>(c) * rec] - gmax);
+                acc0 = fmaf(v.x, w, acc0); acc1 = fmaf(v.y, w, acc1);
+            }
         }
-        sP[tid] = acc;
+        sP[2 * tid] = acc0; sP[2 * tid + 1] = acc1;           // [group][column]: (cg TPR + jp) 2 = cg L1 + 2 jp
         __syncthreads();
         if (tid < L1) {
             float v = 0.f;
@@ -1004,11 +1022,18 @@ __global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t*
     __syncthreads();
     const float* Wcls = models.m[mi].p[8];
     const float* bcls = models.m[mi].p[9];
-    for (int c = tid; c < C; c += blockDim.x) {
-        float acc = __ldg(bcls + c);
-        for (int j = 0; j < L1; ++j) acc = fmaf(__ldg(Wcls + static_cast<size_t>(c) * L1 + j), sM[j], acc);
-        sL[c] = acc;
-        if (logits) logits[static_cast<size_t>(oi) * C + c] = acc;
+    // classifier: a warp per class, lanes over the hidden units (one thread per class walking L1 dependent global loads was
+    // most of this kernel's time for the wider heads)
+    for (int c = tid >> 5; c < C; c += CB_THREADS / 32) {
+        float acc = 0.f;
+        for (int j = tid & 31; j < L1; j += 32) acc = fmaf(__ldg(Wcls + static_cast<size_t>(c) * L1 + j), sM[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) {
+            acc += __ldg(bcls + c);
+            sL[c] = acc;
+            if (logits) logits[static_cast<size_t>(oi) * C + c] = acc;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -1127,18 +1152,33 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         if (grid > num_sms()) grid = num_sms();
         {
             ProfScope ps(10, stream);
-            kern<<<grid, TC_THREADS, smem, stream>>>(map_x, bag_offsets, models, n_bags, total_instances, prefix, work,
-                                                     work_cap, a_raw, partials);
+            // programmatic dependent launch: the prologue (barriers, tensor-memory allocation, weight staging) overlaps the work
+            // table kernel; pdl_wait() in the kernel orders the first read of the table
+            cudaLaunchAttribute pdl[1];
+            pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cfg.attrs = pdl; cfg.numAttrs = 1;
+            const int32_t* prefix_c = prefix; const int32_t* work_c = work;
+            HB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_x, bag_offsets, models, n_bags, total_instances, prefix_c, work_c,
+                                          work_cap, a_raw, partials));
             count_launch();
-            HB_CUDA_OK(cudaGetLastError());
         }
-        dim3 grid2(n_bags, n_models);
-        ProfScope ps2(11, stream);
-        clam_combine_kernel<<<grid2, CB_THREADS, (L1 + C + CB_THREADS + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
-                                                                                        work_cap, TC_M, prefix, partials, m_out,
-                                                                                        logits, y_prob, y_hat, 0, 4);
-        count_launch();
-        HB_CUDA_OK(cudaGetLastError());
+        {
+            ProfScope ps2(11, stream);
+            cudaLaunchAttribute pdl[1];
+            pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(n_bags, n_models); cfg.blockDim = dim3(CB_THREADS);
+            cfg.dynamicSmemBytes = (L1 + C + 2 * CB_THREADS + 8) * sizeof(float); cfg.stream = stream;
+            cfg.attrs = pdl; cfg.numAttrs = 1;
+            const int32_t* prefix_c = prefix; const float* partials_c = partials;
+            HB_CUDA_OK(cudaLaunchKernelEx(&cfg, clam_combine_kernel, bag_offsets, models, n_bags, L1, C, work_cap, static_cast<int>(TC_M),
+                                          prefix_c, partials_c, m_out, logits, y_prob, y_hat, 0, 4));
+            count_launch();
+        }
         return 0;
     }
     clam_work_table_kernel<<<1, 1024, 0, stream>>>(bag_offsets, n_bags, CH, prefix, work, work_cap);
@@ -1176,7 +1216,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     }
     dim3 grid2(n_bags, paired ? 1 : n_models);
     ProfScope ps2(11, stream);
-    clam_combine_kernel<<<grid2, CB_THREADS, (L1 + C + CB_THREADS + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
+    clam_combine_kernel<<<grid2, CB_THREADS, (L1 + C + 2 * CB_THREADS + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                                     work_cap, CH, prefix, partials, m_out,
                                                                                     logits, y_prob, y_hat, paired, 1);
     count_launch();

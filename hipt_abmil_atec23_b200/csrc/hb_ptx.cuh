@@ -65,6 +65,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
         : "memory");
     return ok;
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are visible,
+// pdl_launch_dependents() lets the successor's CTAs be scheduled from here on (they still wait in their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Non-blocking poll (try_wait may suspend the thread for a system-dependent time when the phase is not complete yet).
 __device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

@@ -73,7 +73,10 @@ def test_training_step_with_dropout_matches_the_reference_module(gold, monkeypat
                 assert p.grad is None or float(p.grad.abs().max()) == 0.0, (name, k)
                 continue
             err = (p.grad.cpu() - ref).abs().max().item()
-            assert err < 1e-3 * max(1e-2, ref.abs().max().item()), (name, k, err, ref.abs().max().item())
+            # floor 2e-5: at dropout 0.85 the attention_c gradients are analytically ~1e-8 (sum_i alpha_i (dM.h_i - s) = 0) while
+            # the cancelling terms are O(100) after three 1 / 0.15 rescalings, so fp32 leaves ~1e-5 of rounding noise in both
+            # implementations and the comparison depends on the summation order of M (measured: 0.9e-5 .. 1.1e-5)
+            assert err < 1e-3 * max(2e-2, ref.abs().max().item()), (name, k, err, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("p", [0.25, 0.85, 1.0])
