@@ -277,15 +277,6 @@ __device__ __forceinline__ void tmem_ld_x32_ptr(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ float ex2_approx(float x) {
-#ifdef ATC_EXP_NOMUFU
-    return fmaf(x, 0.001f, 1.0f);        // timing experiment only
-#else
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#endif
-}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 

@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 512, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
 constexpr int TC_MAX_GSLOTS = 8;
+constexpr float TC_SCALE_A = 2.8853900817779268f, TC_SCALE_B = -1.4426950408889634f;    // 2 log2(e), -log2(e)
 // TMEM: two accumulators of acc_stride columns (2 ntot — the X W1 and X lo(W1) halves, later h1 and lo(h1) — rounded up to 32),
 // then g_slots gate accumulators of L1 columns, then 32 columns of lo(X) per stage of the lo ring
 __host__ __device__ inline int clam_tc_acc_stride(int ntot) { return (2 * ntot + 31) & ~31; }
@@ -579,6 +580,176 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
     else {
 #pragma unroll
         for (int i = 0; i < N; i += 32) tmem_ld_32x32(taddr + i, *reinterpret_cast<uint32_t(*)[32]>(v + i));
+    }
+}
+
+// Epilogue of clam_scores_tc_kernel for the folds [M0, M1) of every TSTEP-th tile starting at tile t0 (thread = tile row).
+// The kernel runs it with all folds and TSTEP = 2: the two epilogue warpgroups alternate tiles.
+struct TcEpi {
+    uint64_t *acc_full, *h_full, *g_done, *g_empty;
+    uint32_t tmem_base, acc_stride, t_g, sCu;
+    int g_slots, n_work, work_cap, total_instances;
+    const int32_t* work;
+    const int32_t* bag_offsets;
+    float* a_raw;
+    float* partials;
+};
+template <int L1, int F, int M0, int M1, int TSTEP>
+__device__ __forceinline__ void clam_tc_epilogue(const TcEpi& E, uint32_t t0, int warp, int lane) {
+    constexpr int D = L1 / 2, NF = M1 - M0, ntot = F * L1;
+    constexpr int fold_floats = ((2 * L1 + D + 1) + 3) & ~3;
+    const int r = (warp & 3) * 32 + lane;                        // tile row = TMEM lane (warp % 4 = lane quadrant)
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t sCu = E.sCu, t_g = E.t_g;
+    const int g_slots = E.g_slots;
+    uint32_t g_pos = (t0 * F + M0) % g_slots;                    // tile t, fold m uses gate slot (t F + m) mod g_slots
+    for (uint32_t t = t0; static_cast<long long>(blockIdx.x) + static_cast<long long>(t) * gridDim.x < E.n_work; t += TSTEP) {
+        const int wi = blockIdx.x + t * gridDim.x;
+        const uint32_t b = t & 1;                                // accumulator of the tile
+        const int bag = E.work[2 * wi], chunk = E.work[2 * wi + 1];
+        const int start = E.bag_offsets[bag];
+        const int n_valid = min(TC_M, E.bag_offsets[bag + 1] - start - chunk * TC_M);
+        const bool valid = r < n_valid;
+        const uint32_t t_acc = E.tmem_base + lane_off + b * E.acc_stride;
+        float h[NF * L1];
+        // ---- phase A: h1 of every fold -> registers and (with its low part) back into tensor memory.  Software-pipelined:
+        // the accumulator columns of pass p + 1 are in flight while pass p is computed (inline asm is a compiler barrier,
+        // so the overlap has to be spelled out)
+        constexpr int CW = L1 < 32 ? L1 : 32;                // columns per pass (register pressure at L1 = 64)
+        constexpr int PPF = L1 / CW, NP = NF * PPF;          // passes per fold, passes of this warpgroup per tile
+        uint32_t vb[2][CW], wb[2][CW];                       // the X W1 and X lo(W1) halves of the accumulator, double-buffered
+        mbar_wait(&E.acc_full[b], (t >> 1) & 1);
+        tc_fence_after();
+        tmem_ld_cols<CW>(t_acc + M0 * L1, vb[0]);
+        tmem_ld_cols<CW>(t_acc + ntot + M0 * L1, wb[0]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int mi = p / PPF, m = M0 + mi, c0 = (p % PPF) * CW;   // mi: fold index inside this warpgroup's range
+            uint32_t* v = vb[p & 1];
+            uint32_t* v2 = wb[p & 1];
+            tmem_ld_wait();
+            if (p + 1 < NP) {
+                const int m1 = M0 + (p + 1) / PPF, c1 = ((p + 1) % PPF) * CW;
+                tmem_ld_cols<CW>(t_acc + m1 * L1 + c1, vb[(p + 1) & 1]);
+                tmem_ld_cols<CW>(t_acc + ntot + m1 * L1 + c1, wb[(p + 1) & 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+                const float4 b1 = lds_f4(sCu + (m * fold_floats + c0 + j) * 4);
+                float* hj = h + mi * L1 + c0 + j;
+                hj[0] = fmaxf((__uint_as_float(v[j + 0]) + __uint_as_float(v2[j + 0])) + b1.x, 0.f);
+                hj[1] = fmaxf((__uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1])) + b1.y, 0.f);
+                hj[2] = fmaxf((__uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2])) + b1.z, 0.f);
+                hj[3] = fmaxf((__uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])) + b1.w, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                const float hv = h[mi * L1 + c0 + j];
+                v[j] = __float_as_uint(hv);
+                v2[j] = __float_as_uint(hv - __uint_as_float(v[j] & 0xFFFFE000u));
+            }
+#pragma unroll
+            for (int j = 0; j < CW; j += 16) {
+                tmem_st_32x16(t_acc + m * L1 + c0 + j, v + j);
+                tmem_st_32x16(t_acc + ntot + m * L1 + c0 + j, v2 + j);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&E.h_full[b]);
+        // ---- phase B1: per fold, gate pre-activations from the slot -> score (the next fold's slot is in flight meanwhile)
+        float A[NF];
+        {
+            constexpr int GB = NF > 1 ? 2 : 1;
+            uint32_t gbuf[GB][L1];
+            mbar_wait(&E.g_done[b], (t >> 1) & 1);
+            tc_fence_after();
+            tmem_ld_cols<L1>(t_g + lane_off + g_pos * L1, gbuf[0]);
+#pragma unroll
+            for (int mi = 0; mi < NF; ++mi) {
+                const int m = M0 + mi;
+                const uint32_t cm = sCu + m * fold_floats * 4;
+                const uint32_t* g = gbuf[mi % GB];
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&E.g_empty[g_pos]);
+                if (++g_pos == static_cast<uint32_t>(g_slots)) g_pos = 0;
+                if (mi + 1 < NF) tmem_ld_cols<L1>(t_g + lane_off + g_pos * L1, gbuf[(mi + 1) % GB]);
+                float a = __uint_as_float(lds_u1(cm + (2 * L1 + D) * 4));          // bc
+#pragma unroll
+                for (int d = 0; d < D; d += 4) {
+                    const float4 ba = lds_f4(cm + (L1 + d) * 4), bb = lds_f4(cm + (L1 + D + d) * 4);
+                    const float4 wc = lds_f4(cm + (2 * L1 + d) * 4);
+                    const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+                    const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // tanh(a) sigmoid(b) = (1 - 2 / (1 + e^2a)) / (1 + e^-b) on bare ex2 / rcp (the gate operand and its biases
+                        // are pre-scaled by 2 log2 e and -log2 e); inf-safe without clamps: rcp(inf) = 0
+                        const float e2a = ex2_approx(__uint_as_float(g[d + i]) + bav[i]);
+                        const float enb = ex2_approx(__uint_as_float(g[D + d + i]) + bbv[i]);
+                        const float tasb = fmaf(-2.0f, rcp_approx(1.0f + e2a), 1.0f) * rcp_approx(1.0f + enb);
+                        a = fmaf(wcv[i], tasb, a);
+                    }
+                }
+                A[mi] = a;
+                if (valid) E.a_raw[static_cast<size_t>(m) * E.total_instances + start + chunk * TC_M + r] = a;
+            }
+        }
+        // ---- phase B2: softmax / pooling partials of the WARP's 32 rows for all folds at once (four records per tile and
+        // fold: no barrier, no shared-memory exchange between the warps of the tile — clam_combine_kernel merges
+        // records, it does not care how many).  Every reduction step runs over the folds in its inner loop, so the
+        // shuffles of different folds overlap instead of forming one long dependent chain per fold.
+        float mx[NF], e[NF], sum[NF];
+#pragma unroll
+        for (int m = 0; m < NF; ++m) mx[m] = valid ? A[m] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int m = 0; m < NF; ++m) mx[m] = fmaxf(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], o));
+        }
+#pragma unroll
+        for (int m = 0; m < NF; ++m) { e[m] = valid ? ex2_approx((A[m] - mx[m]) * 1.4426950408889634f) : 0.f; sum[m] = e[m]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int m = 0; m < NF; ++m) sum[m] += __shfl_xor_sync(0xffffffffu, sum[m], o);
+        }
+        // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles per fold instead of 5 L1): each
+        // step a lane hands over the half of its columns its partner keeps; the surviving columns end up on
+        // lane-dependent positions: L1 = 16: column lane >> 1, 32: column lane, 64: columns 2 lane, 2 lane + 1
+#pragma unroll
+        for (int m = 0; m < NF; ++m) {
+#pragma unroll
+            for (int j = 0; j < L1; ++j) h[m * L1 + j] *= e[m];
+        }
+#pragma unroll
+        for (int half = L1 / 2, bit = 16; half >= 1 && bit >= 1; half >>= 1, bit >>= 1) {
+            const bool up = lane & bit;
+#pragma unroll
+            for (int m = 0; m < NF; ++m) {
+#pragma unroll
+                for (int j = 0; j < half; ++j) {
+                    const float keep = up ? h[m * L1 + j + half] : h[m * L1 + j];
+                    const float send = up ? h[m * L1 + j] : h[m * L1 + j + half];
+                    h[m * L1 + j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NF; ++m) {
+            float* out = E.partials + ((static_cast<size_t>(M0 + m) * E.work_cap + wi) * 4 + (warp & 3)) * (L1 + 2);
+            if (lane == 0) *reinterpret_cast<float2*>(out) = make_float2(mx[m], sum[m]);
+            if constexpr (L1 == 16) {                        // 16 columns over 32 lanes: pairs share one
+                const float hv = h[m * L1] + __shfl_xor_sync(0xffffffffu, h[m * L1], 1);
+                if ((lane & 1) == 0) out[2 + (lane >> 1)] = hv;
+            } else if constexpr (L1 == 32) {
+                out[2 + lane] = h[m * L1];
+            } else {
+                *reinterpret_cast<float2*>(out + 2 + 2 * lane) = make_float2(h[m * L1], h[m * L1 + 1]);
+            }
+        }
+        g_pos = (g_pos + TSTEP * F - NF) % g_slots;                 // the folds / tiles of the other warpgroup
     }
 }
 
@@ -641,7 +812,8 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     // gate operand of every fold: row n = gate unit (a: n < D, b: n >= D), K = the L1 hidden units; same layout, hi and lo
     for (int idx = tid; idx < n_models * L1 * L1; idx += TC_THREADS) {
         const int m = idx / (L1 * L1), rem = idx - m * L1 * L1, n = rem / L1, k = rem - n * L1;
-        const float w = (n < D) ? __ldg(models.m[m].p[2] + n * L1 + k) : __ldg(models.m[m].p[4] + (n - D) * L1 + k);
+        // pre-scaled so that the epilogue's exponentials are bare ex2: branch a by 2 log2(e) (e^2a), branch b by -log2(e) (e^-b)
+        const float w = (n < D) ? __ldg(models.m[m].p[2] + n * L1 + k) * TC_SCALE_A : __ldg(models.m[m].p[4] + (n - D) * L1 + k) * TC_SCALE_B;
         const int sl = k >> 5, kk = k & 31;
         const uint32_t off = (m * 2 * GKS + sl) * GSL + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
         *reinterpret_cast<float*>(sG + off) = w;
@@ -652,7 +824,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         const ClamModel& w = models.m[m];
         for (int i = tid; i < L1; i += TC_THREADS) c[i] = __ldg(w.p[1] + i);
         for (int i = tid; i < D; i += TC_THREADS) {
-            c[L1 + i] = __ldg(w.p[3] + i); c[L1 + D + i] = __ldg(w.p[5] + i); c[2 * L1 + i] = __ldg(w.p[6] + i);
+            c[L1 + i] = __ldg(w.p[3] + i) * TC_SCALE_A; c[L1 + D + i] = __ldg(w.p[5] + i) * TC_SCALE_B; c[2 * L1 + i] = __ldg(w.p[6] + i);
         }
         if (tid == 0) c[2 * L1 + D] = __ldg(w.p[7]);
     }
@@ -783,161 +955,16 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     } else {
         // ------------------------------------------------------------------------------------------ epilogue
         setmaxnreg_inc<184>();
-        const int eg = (warp - 8) >> 2;                           // epilogue warpgroup = accumulator = tile parity
-        const int r = (warp & 3) * 32 + lane;                    // tile row = TMEM lane (warp % 4 = lane quadrant)
-        const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t sCu = smem_u32(sC);
-        uint32_t g_pos = (eg * n_models) % g_slots;              // slot of fold 0 of this warpgroup's next tile (tile t, fold m uses
-                                                                 // slot (t n_models + m) mod g_slots)
-        for (uint32_t t = eg; static_cast<long long>(blockIdx.x) + static_cast<long long>(t) * gridDim.x < n_work; t += 2) {
-            const int wi = blockIdx.x + t * gridDim.x;
-            const uint32_t b = eg;
-            const int bag = work[2 * wi], chunk = work[2 * wi + 1];
-            const int start = bag_offsets[bag];
-            const int n_valid = min(TC_M, bag_offsets[bag + 1] - start - chunk * TC_M);
-            const bool valid = r < n_valid;
-            const uint32_t t_acc = tmem_base + lane_off + b * acc_stride;
-            float h[F * L1];
-            // ---- phase A: h1 of every fold -> registers and (with its low part) back into tensor memory.  Software-pipelined:
-            // the accumulator columns of pass p + 1 are in flight while pass p is computed (inline asm is a compiler barrier,
-            // so the overlap has to be spelled out)
-            constexpr int CW = L1 < 32 ? L1 : 32;                // columns per pass (register pressure at L1 = 64)
-            constexpr int PPF = L1 / CW, NP = F * PPF;           // passes per fold, passes per tile
-            uint32_t vb[2][CW], wb[2][CW];                       // the X W1 and X lo(W1) halves of the accumulator, double-buffered
-            mbar_wait(&acc_full[b], (t >> 1) & 1);
-            tc_fence_after();
-            tmem_ld_cols<CW>(t_acc, vb[0]);
-            tmem_ld_cols<CW>(t_acc + ntot, wb[0]);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const int m = p / PPF, c0 = (p % PPF) * CW;
-                uint32_t* v = vb[p & 1];
-                uint32_t* v2 = wb[p & 1];
-                tmem_ld_wait();
-                if (p + 1 < NP) {
-                    const int m1 = (p + 1) / PPF, c1 = ((p + 1) % PPF) * CW;
-                    tmem_ld_cols<CW>(t_acc + m1 * L1 + c1, vb[(p + 1) & 1]);
-                    tmem_ld_cols<CW>(t_acc + ntot + m1 * L1 + c1, wb[(p + 1) & 1]);
-                }
-#pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                    const float4 b1 = lds_f4(sCu + (m * fold_floats + c0 + j) * 4);
-                    float* hj = h + m * L1 + c0 + j;
-                    hj[0] = fmaxf((__uint_as_float(v[j + 0]) + __uint_as_float(v2[j + 0])) + b1.x, 0.f);
-                    hj[1] = fmaxf((__uint_as_float(v[j + 1]) + __uint_as_float(v2[j + 1])) + b1.y, 0.f);
-                    hj[2] = fmaxf((__uint_as_float(v[j + 2]) + __uint_as_float(v2[j + 2])) + b1.z, 0.f);
-                    hj[3] = fmaxf((__uint_as_float(v[j + 3]) + __uint_as_float(v2[j + 3])) + b1.w, 0.f);
-                }
-#pragma unroll
-                for (int j = 0; j < CW; ++j) {
-                    const float hv = h[m * L1 + c0 + j];
-                    v[j] = __float_as_uint(hv);
-                    v2[j] = __float_as_uint(hv - __uint_as_float(v[j] & 0xFFFFE000u));
-                }
-#pragma unroll
-                for (int j = 0; j < CW; j += 16) {
-                    tmem_st_32x16(t_acc + m * L1 + c0 + j, v + j);
-                    tmem_st_32x16(t_acc + ntot + m * L1 + c0 + j, v2 + j);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&h_full[b]);
-            // ---- phase B1: per fold, gate pre-activations from the slot -> score (the next fold's slot is in flight meanwhile)
-            float A[F];
-            {
-                constexpr int GB = F > 1 ? 2 : 1;
-                uint32_t gbuf[GB][L1];
-                mbar_wait(&g_done[b], (t >> 1) & 1);
-                tc_fence_after();
-                tmem_ld_cols<L1>(t_g + lane_off + g_pos * L1, gbuf[0]);
-#pragma unroll
-                for (int m = 0; m < F; ++m) {
-                    const uint32_t cm = sCu + m * fold_floats * 4;
-                    const uint32_t* g = gbuf[m % GB];
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    mbar_arrive(&g_empty[g_pos]);
-                    if (++g_pos == static_cast<uint32_t>(g_slots)) g_pos = 0;
-                    if (m + 1 < F) tmem_ld_cols<L1>(t_g + lane_off + g_pos * L1, gbuf[(m + 1) % GB]);
-                    float a = __uint_as_float(lds_u1(cm + (2 * L1 + D) * 4));          // bc
-#pragma unroll
-                    for (int d = 0; d < D; d += 4) {
-                        const float4 ba = lds_f4(cm + (L1 + d) * 4), bb = lds_f4(cm + (L1 + D + d) * 4);
-                        const float4 wc = lds_f4(cm + (2 * L1 + d) * 4);
-                        const float bav[4] = {ba.x, ba.y, ba.z, ba.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
-                        const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            // tanh(a) sigmoid(b) = (e^2a - 1) / ((e^2a + 1) (1 + e^-b)): two exp2 and ONE reciprocal per gate
-                            // unit.  Clamps keep the denominator finite: tanh saturates to 1 - 2e-13 at |a| = 15,
-                            // sigmoid(-50) = 2e-22 (bar on A: 1e-3)
-                            const float pa = fminf(fmaxf(__uint_as_float(g[d + i]) + bav[i], -15.f), 15.f);
-                            const float pb = fmaxf(__uint_as_float(g[D + d + i]) + bbv[i], -50.f);
-                            const float e2a = __expf(2.0f * pa), enb = __expf(-pb);
-                            const float tasb = __fdividef(e2a - 1.0f, (e2a + 1.0f) * (1.0f + enb));
-                            a = fmaf(wcv[i], tasb, a);
-                        }
-                    }
-                    A[m] = a;
-                    if (valid) a_raw[static_cast<size_t>(m) * total_instances + start + chunk * TC_M + r] = a;
-                }
-            }
-            // ---- phase B2: softmax / pooling partials of the WARP's 32 rows for all folds at once (four records per tile and
-            // fold: no barrier, no shared-memory exchange between the warps of the tile — clam_combine_kernel merges
-            // records, it does not care how many).  Every reduction step runs over the folds in its inner loop, so the
-            // shuffles of different folds overlap instead of forming one long dependent chain per fold.
-            float mx[F], e[F], sum[F];
-#pragma unroll
-            for (int m = 0; m < F; ++m) mx[m] = valid ? A[m] : -INFINITY;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int m = 0; m < F; ++m) mx[m] = fmaxf(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], o));
-            }
-#pragma unroll
-            for (int m = 0; m < F; ++m) { e[m] = valid ? expf(A[m] - mx[m]) : 0.f; sum[m] = e[m]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int m = 0; m < F; ++m) sum[m] += __shfl_xor_sync(0xffffffffu, sum[m], o);
-            }
-            // sum_i e_i h1[i][:] over the warp's 32 rows: recursive halving (L1 - 1 shuffles per fold instead of 5 L1): each
-            // step a lane hands over the half of its columns its partner keeps; the surviving columns end up on
-            // lane-dependent positions: L1 = 16: column lane >> 1, 32: column lane, 64: columns 2 lane, 2 lane + 1
-#pragma unroll
-            for (int m = 0; m < F; ++m) {
-#pragma unroll
-                for (int j = 0; j < L1; ++j) h[m * L1 + j] *= e[m];
-            }
-#pragma unroll
-            for (int half = L1 / 2, bit = 16; half >= 1 && bit >= 1; half >>= 1, bit >>= 1) {
-                const bool up = lane & bit;
-#pragma unroll
-                for (int m = 0; m < F; ++m) {
-#pragma unroll
-                    for (int j = 0; j < half; ++j) {
-                        const float keep = up ? h[m * L1 + j + half] : h[m * L1 + j];
-                        const float send = up ? h[m * L1 + j] : h[m * L1 + j + half];
-                        h[m * L1 + j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-                    }
-                }
-            }
-#pragma unroll
-            for (int m = 0; m < F; ++m) {
-                float* out = partials + ((static_cast<size_t>(m) * work_cap + wi) * 4 + (warp & 3)) * (L1 + 2);
-                if (lane == 0) *reinterpret_cast<float2*>(out) = make_float2(mx[m], sum[m]);
-                if constexpr (L1 == 16) {                        // 16 columns over 32 lanes: pairs share one
-                    const float hv = h[m * L1] + __shfl_xor_sync(0xffffffffu, h[m * L1], 1);
-                    if ((lane & 1) == 0) out[2 + (lane >> 1)] = hv;
-                } else if constexpr (L1 == 32) {
-                    out[2 + lane] = h[m * L1];
-                } else {
-                    *reinterpret_cast<float2*>(out + 2 + 2 * lane) = make_float2(h[m * L1], h[m * L1 + 1]);
-                }
-            }
-            g_pos = (g_pos + n_models) % g_slots;                // the other warpgroup's tile
-        }
+        const int eg = (warp - 8) >> 2;                           // epilogue warpgroup
+        TcEpi E;
+        E.acc_full = acc_full; E.h_full = h_full; E.g_done = g_done; E.g_empty = g_empty;
+        E.tmem_base = tmem_base; E.acc_stride = acc_stride; E.t_g = t_g; E.sCu = smem_u32(sC);
+        E.g_slots = g_slots; E.n_work = n_work; E.work_cap = work_cap; E.total_instances = total_instances;
+        E.work = work; E.bag_offsets = bag_offsets; E.a_raw = a_raw; E.partials = partials;
+        // the two warpgroups alternate tiles.  (Both on every tile, each with half of the folds — clam_tc_epilogue<L1, F, 0, FH, 1>
+        // and <L1, F, FH, F, 1> — measured slower: 5 folds 240 vs 256 us, hipt_small 2 folds 176 vs 183 us in the same run; and an L2
+        // prefetch of the tiles ahead of the shared-memory ring made every configuration 7-60 % slower.)
+        clam_tc_epilogue<L1, F, 0, F, 2>(E, eg, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
