@@ -451,13 +451,17 @@ def test_clam_lean_train_step_matches_the_autograd_route():
         assert (pa - pb).abs().max().item() < 1e-6, k
 
 
-def test_clam_ragged_bags_and_fold_ensemble():
+@pytest.mark.parametrize("size_arg,folds", [("hipt_smaller", 5), ("hipt_smaller", 1), ("hipt_smaller", 3), ("hipt_small", 2),
+                                            ("hipt_medium", 1)])
+def test_clam_ragged_bags_and_fold_ensemble(size_arg, folds):
+    """Every head / fold count the tensor-core score kernel is instantiated for (first Linear and both gate Linears as split-TF32
+    tcgen05 GEMMs), ragged bags from 0 to 20,000 instances, against the oracle."""
     from hipt_abmil_atec23_b200 import clam_engine
     gen = torch.Generator().manual_seed(4)
     lens = [50, 75, 200, 1000, 5000, 20000, 1, 129, 128, 0, 333]
     offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
     feats = torch.randn(sum(lens), 192, generator=gen)
-    models = [seeded_clam("hipt_smaller", 10 + i) for i in range(5)]
+    models = [seeded_clam(size_arg, 10 + i) for i in range(folds)]
     r = clam_engine.forward_bags([m.to(DEV) for m in models], feats.to(DEV), offs)
     torch.cuda.synchronize()
     for mi, m in enumerate(models):
@@ -487,7 +491,9 @@ def test_clam_forward_writes_stay_inside_their_buffers():
     offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
     feats = torch.randn(total, 192, generator=torch.Generator().manual_seed(8)).to(DEV)
     GUARD, SENT = 64, 12345.0
-    for size_arg, n_models in (("hipt_smaller", 5), ("hipt_smaller", 8), ("hipt_big", 2)):
+    # tensor-core path: hipt_smaller x 1 / 3 / 5, hipt_small x 2, hipt_medium x 1; CUDA-core path: 8 folds, hipt_big
+    for size_arg, n_models in (("hipt_smaller", 1), ("hipt_smaller", 3), ("hipt_smaller", 5), ("hipt_small", 2), ("hipt_medium", 1),
+                               ("hipt_smaller", 8), ("hipt_big", 2)):
         models = [seeded_clam(size_arg, 10 + i).to(DEV) for i in range(n_models)]
         L1 = models[0].attention_net[0].out_features
         D = clam_engine._gate_module(models[0]).attention_c.in_features
