@@ -480,6 +480,25 @@ def test_clam_ragged_bags_and_fold_ensemble(size_arg, folds):
             assert int(r["y_hat"][mi, b]) == int(y_hat)
 
 
+@pytest.mark.parametrize("size_arg,folds", [("hipt_smaller", 5), ("hipt_small", 2), ("hipt_medium", 1)])
+def test_clam_tensor_core_forward_is_bit_identical_run_to_run(size_arg, folds):
+    """The tensor-core score kernel hands tiles between five roles through mbarriers and relies on the tensor pipe executing in
+    issue order (the gate of tile t reads its A operand from the accumulator that GEMM 1 of tile t + 2 overwrites): a protocol
+    error shows up as a run-to-run difference long before it breaks a tolerance.  60 launches over ragged bags, all outputs
+    compared bit for bit with the first."""
+    from hipt_abmil_atec23_b200 import clam_engine
+    lens = [5000, 129, 20000, 777, 128, 3000]
+    offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
+    feats = torch.randn(sum(lens), 192, generator=torch.Generator().manual_seed(11)).to(DEV)
+    models = [seeded_clam(size_arg, 20 + i).to(DEV) for i in range(folds)]
+    first = clam_engine.forward_bags(models, feats, offs, max_bag_len=max(lens))
+    torch.cuda.synchronize()
+    for it in range(60):
+        r = clam_engine.forward_bags(models, feats, offs, max_bag_len=max(lens))
+        for k in ("a_raw", "m", "logits", "y_prob", "y_hat"):
+            assert torch.equal(r[k], first[k]), (size_arg, folds, it, k)
+
+
 def test_clam_forward_writes_stay_inside_their_buffers():
     """Guard words around every output and the workspace of hb_clam_sb_forward (tensor-core and CUDA-core score kernels, ragged
     bags incl. a partial last chunk and an empty bag): nothing outside the documented extents is written."""
