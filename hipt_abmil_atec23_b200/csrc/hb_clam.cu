@@ -565,7 +565,7 @@ __host__ __device__ inline int clam_tc_gate_bytes(int L1) { return 2 * ((L1 + 31
 __host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int D) {
     const int ntot = n_models * L1;
     return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 + static_cast<size_t>(n_models) * clam_tc_gate_bytes(L1) +
-           static_cast<size_t>(n_models) * clam_tc_fold_floats(L1, D) * sizeof(float) + 80 * 8;
+           static_cast<size_t>(n_models) * (clam_tc_fold_floats(L1, D) + 8 * (L1 + 2)) * sizeof(float) + 80 * 8;
 }
 // as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
 __host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
@@ -587,7 +587,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
 // The kernel runs it with all folds and TSTEP = 2: the two epilogue warpgroups alternate tiles.
 struct TcEpi {
     uint64_t *acc_full, *h_full, *g_done, *g_empty;
-    uint32_t tmem_base, acc_stride, t_g, sCu;
+    uint32_t tmem_base, acc_stride, t_g, sCu, s_merge, bar_id;
     int g_slots, n_work, work_cap, total_instances;
     const int32_t* work;
     const int32_t* bag_offsets;
@@ -696,10 +696,9 @@ __device__ __forceinline__ void clam_tc_epilogue(const TcEpi& E, uint32_t t0, in
                 if (valid) E.a_raw[static_cast<size_t>(m) * E.total_instances + start + chunk * TC_M + r] = a;
             }
         }
-        // ---- phase B2: softmax / pooling partials of the WARP's 32 rows for all folds at once (four records per tile and
-        // fold: no barrier, no shared-memory exchange between the warps of the tile — clam_combine_kernel merges
-        // records, it does not care how many).  Every reduction step runs over the folds in its inner loop, so the
-        // shuffles of different folds overlap instead of forming one long dependent chain per fold.
+        // ---- phase B2: softmax / pooling partials of the WARP's 32 rows for all folds at once.  Every reduction step runs over
+        // the folds in its inner loop, so the shuffles of different folds overlap instead of forming one long dependent chain
+        // per fold.
         float mx[NF], e[NF], sum[NF];
 #pragma unroll
         for (int m = 0; m < NF; ++m) mx[m] = valid ? A[m] : -INFINITY;
@@ -736,18 +735,42 @@ __device__ __forceinline__ void clam_tc_epilogue(const TcEpi& E, uint32_t t0, in
                 }
             }
         }
+        // ---- phase B3: the four warps' records of every fold -> ONE record per (tile, fold).  Per-warp records in global
+        // memory made clam_combine_kernel walk four times as many (its time is the latency chain over the longest bag's
+        // records: 30 us of a 200 us hipt_medium forward); merging here costs two named barriers per TILE (not per fold) and
+        // ~30 instructions.
+        constexpr int REC = L1 + 2;
+        const uint32_t sw = E.s_merge + (warp & 3) * NF * REC * 4;           // this warp's [NF][REC] slot
+        named_bar_sync(E.bar_id, 128);                                       // the previous tile's records have been read
 #pragma unroll
         for (int m = 0; m < NF; ++m) {
-            float* out = E.partials + ((static_cast<size_t>(M0 + m) * E.work_cap + wi) * 4 + (warp & 3)) * (L1 + 2);
-            if (lane == 0) *reinterpret_cast<float2*>(out) = make_float2(mx[m], sum[m]);
+            if (lane == 0) { sts_f1(sw + (m * REC) * 4, mx[m]); sts_f1(sw + (m * REC + 1) * 4, sum[m]); }
             if constexpr (L1 == 16) {                        // 16 columns over 32 lanes: pairs share one
                 const float hv = h[m * L1] + __shfl_xor_sync(0xffffffffu, h[m * L1], 1);
-                if ((lane & 1) == 0) out[2 + (lane >> 1)] = hv;
+                if ((lane & 1) == 0) sts_f1(sw + (m * REC + 2 + (lane >> 1)) * 4, hv);
             } else if constexpr (L1 == 32) {
-                out[2 + lane] = h[m * L1];
+                sts_f1(sw + (m * REC + 2 + lane) * 4, h[m * L1]);
             } else {
-                *reinterpret_cast<float2*>(out + 2 + 2 * lane) = make_float2(h[m * L1], h[m * L1 + 1]);
+                sts_f1(sw + (m * REC + 2 + 2 * lane) * 4, h[m * L1]);
+                sts_f1(sw + (m * REC + 3 + 2 * lane) * 4, h[m * L1 + 1]);
             }
+        }
+        named_bar_sync(E.bar_id, 128);
+        for (int idx = (warp & 3) * 32 + lane; idx < NF * L1; idx += 128) {
+            const int m = idx / L1, j = idx - m * L1;
+            float mw[4], gm = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { mw[w] = __uint_as_float(lds_u1(E.s_merge + ((w * NF + m) * REC) * 4)); gm = fmaxf(gm, mw[w]); }
+            float vec = 0.f, tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float wgt = ex2_approx((mw[w] - gm) * 1.4426950408889634f);          // a warp without valid rows: -inf -> 0
+                vec = fmaf(wgt, __uint_as_float(lds_u1(E.s_merge + ((w * NF + m) * REC + 2 + j) * 4)), vec);
+                tot = fmaf(wgt, __uint_as_float(lds_u1(E.s_merge + ((w * NF + m) * REC + 1) * 4)), tot);
+            }
+            float* out = E.partials + (static_cast<size_t>(M0 + m) * E.work_cap + wi) * REC;
+            if (j == 0) *reinterpret_cast<float2*>(out) = make_float2(gm, tot);
+            out[2 + j] = vec;
         }
         g_pos = (g_pos + TSTEP * F - NF) % g_slots;                 // the folds / tiles of the other warpgroup
     }
@@ -776,7 +799,8 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
     uint8_t* sG = sWh + 2 * TC_NSL * ntot * 128;                // [n_models][hi, lo][GKS][L1 rows][128 B]: [Wa ; Wb]
     float* sC = reinterpret_cast<float*>(sG + n_models * clam_tc_gate_bytes(L1));   // [n_models][fold constants]
     constexpr int fold_floats = ((2 * L1 + D + 1) + 3) & ~3;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + n_models * fold_floats);
+    float* sMerge = sC + n_models * fold_floats;                // [2 epilogue warpgroups][4 warps][F][L1 + 2]: partial records of a tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMerge + 2 * 4 * n_models * (L1 + 2));
     uint64_t* x_full = bars;              // [12]
     uint64_t* x_empty = bars + 12;        // [12]  MMA commit
     uint64_t* lo_full = bars + 24;        // [12]  128 lo(X) threads
@@ -961,6 +985,7 @@ clam_scores_tc_kernel(const __grid_constant__ CUtensorMap map_x, const int32_t* 
         E.tmem_base = tmem_base; E.acc_stride = acc_stride; E.t_g = t_g; E.sCu = smem_u32(sC);
         E.g_slots = g_slots; E.n_work = n_work; E.work_cap = work_cap; E.total_instances = total_instances;
         E.work = work; E.bag_offsets = bag_offsets; E.a_raw = a_raw; E.partials = partials;
+        E.s_merge = smem_u32(sMerge + eg * 4 * n_models * (L1 + 2)); E.bar_id = 2 + eg;
         // the two warpgroups alternate tiles.  (Both on every tile, each with half of the folds — clam_tc_epilogue<L1, F, 0, FH, 1>
         // and <L1, F, FH, F, 1> — measured slower: 5 folds 240 vs 256 us, hipt_small 2 folds 176 vs 183 us in the same run; and an L2
         // prefetch of the tiles ahead of the shared-memory ring made every configuration 7-60 % slower.)
@@ -987,8 +1012,8 @@ __global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t*
     const int oi = paired ? bag : mi * n_bags + bag;          // paired (multi-trial): model m pools bag m only, compact outputs
     pdl_wait();                                               // no-op unless launched as a programmatic dependent
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
-    const int n_chunks = ((len + CH - 1) / CH) * recs_per_chunk;   // partial records of the bag (the tensor-core score kernel
-                                                                   // writes one per warp = four per 128-instance chunk)
+    const int n_chunks = ((len + CH - 1) / CH) * recs_per_chunk;   // partial records of the bag (every score kernel writes one
+                                                                   // per chunk today)
     const size_t rec = L1 + 2;
     const float* __restrict__ base = partials + (static_cast<size_t>(mi) * work_cap + prefix[bag]) * recs_per_chunk * rec;
     // records are spread over the threads (a 20,000-instance bag has 628 of them: a serial walk is latency-bound)
@@ -1086,8 +1111,7 @@ static size_t clam_ws_layout(size_t cap, int n_bags, int n_models, int L1, size_
     return o + static_cast<size_t>(n_models) * cap * (L1 + 2) * sizeof(float);
 }
 size_t clam_workspace_bytes(int max_bag_len, int n_bags, int n_models, int L1) {
-    // + 3: the tensor-core path writes four records per 128-instance chunk, 4 ceil(n / 128) <= ceil(n / 32) + 3
-    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + 31) / 32 + 3;
+    const size_t max_chunks = (static_cast<size_t>(max_bag_len) + 31) / 32;
     return clam_ws_layout(static_cast<size_t>(n_bags) * (max_chunks ? max_chunks : 1), n_bags, n_models, L1, nullptr, nullptr);
 }
 
@@ -1139,12 +1163,12 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     if (tc_env < 0) { const char* e = getenv("HB_CLAM_TC"); tc_env = (e && e[0] == '0') ? 0 : 1; }
     if (paired && !clam_is192(L0, L1, D)) return set_error("hb_clam: the paired launch is implemented for the HIPT heads (192-d features)");
     if (tc_env && !dropping && !paired && max_chunks > 0 && total_instances >= TC_M && clam_tc_ok(L0, L1, D, n_models)) {
-        // tensor-core path: 128-instance chunks, four partial records per chunk (one per epilogue warp)
+        // tensor-core path: 128-instance chunks
         size_t cap_tc = static_cast<size_t>(total_instances) / TC_M + n_bags;
         const size_t cap_tc2 = static_cast<size_t>(n_bags) * ((max_bag_len + TC_M - 1) / TC_M);
         if (cap_tc2 < cap_tc) cap_tc = cap_tc2;
         size_t off_work_tc, off_part_tc;
-        const size_t need_tc = clam_ws_layout(4 * cap_tc, n_bags, n_models, L1, &off_work_tc, &off_part_tc);
+        const size_t need_tc = clam_ws_layout(cap_tc, n_bags, n_models, L1, &off_work_tc, &off_part_tc);
         if (workspace_bytes < need_tc) return set_error("hb_clam: workspace %zu < %zu bytes", workspace_bytes, need_tc);
         int32_t* work = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + off_work_tc);
         float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + off_part_tc);
@@ -1203,7 +1227,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
             cfg.attrs = pdl; cfg.numAttrs = 1;
             const int32_t* prefix_c = prefix; const float* partials_c = partials;
             HB_CUDA_OK(cudaLaunchKernelEx(&cfg, clam_combine_kernel, bag_offsets, models, n_bags, L1, C, work_cap, static_cast<int>(TC_M),
-                                          prefix_c, partials_c, m_out, logits, y_prob, y_hat, 0, 4));
+                                          prefix_c, partials_c, m_out, logits, y_prob, y_hat, 0, 1));
             count_launch();
         }
         return 0;

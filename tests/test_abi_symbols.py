@@ -29,9 +29,8 @@ def test_abi_version_and_error_string():
     assert lib.hb_abi_version() == 4
     assert isinstance(lib.hb_last_error(), bytes)
     # [prefix: n_bags + 1 ints][work: 2 ints per (bag, chunk) item][partials: n_models x items x (L1 + 2) floats], items bounded
-    # with the smallest chunk (32 instances) + 3 per bag (the tensor-core score kernel writes four records per 128-instance chunk,
-    # 4 ceil(n / 128) <= ceil(n / 32) + 3); each part 16-byte aligned
-    items = 256 * ((20000 + 31) // 32 + 3)
+    # with the smallest chunk (32 instances); each part 16-byte aligned
+    items = 256 * ((20000 + 31) // 32)
     al = lambda v: (v + 15) & ~15
     assert lib.hb_clam_workspace_bytes(20000, 256, 5, 16) == al(al(257 * 4) + 2 * items * 4) + 5 * items * 18 * 4
 
