@@ -10,9 +10,10 @@
 //
 // Forward = work table -> score kernel -> combine:
 //   clam_work_table_kernel   ragged bags -> flat (bag, chunk) list, so only CTAs with work are launched
-//   clam_scores_tc_kernel    192-d features, L1 = 16 / 32, n_models * L1 <= 80: the first Linear of every fold as ONE tcgen05
-//                            kind::tf32 GEMM per 128-instance tile with hi / lo operand splitting (fp32-level accuracy),
-//                            persistent CTAs, TMA ring; gate, score and chunk softmax partials in the epilogue warpgroups
+//   clam_scores_tc_kernel    192-d features, L1 = 16 / 32 / 64, n_models * L1 <= 80: the first Linear of every fold as ONE
+//                            tcgen05 kind::tf32 GEMM per 128-instance tile and both gate Linears as a second one (A = h1 in
+//                            tensor memory), hi / lo operand splitting (fp32-level accuracy), persistent CTAs, TMA ring;
+//                            activations, score and chunk softmax / pooling partials in the epilogue warpgroups
 //   clam_scores192_kernel    192-d features, any L1 <= 128 (the large heads, tiny inputs, > 5 folds): one CTA per
 //                            64-instance chunk, tile staged once with cp.async and reused by every fold, first Linear and gate
 //                            as register-tiled SGEMMs on packed f32x2 FMAs (packed along K: operands are natural float4 halves)
@@ -533,9 +534,12 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 //               only (Little's law: ring bytes / HBM latency is the bandwidth one SM can pull)
 //   warps 8-11, 12-15  two epilogue warpgroups (even / odd tiles = accumulator 0 / 1), thread = row.
 //               Phase A (all folds): TMEM -> +b1, ReLU -> h1 kept in registers for the pooling partials, h1 and lo(h1) -> TMEM.
-//               Phase B (per fold): G slot -> +bias, tanh * sigmoid, score, chunk softmax partials, sum_i e_i h1_i.
+//               Phase B1 (per fold): G slot -> +bias, tanh * sigmoid on bare ex2 / rcp (operand pre-scaled), score.
+//               Phase B2 (all folds together): softmax partials and sum_i e_i h1_i of the warp's 32 rows.
+//               Phase B3: the four warps' records merged in shared memory -> one partial record per (tile, fold).
 // Registers: 512 threads launch with 128 each; setmaxnreg moves them to 72 (first warpgroup) / 64 (lo) / 184 (epilogue; h1 of up to
-// five folds = 80 registers stays live across both phases): 64,512 of the 65,536 the CTA launched with.
+// five folds = 80 registers stays live across the phases): 64,512 of the 65,536 the CTA launched with.  (setmaxnreg.inc beyond
+// what the CTA's own warpgroups released never completes: the kernel then ends in mbar_wait's trap.)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 512, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
 constexpr int TC_MAX_GSLOTS = 8;
