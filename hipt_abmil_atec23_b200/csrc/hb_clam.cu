@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t*
                                                                   const float* __restrict__ partials,
                                                                   float* __restrict__ m_out, float* __restrict__ logits,
                                                                   float* __restrict__ y_prob, long long* __restrict__ y_hat,
-                                                                  int paired, int recs_per_chunk) {
+                                                                  int paired) {
     extern __shared__ float sM[];                             // [L1] + [C] + [2 CB_THREADS] scratch + [8]
     float* sL = sM + L1;
     float* sP = sL + C;                                       // [2 CB_THREADS] per-group partial sums of M
@@ -1016,10 +1016,9 @@ __global__ void __launch_bounds__(CB_THREADS) clam_combine_kernel(const int32_t*
     const int oi = paired ? bag : mi * n_bags + bag;          // paired (multi-trial): model m pools bag m only, compact outputs
     pdl_wait();                                               // no-op unless launched as a programmatic dependent
     const int len = bag_offsets[bag + 1] - bag_offsets[bag];
-    const int n_chunks = ((len + CH - 1) / CH) * recs_per_chunk;   // partial records of the bag (every score kernel writes one
-                                                                   // per chunk today)
+    const int n_chunks = (len + CH - 1) / CH;                 // partial records of the bag: one per chunk
     const size_t rec = L1 + 2;
-    const float* __restrict__ base = partials + (static_cast<size_t>(mi) * work_cap + prefix[bag]) * recs_per_chunk * rec;
+    const float* __restrict__ base = partials + (static_cast<size_t>(mi) * work_cap + prefix[bag]) * rec;
     // records are spread over the threads (a 20,000-instance bag has 628 of them: a serial walk is latency-bound)
     float gm = -INFINITY;
     for (int c = tid; c < n_chunks; c += CB_THREADS) gm = fmaxf(gm, base[c * rec]);
@@ -1231,7 +1230,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
             cfg.attrs = pdl; cfg.numAttrs = 1;
             const int32_t* prefix_c = prefix; const float* partials_c = partials;
             HB_CUDA_OK(cudaLaunchKernelEx(&cfg, clam_combine_kernel, bag_offsets, models, n_bags, L1, C, work_cap, static_cast<int>(TC_M),
-                                          prefix_c, partials_c, m_out, logits, y_prob, y_hat, 0, 1));
+                                          prefix_c, partials_c, m_out, logits, y_prob, y_hat, 0));
             count_launch();
         }
         return 0;
@@ -1273,7 +1272,7 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
     ProfScope ps2(11, stream);
     clam_combine_kernel<<<grid2, CB_THREADS, (L1 + C + 2 * CB_THREADS + 8) * sizeof(float), stream>>>(bag_offsets, models, n_bags, L1, C,
                                                                                     work_cap, CH, prefix, partials, m_out,
-                                                                                    logits, y_prob, y_hat, paired, 1);
+                                                                                    logits, y_prob, y_hat, paired);
     count_launch();
     HB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -157,6 +157,29 @@ def test_u8_path_equals_fp32_path(hipt):
     assert _min_row_cos(out_im, torch.cat(outs)) > 0.9995
 
 
+def test_vit4k_many_regions_chunked_launches_match_oracle_and_single_calls(hipt):
+    """ViT-4K over 150 region grids in one forward_grid call (the engine walks them in chunks of 64: two full chunks and a partial
+    one) and forward_regions_u8 over 5 small regions: every region equals its own stand-alone call bit for bit, and a sample
+    of regions on both sides of the chunk boundaries matches the fp32 oracle (cosine >= 0.999)."""
+    eng = hipt.model4k._engine(DEV)
+    R, T = 150, 256
+    grid = (torch.randn(R * T, 384, generator=torch.Generator().manual_seed(21)) * 0.5).to(torch.bfloat16)
+    out = eng.forward_grid(grid.to(DEV), R, 16, 16).clone()
+    assert out.shape == (R, 192) and bool(torch.isfinite(out).all())
+    sd4k = {k: v.detach().cpu() for k, v in hipt.model4k.state_dict().items()}
+    for r in (0, 63, 64, 127, 128, 149):
+        single = eng.forward_grid(grid[r * T:(r + 1) * T].contiguous().to(DEV), 1, 16, 16)
+        assert torch.equal(single[0], out[r]), r
+        g = grid[r * T:(r + 1) * T].float().view(1, 16, 16, 384).permute(0, 3, 1, 2).contiguous()
+        with torch.no_grad():
+            ref = O.vit4k_forward(sd4k, g)
+        assert _cos(out[r].cpu(), ref[0]) >= 0.999, r
+    reg = torch.randint(0, 256, (5, 3, 256, 512), dtype=torch.uint8, generator=torch.Generator().manual_seed(22)).to(DEV)
+    all5 = hipt.forward_regions_u8(reg).clone()
+    for i in range(5):
+        assert torch.equal(hipt.forward_regions_u8(reg[i:i + 1])[0], all5[i]), i
+
+
 def test_config1_full_region(gold, hipt):
     g = gold["config1_region"]
     reg = O.synthetic_region_u8(seed=g["pixels_seed"]).to(DEV)
@@ -497,6 +520,28 @@ def test_clam_tensor_core_forward_is_bit_identical_run_to_run(size_arg, folds):
         r = clam_engine.forward_bags(models, feats, offs, max_bag_len=max(lens))
         for k in ("a_raw", "m", "logits", "y_prob", "y_hat"):
             assert torch.equal(r[k], first[k]), (size_arg, folds, it, k)
+
+
+def test_clam_forward_replays_from_a_cuda_graph():
+    """The tensor-core path launches its score and combine kernels as programmatic dependents (cudaLaunchKernelEx); captured
+    into a CUDA graph on a side stream and replayed on new features, it must give what the eager call gives."""
+    from hipt_abmil_atec23_b200 import clam_engine
+    lens = [700, 129, 4000, 128]
+    offs = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
+    gen = torch.Generator().manual_seed(31)
+    feats = torch.randn(sum(lens), 192, generator=gen).to(DEV)
+    models = [seeded_clam("hipt_smaller", 40 + i).to(DEV) for i in range(2)]
+    clam_engine.forward_bags(models, feats, offs, max_bag_len=max(lens))          # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured = clam_engine.forward_bags(models, feats, offs, max_bag_len=max(lens))
+    feats.copy_(torch.randn(sum(lens), 192, generator=gen).to(DEV))               # new inputs, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    eager = clam_engine.forward_bags(models, feats, offs, max_bag_len=max(lens))
+    for k in ("a_raw", "m", "logits", "y_prob", "y_hat"):
+        assert torch.equal(captured[k], eager[k]), k
 
 
 def test_clam_forward_writes_stay_inside_their_buffers():
