@@ -1184,11 +1184,9 @@ int clam_forward_launch(const float* feats, const int32_t* bag_offsets, int n_ba
         }
         CUtensorMap map_x;
         if (encode_tmap_2d(&map_x, TMAP_F32, feats, static_cast<uint64_t>(total_instances), 192, 192 * 4, TC_M, TC_KS)) return -1;
-        const int ntot = n_models * L1;
         const int stages = clam_tc_stages(n_models, L1, D);
         if (stages < 2) return set_error("hb_clam: tensor-core path does not fit shared memory (n_models %d, L1 %d)", n_models, L1);
         const size_t smem = clam_tc_fixed_bytes(n_models, L1, D) + static_cast<size_t>(stages) * TC_SLICE_BYTES;
-        (void)ntot;
         decltype(&clam_scores_tc_kernel<16, 1>) kern = nullptr;
         if (L1 == 16) {
             decltype(kern) k16[5] = {clam_scores_tc_kernel<16, 1>, clam_scores_tc_kernel<16, 2>, clam_scores_tc_kernel<16, 3>,
