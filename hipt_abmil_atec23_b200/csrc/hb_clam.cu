@@ -524,14 +524,13 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 //   epilogue keeps only bias, exp / rcp, the score dot product and the pooling partials.
 // All folds' W1 are stacked along N (N = n_models * L1), so the 98 KB feature tile is read from HBM once AND multiplied once
 // for the whole ensemble.  Persistent CTAs walk the (bag, 128-instance chunk) work table.
-//   warp 0      TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a ring of up to 12 stages
+//   warp 0      TMA producer: X in 6 K-slices [128 rows x 32 fp32] (SWIZZLE_128B) through a ring of up to 6 stages
 //   warp 1      MMA issuer: GEMM 1 of tile t, then the gate of tile t - 1 (its h1 was written while GEMM 1 of tile t ran).
 //               The tensor pipe executes in issue order, so GEMM 1 of tile t + 2 may overwrite the accumulator the gate of
 //               tile t read its A operand from without any further hand-shake.
 //   warps 2-3   idle (they only complete the first warpgroup, which gives its registers away)
 //   warps 4-7   lo(X): one thread per row reads the slice from shared memory and writes lo(x) into TENSOR memory (32 columns
-//               per stage of a second, shorter ring): term 3 is an A-from-TMEM MMA, so the shared-memory ring holds features
-//               only (Little's law: ring bytes / HBM latency is the bandwidth one SM can pull)
+//               per stage of a second, shorter ring): term 3 is an A-from-TMEM MMA, so the shared-memory ring holds features only
 //   warps 8-11, 12-15  two epilogue warpgroups (even / odd tiles = accumulator 0 / 1), thread = row.
 //               Phase A (all folds): TMEM -> +b1, ReLU -> h1 kept in registers for the pooling partials, h1 and lo(h1) -> TMEM.
 //               Phase B1 (per fold): G slot -> +bias, tanh * sigmoid on bare ex2 / rcp (operand pre-scaled), score.
@@ -541,7 +540,13 @@ __global__ void __launch_bounds__(256) clam_scores192_kernel(const float* __rest
 // five folds = 80 registers stays live across the phases): 64,512 of the 65,536 the CTA launched with.  (setmaxnreg.inc beyond
 // what the CTA's own warpgroups released never completes: the kernel then ends in mbar_wait's trap.)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 512, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = 12;
+// Ring depth, measured on one hipt_smaller fold (tools/gpu_ring_depth.sh): 4 stages 128.6 us, 5: 119.8, 6: 116.5, 8: 117.3,
+// 12: 119.4 — the kernel is not starved for bytes in flight from five stages (80 KB per SM) on, which is what is left beside the
+// weights of five folds; more than six stages only deepen the DRAM queues.
+#ifndef HB_CLAM_MAX_STAGES
+#define HB_CLAM_MAX_STAGES 6
+#endif
+constexpr int TC_M = 128, TC_KS = 32, TC_NSL = 6, TC_THREADS = 512, TC_SLICE_BYTES = TC_M * 128, TC_MAX_STAGES = HB_CLAM_MAX_STAGES;
 constexpr int TC_MAX_GSLOTS = 8;
 constexpr float TC_SCALE_A = 2.8853900817779268f, TC_SCALE_B = -1.4426950408889634f;    // 2 log2(e), -log2(e)
 // TMEM: two accumulators of acc_stride columns (2 ntot — the X W1 and X lo(W1) halves, later h1 and lo(h1) — rounded up to 32),
@@ -571,7 +576,7 @@ __host__ __device__ inline size_t clam_tc_fixed_bytes(int n_models, int L1, int 
     return 1024 + 2 * static_cast<size_t>(TC_NSL) * ntot * 128 + static_cast<size_t>(n_models) * clam_tc_gate_bytes(L1) +
            static_cast<size_t>(n_models) * (clam_tc_fold_floats(L1, D) + 8 * (L1 + 2)) * sizeof(float) + 80 * 8;
 }
-// as many ring stages as fit (HBM latency x bandwidth needs ~50 KB in flight per SM; a stage carries 16 KB of features)
+// as many ring stages as fit, up to TC_MAX_STAGES (a stage carries 16 KB of features)
 __host__ __device__ inline int clam_tc_stages(int n_models, int L1, int D) {
     const long long room = 232448LL - static_cast<long long>(clam_tc_fixed_bytes(n_models, L1, D));
     const int st = static_cast<int>(room / TC_SLICE_BYTES);
