@@ -594,10 +594,11 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
 
 // Epilogue of clam_scores_tc_kernel for the folds [M0, M1) of every TSTEP-th tile starting at tile t0 (thread = tile row).
 // The kernel runs it with all folds and TSTEP = 2: the two epilogue warpgroups alternate tiles.
-// Known limit at five folds: h1 of every fold lives in registers, so every loop over folds unrolls — 2,400 straight-line
-// instructions (39 KB) per tile, and ncu's source page attributes 49 % of the epilogue warps' samples to stall_no_inst
-// (instruction fetch; none at one fold).  A version with rolled fold loops (h1 re-read from tensor memory) measured slower
-// (208 vs 188 us): tools/patches/README.md.
+// History at five folds: while this epilogue was 2,400 straight-line instructions (39 KB; h1 of every fold lives in registers, so
+// every loop over folds unrolls) ncu attributed 49 % of the epilogue warps' samples to stall_no_inst; the bare ex2 / rcp gate
+// brought it to 1,700 and the kernel from 225 to 189 us, a version with rolled fold loops (h1 re-read from tensor memory)
+// measured 208 us (tools/patches/README.md).  In the final kernel the epilogue WAITS for 46 % of its samples: the slice feed
+// paces five folds (profiles/r02ad_clam_trace.txt).
 struct TcEpi {
     uint64_t *acc_full, *h_full, *g_done, *g_empty;
     uint32_t tmem_base, acc_stride, t_g, sCu, s_merge, bar_id;
