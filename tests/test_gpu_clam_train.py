@@ -187,9 +187,12 @@ def test_multi_trial_step_equals_independent_train_steps(size_arg, n_classes, dr
             if not p.requires_grad:
                 continue
             err = (p - q).abs().max().item()
-            if name.endswith("attention_c.bias"):
+            if name.endswith("attention_c.bias") or (dropout >= 0.5 and name.endswith("attention_c.weight")):
                 # dL/d(bc) = sum_i dA_i is zero analytically (softmax is shift-invariant): its computed value is rounding
-                # noise of the atomics' order, and Adam turns noise into steps of +-lr — in the reference as well
+                # noise of the atomics' order, and Adam turns noise into steps of +-lr — in the reference as well.  At high
+                # dropout dL/d(Wc) = sum_i dA_i (a b)_i is the same kind of quantity (reference gradient ~1e-8 against ~1e-5 of
+                # fp32 noise, see test_training_step_with_dropout_matches_the_reference_module): the atomics' order then decides
+                # the sign Adam sees, which made this comparison fail once in ~10 runs
                 assert err <= 2 * steps * lrs[t] + 1e-7, (t, name, err)
                 continue
             assert err <= 1e-5 * max(1.0, q.abs().max().item()), (t, name, err)
