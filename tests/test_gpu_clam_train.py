@@ -180,8 +180,11 @@ def test_multi_trial_step_equals_independent_train_steps(size_arg, n_classes, dr
         loss = batch.step(bags[s], labels[s])
         assert _lib.launch_count() - n0 == 6
         got = loss.cpu().tolist()
+        # high dropout: once the atomics' order has flipped the sign Adam sees for the noise-level Wc gradient (below), the two
+        # runs' Wc differ by up to 2 lr and the LATER losses by that times the score's sensitivity
+        loss_tol = 1e-5 if (dropout < 0.5 or s == 0) else 2e-3
         for t in range(T):
-            assert abs(got[t] - ref_losses[s][t]) <= 1e-5 * max(1.0, abs(ref_losses[s][t])), (s, t, got[t], ref_losses[s][t])
+            assert abs(got[t] - ref_losses[s][t]) <= loss_tol * max(1.0, abs(ref_losses[s][t])), (s, t, got[t], ref_losses[s][t])
     for t in range(T):
         for (name, p), q in zip(models[t].named_parameters(), ref_models[t].parameters()):
             if not p.requires_grad:
@@ -195,6 +198,6 @@ def test_multi_trial_step_equals_independent_train_steps(size_arg, n_classes, dr
                 # the sign Adam sees, which made this comparison fail once in ~10 runs
                 assert err <= 2 * steps * lrs[t] + 1e-7, (t, name, err)
                 continue
-            assert err <= 1e-5 * max(1.0, q.abs().max().item()), (t, name, err)
+            assert err <= (1e-5 if dropout < 0.5 else 1e-4) * max(1.0, q.abs().max().item()), (t, name, err)
     # the trials really diverged from their common initialisation pattern (different data, lr, seeds)
     assert not torch.equal(models[0].classifiers.weight, models[1].classifiers.weight)
